@@ -1,0 +1,329 @@
+/*
+ * rayhs_b200.h — C ABI of the B200-native ray-casting path of RayHs.
+ *
+ * This header is the drop-in boundary.  The reference (oilandrust/rayhs) has no
+ * FFI; the seam is `rayTrace :: Rendering -> Image` (src/RayHs.hs:161-166),
+ * called from `main` (src/RayHs.hs:229-231).  A Haskell host binds these entry
+ * points with `foreign import ccall safe` after flattening
+ * its Scene (src/Scene.hs:8-10) at `buildGeometry` / `buildMaterial`
+ * (src/Descriptors.hs:50-55, src/MaterialDescriptors.hs:34-45).
+ *
+ * Plain C only: pointers, sizes, POD structs.  No torch / C++ types.
+ * All floating point data is IEEE double, like the reference (src/Vec.hs:29-31).
+ * Every array pointer handed in must be 32-byte aligned when it is a node,
+ * triangle or shading-record array (the library copies; the caller keeps
+ * ownership of all host memory).
+ *
+ * Return convention: 0 = RH_OK, negative = error class; text through
+ * rh_last_error() (thread-local).  The library never exits or aborts.
+ */
+#ifndef RAYHS_B200_H
+#define RAYHS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RH_ABI_VERSION 1
+
+/* ---- error classes -------------------------------------------------- */
+enum {
+  RH_OK = 0,
+  RH_ERR_ARG = -1,      /* bad argument / malformed scene             */
+  RH_ERR_CUDA = -2,     /* CUDA runtime failure (no GPU, launch, ...)  */
+  RH_ERR_NCCL = -3,     /* NCCL failure                                */
+  RH_ERR_OOM = -4,      /* host or device allocation failed            */
+  RH_ERR_STATE = -5,    /* rh_init not called / called twice           */
+  RH_ERR_IO = -6,       /* front end: file missing / parse error       */
+  RH_ERR_OVERFLOW = -7  /* internal ray queue overflow (not recoverable by chunk split) */
+};
+
+/* ---- kinds ---------------------------------------------------------- */
+/* Geometry.hs:62-63 (Plane | Sphere), KDTree.hs:59-61 (mesh tree)       */
+enum { RH_OBJ_PLANE = 0, RH_OBJ_SPHERE = 1, RH_OBJ_MESH = 2 };
+/* Material.hs:13-20                                                      */
+enum {
+  RH_MAT_MIRROR = 0, RH_MAT_DIFFUSE = 1, RH_MAT_PLASTIC = 2, RH_MAT_EMMIT = 3,
+  RH_MAT_TRANSPARENT = 4, RH_MAT_SHOWNORMAL = 5, RH_MAT_SHOWUV = 6
+};
+/* ColorMap.hs:11-16                                                      */
+enum { RH_CMAP_FLAT = 0, RH_CMAP_CHECKER = 1, RH_CMAP_TEXTURE = 2 };
+/* Light.hs:8-10                                                          */
+enum { RH_LIGHT_DIRECTIONAL = 0, RH_LIGHT_POINT = 1 };
+/* Projection.hs:10-15                                                    */
+enum { RH_PROJ_ORTHOGRAPHIC = 0, RH_PROJ_PERSPECTIVE = 1 };
+/* sample-offset formats for rh_render (RayHs.hs:173-188)                 */
+enum {
+  RH_OFFSETS_NONE = 0,     /* 1 sample at the integer pixel coordinate (generatePixels, Image.hs:34-36) */
+  RH_OFFSETS_F64 = 1,      /* double[w*h][spp][2], pixel-major, values already (x-0.5, y-0.5)          */
+  RH_OFFSETS_F32 = 2,      /* float [w*h][spp][2], same order                                          */
+  RH_OFFSETS_TILED_F64 = 3 /* double[tile*tile][spp][2], tile period given in rh_render_opts (declared deviation) */
+};
+
+#define RH_NO_NODE 0xFFFFFFFFu /* KDTree.hs:61 `Empty` */
+
+/* ---- tables shared by the raw and the flat scene -------------------- */
+
+/* Material.hs:13-20 + ColorMap.hs:11-16 folded into one 96-byte record.
+ * Emmit: ce in color1.  Flat: colour in color1.  Checker: color1/color2/size
+ * (ColorMap.hs:21-24: color1 where the product is negative).             */
+typedef struct rh_material {
+  int32_t kind;       /* RH_MAT_*                                        */
+  int32_t cmap_kind;  /* RH_CMAP_* (diffuse / plastic only)              */
+  double ior;
+  double color1[3];
+  double color2[3];
+  double size;
+  int32_t texture;    /* index into textures[] or -1                      */
+  int32_t pad_;
+  double pad2_[2];
+} rh_material;
+
+/* Light.hs:8-10.  vec = direction (un-normalised, Light.hs:14) or position. */
+typedef struct rh_light {
+  int32_t kind;  /* RH_LIGHT_* */
+  int32_t pad_;
+  double vec[3];
+  double color[3];
+  double radius;
+} rh_light;
+
+/* Bitmap.hs:13-15.  Texels are RGB triples of double (= byte/255, Bitmap.hs:28-29),
+ * row-major, first PPM row first; `offset` counts texels into the shared texel array. */
+typedef struct rh_texture {
+  int32_t w, h;
+  uint64_t offset;
+} rh_texture;
+
+/* Projection.hs:17-20 + 10-15 */
+typedef struct rh_camera {
+  double position[3];
+  double target[3];
+  double up[3];
+  int32_t projection; /* RH_PROJ_* */
+  int32_t pad_;
+  double fovy;        /* perspective only                       */
+  double proj_width;  /* parsed but unused by the reference     */
+  double proj_height; /* (Projection.hs:34)                     */
+  double near_;
+} rh_camera;
+
+/* ---- raw scene: what the front end holds BEFORE the tree build ------ */
+/* One entry per Scene.shapes element (Scene.hs:8), in scene order.
+ * plane : a = point, b = normal, c = tangent        (Geometry.hs:62)
+ * sphere: a = center, b[0] = radius                 (Geometry.hs:63)
+ * mesh  : vertices after Mesh.transform (Mesh.hs:89-101); positions/normals
+ *         are double[n_verts][3], uvs double[n_verts][2], indices uint32[n_indices]
+ *         grouped in threes (Mesh.hs:105-109).                                    */
+typedef struct rh_raw_object {
+  int32_t kind;
+  int32_t material;
+  double a[3], b[3], c[3];
+  uint32_t n_verts;
+  uint32_t n_indices;
+  const double* positions;
+  const double* normals;
+  const double* uvs;
+  const uint32_t* indices;
+} rh_raw_object;
+
+typedef struct rh_raw_scene {
+  uint32_t n_objects;
+  uint32_t n_materials;
+  uint32_t n_lights;
+  uint32_t n_textures;
+  const rh_raw_object* objects;
+  const rh_material* materials;
+  const rh_light* lights;
+  const rh_texture* textures;
+  const double* texels; /* RGB triples */
+  uint64_t n_texels;
+} rh_raw_scene;
+
+/* ---- flat scene: what crosses into the CUDA library ----------------- */
+
+/* 64-byte tree node (KDTree.hs:59-61).  Inner: left/right = node indices or
+ * RH_NO_NODE for `Empty`.  Leaf: left = first triangle, right = count.
+ * leaf_index numbers the leaves of one mesh in left-to-right DFS order; it
+ * carries the reference's tie rule (KDTree.hs:109-115) across any traversal order. */
+typedef struct rh_node {
+  double lo[3];
+  double hi[3];
+  uint32_t left;
+  uint32_t right;
+  uint32_t leaf_index;
+  uint32_t is_leaf;
+} rh_node;
+
+/* 80-byte intersection record: p0, e1 = p1 - p0, e2 = p2 - p0 (Mesh.hs:70-71),
+ * stored in leaf order.  tri_id = index in the mesh's `triangles` list (Mesh.hs:105-109). */
+typedef struct rh_tri {
+  double p0[3];
+  double e1[3];
+  double e2[3];
+  uint32_t tri_id;
+  uint32_t pad_;
+} rh_tri;
+
+/* 128-byte shading record, same order as rh_tri; read only for the winning hit
+ * (Mesh.hs:81-82). */
+typedef struct rh_tri_shade {
+  double n0[3], n1[3], n2[3];
+  double uv0[2], uv1[2], uv2[2];
+  double pad_;
+} rh_tri_shade;
+
+typedef struct rh_object {
+  int32_t kind;
+  int32_t material;
+  double a[3], b[3], c[3];
+  uint32_t root;     /* mesh: root node index or RH_NO_NODE */
+  uint32_t n_leaves; /* mesh: number of leaves              */
+  uint32_t depth;    /* mesh: tree depth (root = 0)         */
+  uint32_t pad_;
+} rh_object;
+
+typedef struct rh_scene_desc {
+  uint32_t n_objects, n_materials, n_lights, n_textures;
+  uint32_t n_nodes, n_tris;
+  const rh_object* objects;
+  const rh_material* materials;
+  const rh_light* lights;
+  const rh_texture* textures;
+  const double* texels;
+  uint64_t n_texels;
+  const rh_node* nodes;          /* 32-byte aligned */
+  const rh_tri* tris;            /* 32-byte aligned */
+  const rh_tri_shade* tri_shade; /* 32-byte aligned */
+} rh_scene_desc;
+
+/* ---- render call ---------------------------------------------------- */
+
+typedef struct rh_render_opts {
+  int32_t width, height;  /* RayHs.hs:43-44 */
+  int32_t max_depth;      /* RayHs.hs:45    */
+  int32_t spp;            /* >= 1; RayHs.hs:175 hard-codes 64 */
+  int32_t offset_mode;    /* RH_OFFSETS_*   */
+  int32_t offset_tile;    /* period in pixels for RH_OFFSETS_TILED_F64 */
+  const void* offsets;    /* host pointer, layout per offset_mode; may be NULL for RH_OFFSETS_NONE */
+  /* image partition: this call renders the rows whose band
+   * (row / band_height) satisfies band % shard_count == shard_index.      */
+  int32_t shard_index;    /* 0 .. shard_count-1 */
+  int32_t shard_count;    /* >= 1               */
+  int32_t band_height;    /* rows per band; 0 = library default */
+  int32_t chunk_samples;  /* wavefront chunk size in pixel samples; 0 = default */
+  int32_t flags;          /* RH_FLAG_* */
+  int32_t pad_;
+} rh_render_opts;
+
+enum {
+  RH_FLAG_HIT_IDS = 1,      /* also produce primary hit ids (see rh_render) */
+  RH_FLAG_DEVICE_OUT = 2,   /* rgb_out / hit_ids_out are DEVICE pointers on the current device */
+  RH_FLAG_DEVICE_OFFSETS = 4, /* offsets is a DEVICE pointer (already uploaded, full-frame layout) */
+  RH_FLAG_COUNT = 8,         /* run the instrumented kernels: fills box_tests .. texel_fetches (slower) */
+  RH_FLAG_PROFILE = 16       /* bracket every launch with CUDA events: fills ms_trace / ms_shadow / ms_resolve */
+};
+
+/* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
+ * shadowIntersection (RayHs.hs:74) call. */
+typedef struct rh_stats {
+  uint64_t rays_primary;
+  uint64_t rays_reflect;  /* specular children, RayHs.hs:99-104                */
+  uint64_t rays_probe;    /* interior probe of Transparent, RayHs.hs:140        */
+  uint64_t rays_exit;     /* transmitted child, RayHs.hs:143                    */
+  uint64_t rays_shadow;   /* RayHs.hs:93                                        */
+  uint64_t shadow_tasks;  /* shaded Diffuse/Plastic hits (each folds over all lights) */
+  uint64_t box_tests;     /* RH_FLAG_COUNT only: child boxes tested              */
+  uint64_t tri_tests;     /* RH_FLAG_COUNT only: triangle records tested         */
+  uint64_t prim_tests;    /* RH_FLAG_COUNT only: sphere / plane tests            */
+  uint64_t shade_fetches; /* RH_FLAG_COUNT only: winning triangle shading records read */
+  uint64_t texel_fetches; /* RH_FLAG_COUNT only                                  */
+  uint64_t node_visits;   /* RH_FLAG_COUNT only: 128-byte wide-node records read */
+  uint64_t upload_bytes;  /* sample-offset bytes copied host -> device           */
+  double ms_total;        /* CUDA events around the whole call's device work (uploads and read-back included) */
+  double ms_trace;        /* RH_FLAG_PROFILE only: closest-hit + shade kernels   */
+  double ms_shadow;       /* RH_FLAG_PROFILE only: shadow any-hit kernels        */
+  double ms_resolve;      /* RH_FLAG_PROFILE only: average + quantise            */
+  uint32_t trace_launches;
+  uint32_t shadow_launches;
+  uint32_t kernel_launches;
+  uint32_t chunks;
+  uint32_t negative_channels; /* pixels with a channel whose toIntC is < 0 before the RGB8 clamp (App. A-Q2) */
+  uint32_t queue_factor;      /* ray-queue capacity / chunk samples that was needed */
+} rh_stats;
+
+typedef struct rh_scene rh_scene; /* opaque; owns device copies */
+
+/* Library / device bring-up.  device < 0: use the current CUDA device. */
+int rh_init(int device);
+void rh_shutdown(void);
+const char* rh_last_error(void);
+int rh_abi_version(void);
+/* Number of kernels this library has launched since rh_init (for gpu_launches). */
+uint64_t rh_launch_count(void);
+
+/* Upload a flat scene.  Copies everything; host arrays may be freed after return. */
+int rh_scene_create(const rh_scene_desc* desc, rh_scene** out);
+void rh_scene_destroy(rh_scene* scene);
+
+/* Replaces `rayTrace` (RayHs.hs:161-166) / `distributedRayTrace` (RayHs.hs:190-195).
+ * rgb_out: RGB8, row-major.  For shard_count == 1 it is width*height*3 bytes.
+ * For shard_count > 1 it is the COMPACT band buffer of this shard:
+ * rh_shard_rows(...) rows of width*3 bytes (assemble with rh_assemble_bands or
+ * an all-gather + rh_deinterleave_bands).
+ * hit_ids_out (RH_FLAG_HIT_IDS): int32[rows*width*spp][2] = (object index,
+ * triangle id | -1), (-1,-1) for a miss; may be NULL otherwise.
+ * Quantisation = toIntC (Image.hs:54-55) clamped into 0..255.               */
+int rh_render(const rh_scene* scene, const rh_camera* camera, const rh_render_opts* opts,
+              uint8_t* rgb_out, int32_t* hit_ids_out, rh_stats* stats);
+
+/* Rows owned by one shard (equal for all shards: bands are padded). */
+int rh_shard_rows(int height, int shard_count, int band_height);
+int rh_default_band_height(int height, int shard_count);
+
+/* Device-side de-interleave after an all-gather: gathered = [shard][rows_per_shard][w][3]
+ * (device), out = [h][w][3] (device).  Runs on the library stream and synchronises. */
+int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int width, int height,
+                          int shard_count, int band_height);
+
+/* Micro-benchmarks used by bench.py for the roofline denominators:
+ * random 32-byte-aligned 64-byte gathers over `bytes` of device memory; returns GB/s. */
+int rh_bench_gather(uint64_t bytes, int iters, double* gbs_out);
+/* Dependent DFMA chains on all SMs; returns TFLOP/s (2 flop per DFMA). */
+int rh_bench_dfma(int iters, double* tflops_out);
+
+/* ---- host-side front end (C++; stands in for the Haskell one) ------- */
+/* KDTree.hs:68-90 build + flattening into the arrays above.              */
+typedef struct rh_flat_scene rh_flat_scene; /* opaque; owns host arrays */
+int rh_flatten(const rh_raw_scene* raw, rh_flat_scene** out);
+const rh_scene_desc* rh_flat_desc(const rh_flat_scene* flat);
+void rh_flat_destroy(rh_flat_scene* flat);
+
+/* JSON.hs:22-141 + Descriptors.hs:39-55 + Mesh.hs:118-221 + Bitmap.hs:20-37. */
+typedef struct rh_loaded rh_loaded; /* opaque; owns a raw scene + camera + size */
+int rh_load_json(const char* json_path, const char* base_dir, rh_loaded** out);
+/* binary pack of a loaded scene (fixtures for boxes without the data files) */
+int rh_load_pack(const char* pack_path, rh_loaded** out);
+int rh_save_pack(const rh_loaded* loaded, const char* pack_path);
+/* n_tris random triangles + n_spheres spheres + floor, dragon.json camera/lights */
+int rh_make_synthetic(uint64_t n_tris, uint32_t n_spheres, uint64_t seed, rh_loaded** out);
+const rh_raw_scene* rh_loaded_raw(const rh_loaded* l);
+const rh_camera* rh_loaded_camera(const rh_loaded* l);
+void rh_loaded_size(const rh_loaded* l, int32_t* width, int32_t* height, int32_t* max_depth);
+void rh_loaded_destroy(rh_loaded* l);
+
+/* Sample offsets (RayHs.hs:173-188 shape; SplitMix64 stream):
+ * fills out[n_pixels][spp][2] with (x-0.5, y-0.5), x drawn before y. */
+void rh_sample_offsets_f64(uint64_t seed, uint64_t n_pixels, int spp, double* out);
+void rh_sample_offsets_f32(uint64_t seed, uint64_t n_pixels, int spp, float* out);
+
+/* P3 writer byte-identical to Image.hs:60-75. */
+int rh_write_ppm(const char* path, const uint8_t* rgb, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYHS_B200_H */

@@ -1,0 +1,11 @@
+"""rayhs_b200 — B200-native (sm_100a CUDA) ray-casting path of RayHs behind a C ABI.
+
+See DESIGN.md.  The Python layer mirrors the reference's interface for this path
+(`Rendering`, `rayTrace`, `distributedRayTrace`, `writePPM`); the kernels live in
+csrc/kernels.cu and are reached through librayhs_b200.so (include/rayhs_b200.h).
+"""
+from .host import (Image, Rendering, Scene, assemble_bands, buildRendering, distributedRayTrace, init, main, rayTrace,
+                   render, render_device, renderingFromScene, sample_offsets, shutdown, writePPM)
+
+__all__ = ["Image", "Rendering", "Scene", "assemble_bands", "buildRendering", "distributedRayTrace", "init", "main",
+           "rayTrace", "render", "render_device", "renderingFromScene", "sample_offsets", "shutdown", "writePPM"]

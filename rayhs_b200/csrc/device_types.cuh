@@ -1,0 +1,141 @@
+// device_types.cuh — HBM layouts and kernel parameter blocks of the ray-casting path.
+// See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+
+#include "../../include/rayhs_b200.h"
+
+namespace rhd {
+
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;    // KDTree.hs:61 `Empty`
+constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 31 bits = triangle count
+constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
+constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
+constexpr int kStack = 104;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82)
+constexpr int kSmemNodes = 224;             // top wide nodes staged in shared memory (28 KB)
+constexpr int kSmemObjects = 64;            // object / material tables staged when the scene has at most this many
+constexpr int kSmemLights = 16;
+constexpr int kBlock = 128;
+
+// 128-byte "wide" node: one record per inner tree node holding BOTH child boxes, so a
+// visit is one 128-byte line (4 sectors) and every box is still tested exactly once,
+// as in KDTree.hs:96-107 (box test at every Node and Leaf).  A synthetic super-root per
+// mesh carries the root's own box in slot 0.  Wide nodes are stored in level order over
+// all meshes, so the first kSmemNodes records are the top levels of every tree.
+struct __align__(16) WideNode {
+  double box[12];     // child0 lo.xyz hi.xyz, child1 lo.xyz hi.xyz
+  uint32_t child[2];  // kEmpty | kLeafBit|count | wide-node index
+  uint32_t first[2];  // leaf child: first triangle slot.  Slots follow left-to-right leaf order, so
+                      // `first` also carries the reference's tie rule (KDTree.hs:109-115).
+  uint32_t pad_[4];
+};
+static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
+
+// Object table entry (device copy of rh_object with the wide super-root index).
+struct __align__(16) DObject {
+  double a[3], b[3], c[3];
+  int32_t kind;
+  int32_t material;
+  uint32_t root;  // wide-node index of the mesh's super-root or kEmpty
+  uint32_t is_emitter;
+};
+static_assert(sizeof(DObject) == 96, "DObject must be 96 bytes");
+
+struct SceneView {
+  const WideNode* wide;
+  const rh_tri* tris;
+  const rh_tri_shade* shade;
+  const DObject* objects;
+  const rh_material* materials;
+  const rh_light* lights;
+  const rh_texture* textures;
+  const double* texels;
+  uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
+  uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
+  uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables
+};
+
+// Camera with everything `rayFromPixel` recomputes per pixel hoisted to the host
+// (Projection.hs:22-46, Mat.hs:89-93): the values are identical, they are just computed once.
+struct CameraParams {
+  double m[9];  // lookAt matrix rows (Mat.hs:83-93)
+  double pos[3];
+  double w, h, half_w, half_h, apw, aph, f;
+  int32_t projection;
+  int32_t pad_;
+};
+
+// Per-chunk control block in device memory (zeroed before each chunk).
+struct ChunkCtl {
+  uint32_t ray_count[kMaxPasses + 2];     // entries in the ray queue consumed by pass k
+  uint32_t shadow_count[kMaxPasses + 2];  // shadow tasks produced by pass k
+  uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors
+  uint32_t shadow_cursor[kMaxPasses + 2];
+  uint32_t overflow;
+  uint32_t pad_[3];
+};
+
+// Frame-level counters (zeroed per rh_render).
+struct FrameCounters {
+  unsigned long long rays_reflect, rays_probe, rays_exit, shadow_tasks;
+  unsigned long long box_tests, tri_tests, prim_tests, shade_fetches, texel_fetches;
+  unsigned long long negative_channels;
+  unsigned long long node_visits;
+  unsigned long long pad_;
+};
+
+// SoA-of-16-byte planes so that a warp's compacted pushes are fully coalesced.
+// Ray queue: 4 planes (ox,oy) (oz,dx) (dy,dz) (weight, bits).
+// bits = sample | depth << 32 | kind << 40 | material << 48.
+struct RayQueue {
+  double2* plane;  // plane k at plane + k*capacity
+  uint32_t capacity;
+};
+// Shadow queue: 5 planes (px,py) (pz,nx) (ny,nz) (cr,cg) (cb,w) + sample ids (bit 31 = ambient term).
+struct ShadowQueue {
+  double2* plane;
+  uint32_t* sample;
+  uint32_t capacity;
+};
+
+enum { kRayNormal = 0, kRayProbe = 1 };
+enum { kOffIndexLocal = 0, kOffIndexGlobal = 1 };
+
+struct ChunkParams {
+  uint32_t first_row;     // first local (shard-compact) row of the chunk
+  uint32_t n_rows;        // rows in the chunk
+  uint32_t n_samples;     // n_rows * width * spp
+  uint32_t spp;
+  uint32_t width, height;
+  uint32_t shard_index, shard_count, band_height;
+  int32_t max_depth;
+  int32_t offset_mode;    // RH_OFFSETS_*
+  int32_t offset_index;   // kOffIndex*: per-pixel offsets indexed by chunk-local or full-frame pixel
+  int32_t offset_tile;
+  int32_t pass;           // wavefront pass (0 = primary)
+  const void* offsets;    // device
+  double* accum;          // 3 planes of accum_stride (r,g,b), chunk-local sample order
+  uint32_t accum_stride;
+  uint32_t pad_;
+  int2* hit_ids;          // shard-compact [pixel][spp] (object, tri) or null
+  uint8_t* rgb;           // shard-compact framebuffer
+  ChunkCtl* ctl;
+  FrameCounters* counters;
+  RayQueue q_in, q_out;
+  ShadowQueue q_shadow;
+};
+
+// Launchers (kernels.cu).  `count` selects the instrumented instantiation (box/tri counters).
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
+void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream);
+void launch_resolve(const ChunkParams& P, void* stream);
+void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
+                         void* stream);
+int trace_blocks_per_sm(bool count);
+int shadow_blocks_per_sm(bool count);
+// micro-benchmarks
+void launch_gather_bench(const double2* buf, uint64_t n_records, uint32_t loads_per_thread, double2* sink, int grid, int block,
+                         void* stream);
+void launch_dfma_bench(double* sink, int iters, int grid, int block, void* stream);
+
+}  // namespace rhd

@@ -1,0 +1,948 @@
+// kernels.cu — sm_100a kernels of the RayHs ray-casting path.
+//
+//   trace_kernel   K1/K4: camera-ray generation (pass 0) or queued secondary rays (pass >= 1),
+//                  closest hit through the object list + wide-BVH traversal, shading, and
+//                  warp-ballot compaction of the shadow tasks and child rays it emits (K2, K5).
+//   shadow_kernel  K3: per shaded hit, fold over the lights with an any-hit query each.
+//   resolve_kernel K6: average the samples of a pixel, toIntC, coalesced RGB8 store.
+//   deinterleave   K7: band re-assembly after the all-gather.
+//
+// All arithmetic is IEEE double in the reference's operation order and this file is compiled
+// with -fmad=false (GHC emits no fused multiply-adds), so every value the reference defines
+// (t, u, v, hit point, normal, colour) is computed bit-identically; only atan/acos (sphere
+// uv, Geometry.hs:96) go through CUDA's libm instead of the host's.  No tensor cores: the
+// path is branchy gather-bound traversal.  Each device function cites the reference lines
+// it restates; nothing here is shared with oracle/.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.cuh"
+
+namespace rhd {
+namespace {
+
+constexpr double kEps = 0.000001;              // Geometry.hs:31-32
+constexpr double kPiInv = 0.3183098861837907;  // Math.hs:11-12 (1 / pi in double)
+constexpr double kPruneSlack = 1.0000001;      // boxes are skipped only when tmin exceeds the best t by > 1e-7 relative
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------ GHC Ord Double
+__device__ __forceinline__ double hs_max(double x, double y) { return (x <= y) ? y : x; }
+__device__ __forceinline__ double hs_min(double x, double y) { return (x <= y) ? x : y; }
+
+// ------------------------------------------------------------------ Vec.hs
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ V3 mk(double x, double y, double z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }  // Vec.hs:36
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }  // Vec.hs:40
+__device__ __forceinline__ V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }                              // Vec.hs:42
+__device__ __forceinline__ V3 mul(double l, V3 a) { return mk(l * a.x, l * a.y, l * a.z); }            // Vec.hs:69
+__device__ __forceinline__ V3 cmul(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }        // Color.hs:23
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }        // Vec.hs:105
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {                                                       // Vec.hs:108-110
+  return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double sqrLen(V3 v) { return dot(v, v); }                           // Vec.hs:114
+__device__ __forceinline__ double sqrDist(V3 v, V3 w) { return sqrLen(v - w); }                // Vec.hs:118
+__device__ __forceinline__ V3 normalize(V3 v) { return mul(1 / sqrt(sqrLen(v)), v); }          // Vec.hs:126
+__device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - mul(2 * dot(v, n), n); }        // Vec.hs:130
+// Vec.hs:132-140
+__device__ __forceinline__ bool refract(V3 i, V3 n, double n1, double n2, V3& out) {
+  double n1n2 = n1 / n2;
+  double cos0 = -(dot(i, n));
+  double sin20 = n1n2 * n1n2 * (1 - cos0 * cos0);
+  if (sin20 > 1) return false;
+  double coeff = n1n2 * cos0 - sqrt(1.0 - sin20);
+  out = mul(n1n2, i) + mul(coeff, n);
+  return true;
+}
+__device__ __forceinline__ V3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+struct Ray {
+  V3 o, d;
+};
+__device__ __forceinline__ V3 rayAt(const Ray& r, double t) { return r.o + mul(t, r.d); }  // Geometry.hs:29
+__device__ __forceinline__ Ray rayEps(V3 p, V3 n) { return Ray{p + mul(kEps, n), n}; }      // Geometry.hs:36
+
+// ------------------------------------------------------------------ shared-memory staging
+struct SmemTables {
+  WideNode nodes[kSmemNodes];
+  DObject objects[kSmemObjects];
+  rh_material materials[kSmemObjects];
+  rh_light lights[kSmemLights];
+};
+static_assert(sizeof(rh_material) == 96 && sizeof(rh_light) == 64, "table record sizes");
+static_assert(sizeof(SmemTables) <= 48 * 1024, "static shared memory budget");
+
+__device__ __forceinline__ void copy16(void* dst, const void* src, uint32_t bytes) {
+  uint4* d = (uint4*)dst;
+  const uint4* s = (const uint4*)src;
+  for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+struct Ctx {
+  const SceneView* S;
+  const SmemTables* sm;
+  const DObject* objects;
+  const rh_material* materials;
+  const rh_light* lights;
+};
+
+__device__ __forceinline__ void stage_tables(SmemTables& sm, const SceneView& S, Ctx& cx) {
+  copy16(sm.nodes, S.wide, S.n_smem_nodes * (uint32_t)sizeof(WideNode));
+  if (S.tables_in_smem) {
+    copy16(sm.objects, S.objects, S.n_objects * (uint32_t)sizeof(DObject));
+    copy16(sm.materials, S.materials, S.n_materials * (uint32_t)sizeof(rh_material));
+    copy16(sm.lights, S.lights, S.n_lights * (uint32_t)sizeof(rh_light));
+  }
+  __syncthreads();
+  cx.S = &S;
+  cx.sm = &sm;
+  cx.objects = S.tables_in_smem ? sm.objects : S.objects;
+  cx.materials = S.tables_in_smem ? sm.materials : S.materials;
+  cx.lights = S.tables_in_smem ? sm.lights : S.lights;
+}
+
+// ------------------------------------------------------------------ counters
+template <bool COUNT>
+struct Cnt {
+  unsigned long long box, tri, prim, nodes, shade, texel;
+  __device__ __forceinline__ void zero() { box = tri = prim = nodes = shade = texel = 0; }
+};
+template <>
+struct Cnt<false> {
+  __device__ __forceinline__ void zero() {}
+};
+#define RH_CNT(field, n) \
+  if constexpr (COUNT) cnt.field += (n)
+
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc) {
+  if constexpr (COUNT) {
+    unsigned long long* src[6] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel};
+    unsigned long long* dst[6] = {&fc->box_tests, &fc->tri_tests, &fc->prim_tests, &fc->node_visits, &fc->shade_fetches,
+                                  &fc->texel_fetches};
+    for (int k = 0; k < 6; k++) {
+      unsigned long long v = *src[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst[k], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ KDTree.hs:39-56 rayInterBox
+// `inv` holds 1/dx, 1/dy, 1/dz, which the reference recomputes at every box (same values).
+__device__ __forceinline__ bool slab(const Ray& r, const V3& inv, double lx, double ly, double lz, double hx, double hy,
+                                     double hz, double& tmin) {
+  double t1 = inv.x * (lx - r.o.x);
+  double t2 = inv.x * (hx - r.o.x);
+  double t3 = inv.y * (ly - r.o.y);
+  double t4 = inv.y * (hy - r.o.y);
+  double t5 = inv.z * (lz - r.o.z);
+  double t6 = inv.z * (hz - r.o.z);
+  tmin = hs_max(hs_max(hs_min(t1, t2), hs_min(t3, t4)), hs_min(t5, t6));
+  double tmax = hs_min(hs_min(hs_max(t1, t2), hs_max(t3, t4)), hs_max(t5, t6));
+  return !(tmax < 0 || tmin > tmax);
+}
+
+// Closest-hit candidate: key (t asc, leaf desc, position-in-leaf asc) inside one mesh
+// (KDTree.hs:109-115 right child wins ties; Geometry.hs:54-57 first minimum inside a leaf),
+// strict `<` across objects (RayHs.hs:67-71 first object wins ties).
+struct Closest {
+  double t, u, v;
+  uint32_t slot, leaf_first;
+  int obj, cur_obj;
+  __device__ __forceinline__ bool offer(const Ray&, double tt, double uu, double vv, uint32_t s, uint32_t lf, double& bound) {
+    if (tt < t || (tt == t && obj == cur_obj && lf > leaf_first)) {
+      t = tt;
+      u = uu;
+      v = vv;
+      slot = s;
+      leaf_first = lf;
+      obj = cur_obj;
+      bound = tt * kPruneSlack;
+    }
+    return false;
+  }
+};
+
+// Shadow candidate (RayHs.hs:74-87): any hit in front of the light ends the query.
+struct AnyHit {
+  V3 lpos;
+  double dl2;  // sqrDist origin lightPos
+  bool directional;
+  __device__ __forceinline__ bool in_front(const Ray& r, double tt) const {
+    if (directional) return true;
+    return dl2 > sqrDist(r.o, rayAt(r, tt));
+  }
+  __device__ __forceinline__ bool offer(const Ray& r, double tt, double, double, uint32_t, uint32_t, double&) const {
+    return in_front(r, tt);
+  }
+};
+
+__device__ __forceinline__ const double2* node_ptr(const Ctx& cx, uint32_t idx) {
+  return idx < cx.S->n_smem_nodes ? (const double2*)&cx.sm->nodes[idx] : (const double2*)&cx.S->wide[idx];
+}
+
+// KDTree.hs:96-107 rayInter, ordered and pruned.  Every box the reference would test on the
+// way to a triangle is tested here with the same arithmetic; subtrees are skipped only when
+// their entry distance exceeds `bound` (the best t so far, or the light distance).
+// Returns true when the candidate sink asked to stop (any-hit).
+template <bool COUNT, class Sink>
+__device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const V3& inv, double& bound, Sink& sink,
+                                         uint2* stack, Cnt<COUNT>& cnt) {
+  int sp = 0;
+  uint32_t ref = root, first = 0;
+  const rh_tri* tris = cx.S->tris;
+  for (;;) {
+    if (!(ref & kLeafBit)) {
+      const double2* np = node_ptr(cx, ref);
+      const double2 b0 = np[0], b1 = np[1], b2 = np[2], b3 = np[3], b4 = np[4], b5 = np[5];
+      const uint4 cw = *(const uint4*)(np + 6);  // child0, child1, first0, first1
+      RH_CNT(nodes, 1);
+      bool h0 = false, h1 = false;
+      double tm0 = 0, tm1 = 0;
+      if (cw.x != kEmpty) {
+        RH_CNT(box, 1);
+        h0 = slab(r, inv, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, tm0) && !(tm0 > bound);
+      }
+      if (cw.y != kEmpty) {
+        RH_CNT(box, 1);
+        h1 = slab(r, inv, b3.x, b3.y, b4.x, b4.y, b5.x, b5.y, tm1) && !(tm1 > bound);
+      }
+      if (h0 && h1) {
+        if (tm1 < tm0) {
+          stack[sp++] = make_uint2(cw.x, cw.z);
+          ref = cw.y;
+          first = cw.w;
+        } else {
+          stack[sp++] = make_uint2(cw.y, cw.w);
+          ref = cw.x;
+          first = cw.z;
+        }
+        continue;
+      }
+      if (h0) {
+        ref = cw.x;
+        first = cw.z;
+        continue;
+      }
+      if (h1) {
+        ref = cw.y;
+        first = cw.w;
+        continue;
+      }
+    } else {
+      const uint32_t count = ref & ~kLeafBit;
+      for (uint32_t k = 0; k < count; k++) {
+        const uint32_t slot = first + k;
+        const double2* tp = (const double2*)(tris + slot);
+        const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+        const double e2z = __ldg((const double*)(tp + 4));
+        RH_CNT(tri, 1);
+        // Mesh.hs:59-82 triangleIntersection
+        const V3 p0 = mk(a.x, a.y, b.x), e1 = mk(b.y, c.x, c.y), e2 = mk(d.x, d.y, e2z);
+        const V3 p = cross(r.d, e2);
+        const double det = dot(e1, p);
+        const double idet = 1 / det;
+        const V3 t0 = r.o - p0;
+        const double u = idet * dot(t0, p);
+        const V3 q = cross(t0, e1);
+        const double v = idet * dot(r.d, q);
+        const double t = idet * dot(e2, q);
+        if (fabs(det) < kEps || u < 0 || u > 1 || v < 0 || (u + v) > 1 || t < kEps) continue;
+        if (sink.offer(r, t, u, v, slot, first, bound)) return true;
+      }
+    }
+    if (sp == 0) return false;
+    const uint2 e = stack[--sp];
+    ref = e.x;
+    first = e.y;
+  }
+}
+
+// Geometry.hs:70-79 (plane) — returns the hit time only; position/normal/uv are rebuilt by the shader.
+__device__ __forceinline__ bool plane_time(const Ray& r, const DObject& ob, double& time) {
+  const V3 p = ld3(ob.a), n = ld3(ob.b);
+  const double dDotn = dot(r.d, n);
+  time = dot(n, p - r.o) / dDotn;
+  return fabs(dDotn) > 0 && time > 0;
+}
+// Geometry.hs:81-95 (sphere): first positive root.
+__device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, double& time) {
+  const V3 ct = ld3(ob.a);
+  const double rad = ob.b[0];
+  const double a = dot(r.d, r.d);
+  const double b = 2.0 * dot(r.d, r.o - ct);
+  const double c = sqrLen(r.o - ct) - rad * rad;
+  const double delta = b * b - 4.0 * a * c;
+  if (delta < 0.0) return false;
+  const double t0 = 0.5 * ((-b) - sqrt(delta)) / a;
+  if (t0 > 0) {
+    time = t0;
+    return true;
+  }
+  const double t1 = 0.5 * ((-b) + sqrt(delta)) / a;
+  if (t1 > 0) {
+    time = t1;
+    return true;
+  }
+  return false;
+}
+
+// RayHs.hs:58-71 closestIntersection over the object list.
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, Closest& best, uint2* stack, Cnt<COUNT>& cnt) {
+  const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
+  best.t = __longlong_as_double(0x7ff0000000000000LL);
+  best.u = best.v = 0;
+  best.slot = best.leaf_first = 0;
+  best.obj = -1;
+  const uint32_t n = cx.S->n_objects;
+  for (uint32_t i = 0; i < n; i++) {
+    const DObject& ob = cx.objects[i];
+    const int kind = ob.kind;
+    if (kind == RH_OBJ_MESH) {
+      const uint32_t root = ob.root;
+      if (root == kEmpty) continue;
+      best.cur_obj = (int)i;
+      double bound = best.t * kPruneSlack;
+      traverse<COUNT>(cx, root, r, inv, bound, best, stack, cnt);
+    } else {
+      double time;
+      RH_CNT(prim, 1);
+      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, time) : sphere_time(r, ob, time);
+      if (hit && time < best.t) {
+        best.t = time;
+        best.obj = (int)i;
+      }
+    }
+  }
+}
+
+// RayHs.hs:74-87 shadowIntersection: true when some non-emitter object has a hit in front of the light.
+template <bool COUNT>
+__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, const rh_light& L, uint2* stack, Cnt<COUNT>& cnt) {
+  const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
+  AnyHit sink;
+  sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
+  sink.lpos = ld3(L.vec);
+  sink.dl2 = sink.directional ? 0.0 : sqrDist(r.o, sink.lpos);
+  // hits farther than the light cannot be in front of it; 1e-6 relative slack covers |d| != 1 rounding
+  const double far = sink.directional ? __longlong_as_double(0x7ff0000000000000LL)
+                                      : sqrt(sink.dl2) * 1.000001 / sqrt(dot(r.d, r.d));
+  const uint32_t n = cx.S->n_objects;
+  for (uint32_t i = 0; i < n; i++) {
+    const DObject& ob = cx.objects[i];
+    if (ob.is_emitter) continue;  // isOccluder, RayHs.hs:81-82
+    const int kind = ob.kind;
+    if (kind == RH_OBJ_MESH) {
+      const uint32_t root = ob.root;
+      if (root == kEmpty) continue;
+      double bound = far;
+      if (traverse<COUNT>(cx, root, r, inv, bound, sink, stack, cnt)) return true;
+    } else {
+      double time;
+      RH_CNT(prim, 1);
+      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, time) : sphere_time(r, ob, time);
+      if (hit && sink.in_front(r, time)) return true;
+    }
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------ Material.hs / Light.hs / ColorMap.hs
+__device__ __forceinline__ double r0f(double n1, double n2) {  // Material.hs:22-24
+  const double q = (n1 - n2) / (n1 + n2);
+  return q * q;
+}
+__device__ __forceinline__ double fresnel(double ior, double cos0) {  // Material.hs:26-29
+  const double r = r0f(1.0, ior);
+  const double x = 1 - cos0;
+  const double x2 = x * x;
+  const double x5 = (x2 * x2) * x;  // GHC (^): square-and-multiply
+  return r + (1 - r) * x5;
+}
+
+// Data.Fixed.mod' n d = n - fromInteger (floor (toRational n / toRational d)) * d   (exact rational floor)
+__device__ __noinline__ double hs_mod1(double n, double d) {
+  if (!isfinite(n) || !isfinite(d) || d == 0) return __longlong_as_double(0x7ff8000000000000LL);
+  double q = floor(n / d);
+  if (fabs(q) >= 4503599627370496.0) return n - q * d;
+  if (d > 0) {
+    while (__fma_rn(-q, d, n) < 0) q -= 1;
+    while (__fma_rn(-(q + 1), d, n) >= 0) q += 1;
+  } else {
+    while (__fma_rn(-q, d, n) > 0) q -= 1;
+    while (__fma_rn(-(q + 1), d, n) <= 0) q += 1;
+  }
+  return n - q * d;
+}
+__device__ __forceinline__ long long hs_mod_int(long long a, long long m) {
+  long long r = a % m;
+  return (r != 0 && ((r < 0) != (m < 0))) ? r + m : r;
+}
+
+// ColorMap.hs:18-58
+template <bool COUNT>
+__device__ __noinline__ V3 color_at(const Ctx& cx, const rh_material& m, double u, double v, Cnt<COUNT>& cnt) {
+  const V3 c1 = ld3(m.color1);
+  if (m.cmap_kind == RH_CMAP_FLAT) return c1;
+  if (m.cmap_kind == RH_CMAP_CHECKER) {
+    const double s = m.size;
+    return ((hs_mod1(u, s) - (0.5 * s)) * (hs_mod1(v, s) - (0.5 * s)) < 0) ? c1 : ld3(m.color2);
+  }
+  const rh_texture tx = cx.S->textures[m.texture];
+  const double* px = cx.S->texels + 3 * tx.offset;
+  const double uu = hs_mod1(u, 1) * (double)tx.w;  // toPixel / repeatUV
+  const double vv = hs_mod1(v, 1) * (double)tx.h;
+  const long long ui = (long long)rint(uu);  // round: half to even
+  const long long vi = (long long)rint(vv);
+  const long long x0 = hs_mod_int(ui - 1, tx.w), x1 = hs_mod_int(ui, tx.w);
+  const long long y0 = hs_mod_int(vi - 1, tx.h), y1 = hs_mod_int(vi, tx.h);
+  const double lx = uu - (double)(ui - 1) - 0.5;
+  const double ly = vv - (double)(vi - 1) - 0.5;
+  RH_CNT(texel, 4);
+  const V3 c0 = ld3(px + 3 * (x0 + (long long)tx.w * y0));  // Bitmap.hs:17-18
+  const V3 c1t = ld3(px + 3 * (x1 + (long long)tx.w * y0));
+  const V3 c2 = ld3(px + 3 * (x0 + (long long)tx.w * y1));
+  const V3 c3 = ld3(px + 3 * (x1 + (long long)tx.w * y1));
+  const V3 cx0 = mul(lx, c1t) + mul(1 - lx, c0);  // bilinearInterp, ColorMap.hs:41-45
+  const V3 cx1 = mul(lx, c3) + mul(1 - lx, c2);
+  return mul(ly, cx1) + mul(1 - ly, cx0);
+}
+
+// ------------------------------------------------------------------ queues (warp-aggregated compaction)
+__device__ __forceinline__ uint64_t pack_bits(uint32_t sample, int depth, int kind, uint32_t mat) {
+  return (uint64_t)sample | ((uint64_t)(depth & 0xff) << 32) | ((uint64_t)(kind & 0xff) << 40) | ((uint64_t)(mat & 0xffff) << 48);
+}
+
+__device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint64_t bits, const RayQueue& q, uint32_t* counter,
+                                         uint32_t* overflow, uint32_t lane) {
+  const unsigned m = __ballot_sync(kFull, has);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (has) {
+    const uint32_t idx = base + __popc(m & ((1u << lane) - 1));
+    if (idx < q.capacity) {
+      const size_t cap = q.capacity;
+      q.plane[idx] = make_double2(r.o.x, r.o.y);
+      q.plane[cap + idx] = make_double2(r.o.z, r.d.x);
+      q.plane[2 * cap + idx] = make_double2(r.d.y, r.d.z);
+      q.plane[3 * cap + idx] = make_double2(w, __longlong_as_double((long long)bits));
+    } else {
+      *overflow = 1;
+    }
+  }
+}
+
+struct ShadowTask {
+  V3 p, n, cd;
+  double w;
+  uint32_t sample;  // bit 31: add the 0.2*cd ambient term (Diffuse, RayHs.hs:111-114)
+};
+
+__device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const ShadowQueue& q, uint32_t* counter,
+                                            uint32_t* overflow, uint32_t lane) {
+  const unsigned m = __ballot_sync(kFull, has);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (has) {
+    const uint32_t idx = base + __popc(m & ((1u << lane) - 1));
+    if (idx < q.capacity) {
+      const size_t cap = q.capacity;
+      q.plane[idx] = make_double2(t.p.x, t.p.y);
+      q.plane[cap + idx] = make_double2(t.p.z, t.n.x);
+      q.plane[2 * cap + idx] = make_double2(t.n.y, t.n.z);
+      q.plane[3 * cap + idx] = make_double2(t.cd.x, t.cd.y);
+      q.plane[4 * cap + idx] = make_double2(t.cd.z, t.w);
+      q.sample[idx] = t.sample;
+    } else {
+      *overflow = 1;
+    }
+  }
+}
+
+__device__ __forceinline__ void accumulate(const ChunkParams& P, uint32_t sample, double w, V3 c) {
+  double* a = P.accum + sample;
+  atomicAdd(a, w * c.x);
+  atomicAdd(a + P.accum_stride, w * c.y);
+  atomicAdd(a + 2 * (size_t)P.accum_stride, w * c.z);
+}
+
+// What one shaded hit emits.  Kept in registers until the warp reconverges, then pushed
+// with one ballot + one atomic per queue (north_star requirement 3).
+struct Emit {
+  bool has_a, has_b, has_s;
+  Ray ra, rb;
+  double wa, wb;
+  uint64_t bits_a, bits_b;
+  ShadowTask s;
+};
+
+// Rebuild the Hit (Geometry.hs:39) of the winning primitive and run `irradiance`
+// (RayHs.hs:107-147) with the recursion unrolled into weighted child rays: every combine in
+// the reference is `mul scalar colour` + add, so a child carries the scalar product `w`.
+template <bool COUNT>
+__device__ __forceinline__ void shade(const Ctx& cx, const ChunkParams& P, const Ray& r, const Closest& best, double w,
+                                      int depth, int kind, uint32_t probe_mat, uint32_t sample, Emit& em, Cnt<COUNT>& cnt,
+                                      FrameCounters* fc_unused) {
+  const DObject& ob = cx.objects[best.obj];
+  V3 p, n;
+  double tu = 0, tv = 0;
+  const rh_material& mat = cx.materials[ob.material];
+  const int mkind = mat.kind;
+  const bool need_uv = (kind == kRayNormal) && (mkind == RH_MAT_SHOWUV || ((mkind == RH_MAT_DIFFUSE || mkind == RH_MAT_PLASTIC) &&
+                                                                            mat.cmap_kind != RH_CMAP_FLAT));
+  if (ob.kind == RH_OBJ_MESH) {
+    p = rayAt(r, best.t);
+    const double* sh = (const double*)(cx.S->shade + best.slot);
+    RH_CNT(shade, 1);
+    const double wu = best.u, wv = best.v, ww = 1 - best.u - best.v;
+    // barycentricInterp u n1 v n2 (1-u-v) n0 = mul a p + mul b q + mul c r   (Mesh.hs:57, 81)
+    n = mul(wu, ld3(sh + 3)) + mul(wv, ld3(sh + 6)) + mul(ww, ld3(sh));
+    if (need_uv) {
+      tu = wu * sh[11] + wv * sh[13] + ww * sh[9];
+      tv = wu * sh[12] + wv * sh[14] + ww * sh[10];
+    }
+  } else if (ob.kind == RH_OBJ_PLANE) {  // Geometry.hs:70-79
+    p = rayAt(r, best.t);
+    n = ld3(ob.b);
+    if (need_uv) {
+      const V3 tg = ld3(ob.c);
+      const V3 b = cross(tg, n);
+      const V3 rel = p - ld3(ob.a);
+      tu = dot(tg, rel);
+      tv = dot(b, rel);
+    }
+  } else {  // Geometry.hs:83-96
+    p = rayAt(r, best.t);
+    n = normalize(p - ld3(ob.a));
+    if (need_uv) {
+      tu = kPiInv * atan(n.z / n.x);
+      tv = kPiInv * acos(n.y);
+    }
+  }
+
+  if (kind == kRayProbe) {
+    // interior probe of a Transparent hit (RayHs.hs:140-143): leave through the far interface
+    const double ior = cx.materials[probe_mat].ior;
+    V3 outDir;
+    if (refract(r.d, neg(n), ior, 1.0, outDir)) {
+      em.has_a = true;
+      em.ra = rayEps(p, outDir);
+      em.wa = w;
+      em.bits_a = pack_bits(sample, depth, kRayNormal, 0) | (1ull << 63);  // bit 63: counts as an exit ray
+    }
+    return;
+  }
+
+  const V3 v = r.d;
+  switch (mkind) {
+    case RH_MAT_DIFFUSE:
+    case RH_MAT_PLASTIC: {
+      em.has_s = true;
+      em.s.p = p;
+      em.s.n = n;
+      em.s.cd = color_at<COUNT>(cx, mat, tu, tv, cnt);
+      em.s.w = w;
+      em.s.sample = sample | (mkind == RH_MAT_DIFFUSE ? 0x80000000u : 0u);
+      if (mkind == RH_MAT_DIFFUSE) break;
+    }
+    // fallthrough: Plastic adds the Fresnel-weighted mirror term
+    case RH_MAT_MIRROR: {
+      if (depth < P.max_depth) {  // specular, RayHs.hs:99-104
+        const V3 rd = reflect(v, n);
+        const double f = fresnel(mat.ior, dot(n, neg(v)));
+        em.has_a = true;
+        em.ra = rayEps(p, rd);
+        em.wa = w * (f * dot(rd, n));
+        em.bits_a = pack_bits(sample, depth + 1, kRayNormal, 0);
+      }
+      break;
+    }
+    case RH_MAT_EMMIT:
+      accumulate(P, sample, w, ld3(mat.color1));
+      break;
+    case RH_MAT_TRANSPARENT: {
+      if (depth != P.max_depth) {  // RayHs.hs:136-139
+        V3 refDir;
+        if (refract(v, n, 1.0, mat.ior, refDir)) {
+          em.has_b = true;
+          em.rb = rayEps(p, refDir);
+          em.wb = w * (1 - r0f(mat.ior, 1.0));
+          em.bits_b = pack_bits(sample, depth + 1, kRayProbe, (uint32_t)ob.material);
+        }
+      }
+      if (depth < P.max_depth) {
+        const V3 rd = reflect(v, n);
+        const double f = fresnel(mat.ior, dot(n, neg(v)));
+        em.has_a = true;
+        em.ra = rayEps(p, rd);
+        em.wa = w * (f * dot(rd, n));
+        em.bits_a = pack_bits(sample, depth + 1, kRayNormal, 0);
+      }
+      break;
+    }
+    case RH_MAT_SHOWNORMAL:
+      accumulate(P, sample, w, n);
+      break;
+    case RH_MAT_SHOWUV:
+      accumulate(P, sample, w, mk(tu, tv, 0));
+      break;
+    default:
+      break;
+  }
+}
+
+// Image row of a shard-compact row: band b = row / band_height goes to shard b mod G.
+__device__ __forceinline__ uint32_t global_row(const ChunkParams& P, uint32_t local_row) {
+  const uint32_t lb = local_row / P.band_height, rib = local_row % P.band_height;
+  return (lb * P.shard_count + P.shard_index) * P.band_height + rib;
+}
+
+// Projection.hs:22-39 rayFromPixel with the per-frame constants hoisted into CameraParams.
+__device__ __forceinline__ Ray camera_ray(const CameraParams& cam, double px, double py) {
+  const double vx = cam.apw * (px - cam.half_w) / cam.w;
+  const double vy = cam.aph * ((-py) + cam.half_h) / cam.h;
+  V3 o, d;
+  if (cam.projection == RH_PROJ_ORTHOGRAPHIC) {
+    o = mk(vx, vy, 0);
+    d = mk(0, 0, 1);
+  } else {
+    d = normalize(mk(vx, vy, cam.f));
+    o = mk(0, 0, 0);
+  }
+  Ray r;
+  r.o = o + ld3(cam.pos);
+  r.d = mk(cam.m[0] * d.x + cam.m[1] * d.y + cam.m[2] * d.z, cam.m[3] * d.x + cam.m[4] * d.y + cam.m[5] * d.z,
+           cam.m[6] * d.x + cam.m[7] * d.y + cam.m[8] * d.z);  // Mat.hs:40-44
+  return r;
+}
+
+// ------------------------------------------------------------------ K1/K2/K4/K5
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ SceneView S,
+                                                       const __grid_constant__ CameraParams cam,
+                                                       const __grid_constant__ ChunkParams P) {
+  __shared__ SmemTables sm;
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  uint2 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  const uint32_t lane = threadIdx.x & 31;
+  const bool primary = (P.pass == 0);
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = primary ? P.n_samples : min(ctl->ray_count[P.pass], P.q_in.capacity);
+  unsigned long long n_reflect = 0, n_probe = 0, n_exit = 0;
+
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->trace_cursor[P.pass], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n_items) break;
+    const uint32_t item = base + lane;
+    bool valid = item < n_items;
+    Ray r;
+    r.o = r.d = mk(0, 0, 1);
+    double w = 1;
+    uint32_t sample = item, probe_mat = 0;
+    int depth = 0, kind = kRayNormal;
+    if (valid) {
+      if (primary) {
+        const uint32_t lp = item / P.spp, s = item - lp * P.spp;
+        const uint32_t lrow = lp / P.width, col = lp - lrow * P.width;
+        const uint32_t grow = global_row(P, P.first_row + lrow);
+        if (grow >= P.height) {
+          valid = false;  // padding row of the last band
+        } else {
+          double ox = 0, oy = 0;
+          if (P.offset_mode != RH_OFFSETS_NONE) {
+            size_t idx;
+            if (P.offset_mode == RH_OFFSETS_TILED_F64)
+              idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
+            else if (P.offset_index == kOffIndexGlobal)
+              idx = ((size_t)grow * P.width + col) * P.spp + s;
+            else
+              idx = item;
+            if (P.offset_mode == RH_OFFSETS_F32) {
+              const float2 o2 = __ldg((const float2*)P.offsets + idx);
+              ox = (double)o2.x;
+              oy = (double)o2.y;
+            } else {
+              const double2 o2 = __ldg((const double2*)P.offsets + idx);
+              ox = o2.x;
+              oy = o2.y;
+            }
+          }
+          // pixelCoord (Image.hs:31-32) + sample offset (RayHs.hs:178-181)
+          r = camera_ray(cam, (double)col + ox, (double)grow + oy);
+        }
+      } else {
+        const size_t cap = P.q_in.capacity;
+        const double2 a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item],
+                      d = P.q_in.plane[3 * cap + item];
+        r.o = mk(a.x, a.y, b.x);
+        r.d = mk(b.y, c.x, c.y);
+        w = d.x;
+        const uint64_t bits = (uint64_t)__double_as_longlong(d.y);
+        sample = (uint32_t)bits;
+        depth = (int)((bits >> 32) & 0xff);
+        kind = (int)((bits >> 40) & 0xff);
+        probe_mat = (uint32_t)((bits >> 48) & 0x7fff);
+      }
+    }
+
+    Closest best;
+    best.obj = -1;
+    if (valid) closest_hit<COUNT>(cx, r, best, stack, cnt);
+
+    if (primary && valid && P.hit_ids) {
+      int tri = -1;
+      if (best.obj >= 0 && cx.objects[best.obj].kind == RH_OBJ_MESH) tri = (int)S.tris[best.slot].tri_id;
+      P.hit_ids[(size_t)P.first_row * P.width * P.spp + item] = make_int2(best.obj, tri);
+    }
+
+    Emit em;
+    em.has_a = em.has_b = em.has_s = false;
+    if (valid && best.obj >= 0) shade<COUNT>(cx, P, r, best, w, depth, kind, probe_mat, sample, em, cnt, P.counters);
+
+    // RayHs.hs:149-154: a miss contributes black — nothing to do.
+    if (em.has_a) {
+      if (em.bits_a >> 63) n_exit++; else n_reflect++;
+    }
+    if (em.has_b) n_probe++;
+    push_ray(em.has_a, em.ra, em.wa, em.bits_a & ~(1ull << 63), P.q_out, &ctl->ray_count[P.pass + 1], &ctl->overflow, lane);
+    push_ray(em.has_b, em.rb, em.wb, em.bits_b, P.q_out, &ctl->ray_count[P.pass + 1], &ctl->overflow, lane);
+    push_shadow(em.has_s, em.s, P.q_shadow, &ctl->shadow_count[P.pass], &ctl->overflow, lane);
+  }
+
+  // ray-class statistics (one ray per closestIntersection call)
+  for (int o = 16; o > 0; o >>= 1) {
+    n_reflect += __shfl_xor_sync(kFull, n_reflect, o);
+    n_probe += __shfl_xor_sync(kFull, n_probe, o);
+    n_exit += __shfl_xor_sync(kFull, n_exit, o);
+  }
+  if (lane == 0) {
+    if (n_reflect) atomicAdd(&P.counters->rays_reflect, n_reflect);
+    if (n_probe) atomicAdd(&P.counters->rays_probe, n_probe);
+    if (n_exit) atomicAdd(&P.counters->rays_exit, n_exit);
+  }
+  flush_counters<COUNT>(cnt, P.counters);
+}
+
+// ------------------------------------------------------------------ K3: accumDiffuse (RayHs.hs:89-97)
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ SceneView S,
+                                                        const __grid_constant__ ChunkParams P) {
+  __shared__ SmemTables sm;
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  uint2 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  const uint32_t lane = threadIdx.x & 31;
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
+  const size_t cap = P.q_shadow.capacity;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->shadow_cursor[P.pass], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n_items) break;
+    const uint32_t item = base + lane;
+    if (item >= n_items) continue;
+    const double2 a = P.q_shadow.plane[item], b = P.q_shadow.plane[cap + item], c = P.q_shadow.plane[2 * cap + item],
+                  d = P.q_shadow.plane[3 * cap + item], e = P.q_shadow.plane[4 * cap + item];
+    const uint32_t sbits = P.q_shadow.sample[item];
+    const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+    const double w = e.y;
+    V3 acc = mk(0, 0, 0);  // foldl ... black lts
+    for (uint32_t li = 0; li < S.n_lights; li++) {
+      const rh_light& L = cx.lights[li];
+      V3 ld, lc;
+      if (L.kind == RH_LIGHT_DIRECTIONAL) {  // Light.hs:14
+        ld = ld3(L.vec);
+        lc = ld3(L.color);
+      } else {  // Light.hs:15-17
+        const V3 lp = ld3(L.vec);
+        const double dd = sqrt(sqrDist(lp, p));
+        const double s = 1.0 + dd / L.radius;
+        const double falloff = 1.0 / (s * s);
+        ld = mul(1 / dd, lp - p);
+        lc = mul(falloff, ld3(L.color));
+      }
+      const bool shadowed = occluded<COUNT>(cx, rayEps(p, ld), L, stack, cnt);
+      if (!shadowed) acc = acc + mul(hs_max(dot(ld, n), 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+    }
+    const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
+    accumulate(P, sbits & 0x7fffffffu, w, total);
+  }
+  flush_counters<COUNT>(cnt, P.counters);
+}
+
+// ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
+__device__ __forceinline__ int to_int_c(double c, bool& negative) {
+  const double v = 255 * hs_min(c, 1);  // hs_min NaN 1 = 1
+  if (v < 0) {
+    if (v <= -1) negative = true;
+    return 0;
+  }
+  return min((int)v, 255);  // truncate toward zero, then the RGB8 clamp
+}
+
+__global__ void __launch_bounds__(kBlock) resolve_kernel(const __grid_constant__ ChunkParams P) {
+  __shared__ __align__(16) uint8_t bytes[kBlock * 3];
+  const uint32_t n_pixels = P.n_rows * P.width;
+  const uint32_t lp = blockIdx.x * kBlock + threadIdx.x;
+  bool negative = false;
+  if (lp < n_pixels) {
+    uint8_t r8 = 0, g8 = 0, b8 = 0;
+    const uint32_t lrow = lp / P.width;
+    if (global_row(P, P.first_row + lrow) < P.height) {
+      double sr = 0, sg = 0, sb = 0;  // foldl (+) black
+      const double* a = P.accum + (size_t)lp * P.spp;
+      for (uint32_t s = 0; s < P.spp; s++) {
+        sr = sr + a[s];
+        sg = sg + a[P.accum_stride + s];
+        sb = sb + a[2 * (size_t)P.accum_stride + s];
+      }
+      const double inv = 1.0 / (double)P.spp;
+      r8 = (uint8_t)to_int_c(inv * sr, negative);
+      g8 = (uint8_t)to_int_c(inv * sg, negative);
+      b8 = (uint8_t)to_int_c(inv * sb, negative);
+    }
+    bytes[3 * threadIdx.x] = r8;
+    bytes[3 * threadIdx.x + 1] = g8;
+    bytes[3 * threadIdx.x + 2] = b8;
+  }
+  const unsigned neg = __ballot_sync(kFull, negative);
+  if ((threadIdx.x & 31) == 0 && neg) atomicAdd(&P.counters->negative_channels, (unsigned long long)__popc(neg));
+  __syncthreads();
+  // coalesced store: the block's 384 bytes leave as 32-bit words when the destination allows it
+  uint8_t* dst = P.rgb + ((size_t)P.first_row * P.width + (size_t)blockIdx.x * kBlock) * 3;
+  const uint32_t n_here = min((uint32_t)kBlock, n_pixels - blockIdx.x * kBlock) * 3;
+  if ((((uintptr_t)dst) & 3) == 0) {
+    const uint32_t words = n_here / 4;
+    if (threadIdx.x < words) ((uint32_t*)dst)[threadIdx.x] = ((const uint32_t*)bytes)[threadIdx.x];
+    const uint32_t tail = words * 4 + threadIdx.x;
+    if (tail < n_here) dst[tail] = bytes[tail];
+  } else {
+    for (uint32_t i = threadIdx.x; i < n_here; i += kBlock) dst[i] = bytes[i];
+  }
+}
+
+// ------------------------------------------------------------------ K7: band de-interleave after the all-gather
+__global__ void deinterleave_kernel(const uint8_t* __restrict__ gathered, uint8_t* __restrict__ out, uint32_t row_bytes,
+                                    uint32_t height, uint32_t shard_count, uint32_t band_height, uint32_t rows_per_shard) {
+  const uint32_t row = blockIdx.y;
+  if (row >= height) return;
+  const uint32_t band = row / band_height, rib = row % band_height;
+  const uint32_t shard = band % shard_count, lrow = (band / shard_count) * band_height + rib;
+  const uint8_t* src = gathered + ((size_t)shard * rows_per_shard + lrow) * row_bytes;
+  uint8_t* dst = out + (size_t)row * row_bytes;
+  if (((row_bytes & 3) == 0) && ((((uintptr_t)src) | ((uintptr_t)dst)) & 3) == 0) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes / 4; i += gridDim.x * blockDim.x)
+      ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------ micro-benchmarks (roofline denominators)
+// Random 128-byte record gathers (the wide-node access pattern), `loads` independent records per thread.
+__global__ void gather_bench_kernel(const double2* __restrict__ buf, uint64_t n_records, uint32_t loads, double2* sink) {
+  uint64_t x = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  double2 acc = make_double2(0, 0);
+  for (uint32_t i = 0; i < loads; i += 4) {
+    uint64_t idx[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+      idx[k] = x % n_records;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double2* p = buf + idx[k] * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double2 v = __ldg(p + j);
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+    }
+  }
+  if (acc.x == 1.2345e300) sink[0] = acc;
+}
+
+__global__ void dfma_bench_kernel(double* sink, int iters) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 1.2345e300) sink[0] = s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
+  if (count)
+    trace_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, cam, P);
+  else
+    trace_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, cam, P);
+}
+void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream) {
+  if (count)
+    shadow_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, P);
+  else
+    shadow_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, P);
+}
+void launch_resolve(const ChunkParams& P, void* stream) {
+  const uint32_t n_pixels = P.n_rows * P.width;
+  resolve_kernel<<<(n_pixels + kBlock - 1) / kBlock, kBlock, 0, (cudaStream_t)stream>>>(P);
+}
+void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
+                         void* stream) {
+  const uint32_t n_bands = (height + band_height - 1) / band_height;
+  const uint32_t rows_per_shard = ((n_bands + shard_count - 1) / shard_count) * band_height;
+  dim3 grid(4, height);
+  deinterleave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gathered, out, (uint32_t)width * 3, height, shard_count,
+                                                              band_height, rows_per_shard);
+}
+int trace_blocks_per_sm(bool count) {
+  int n = 0;
+  if (count)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<true>, kBlock, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<false>, kBlock, 0);
+  return n;
+}
+int shadow_blocks_per_sm(bool count) {
+  int n = 0;
+  if (count)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<true>, kBlock, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<false>, kBlock, 0);
+  return n;
+}
+void launch_gather_bench(const double2* buf, uint64_t n_records, uint32_t loads_per_thread, double2* sink, int grid, int block,
+                         void* stream) {
+  gather_bench_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(buf, n_records, loads_per_thread, sink);
+}
+void launch_dfma_bench(double* sink, int iters, int grid, int block, void* stream) {
+  dfma_bench_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sink, iters);
+}
+
+}  // namespace rhd

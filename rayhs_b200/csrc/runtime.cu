@@ -1,0 +1,750 @@
+// runtime.cu — host side of librayhs_b200: device bring-up, scene upload, and the wavefront
+// schedule behind rh_render (the replacement for `rayTrace`, RayHs.hs:161-166, and
+// `distributedRayTrace`, RayHs.hs:190-195).  C ABI in include/rayhs_b200.h.
+//
+// Schedule per chunk of rows (all launches asynchronous on one stream, no host round trip
+// between passes — queue lengths stay in device memory and the kernels are persistent):
+//   pass 0      trace_kernel(primary)  -> shadow tasks, child rays
+//               shadow_kernel
+//   pass 1..2D  trace_kernel(queued)   -> shadow tasks, child rays     (D = maxDepth; a Transparent
+//               shadow_kernel                                            hit adds one probe pass per level)
+//   resolve_kernel -> RGB8
+// Sample offsets for chunk k+1 are uploaded on a second stream while chunk k is traced.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "device_types.cuh"
+
+namespace rh {
+static thread_local std::string g_err;
+int set_error(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+}  // namespace rh
+
+using namespace rhd;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+#define RH_CUDA(expr)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t e_ = (expr);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      int code_ = (e_ == cudaErrorMemoryAllocation) ? RH_ERR_OOM : RH_ERR_CUDA;                           \
+      return rh::set_error(code_, std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+    }                                                                                                     \
+  } while (0)
+
+// A growable device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n) {
+    if (n <= bytes) return RH_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    RH_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return RH_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+// Everything the library owns on one GPU.
+struct Device {
+  int dev = -1;
+  int n_sms = 0;
+  cudaStream_t stream = nullptr;       // kernels
+  cudaStream_t copy_stream = nullptr;  // sample-offset uploads
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  DevBuf accum, rayq[2], shq, shq_sample, ctl, counters, offsets[2], rgb, ids;
+  void* pinned = nullptr;  // ctl + counters read-back
+  size_t pinned_bytes = 0;
+  int grid_trace[2] = {0, 0}, grid_shadow[2] = {0, 0};
+  std::vector<cudaEvent_t> prof_events;
+
+  int open(int device) {
+    dev = device;
+    RH_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    RH_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+      return rh::set_error(RH_ERR_CUDA, std::string("rayhs_b200 needs an sm_100 device, found ") + prop.name);
+    n_sms = prop.multiProcessorCount;
+    RH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    RH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RH_CUDA(cudaEventCreate(&ev_begin));
+    RH_CUDA(cudaEventCreate(&ev_end));
+    for (int k = 0; k < 2; k++) {
+      RH_CUDA(cudaEventCreateWithFlags(&ev_up[k], cudaEventDisableTiming));
+      RH_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
+    for (int c = 0; c < 2; c++) {
+      grid_trace[c] = n_sms * std::max(1, trace_blocks_per_sm(c != 0));
+      grid_shadow[c] = n_sms * std::max(1, shadow_blocks_per_sm(c != 0));
+    }
+    RH_CUDA(cudaGetLastError());
+    return RH_OK;
+  }
+  void close() {
+    if (dev < 0) return;
+    cudaSetDevice(dev);
+    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &ctl, &counters, &offsets[0], &offsets[1], &rgb, &ids})
+      b->release();
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_bytes = 0;
+    for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+    prof_events.clear();
+    for (cudaEvent_t e : {ev_begin, ev_end, ev_up[0], ev_up[1], ev_done[0], ev_done[1]})
+      if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    stream = copy_stream = nullptr;
+    dev = -1;
+  }
+};
+
+std::mutex g_mu;
+std::unique_ptr<Device> g_dev;  // rh_init
+
+}  // namespace
+
+struct rh_scene {
+  Device* device = nullptr;
+  DevBuf wide, tris, shade, objects, materials, lights, textures, texels;
+  SceneView view{};
+  uint32_t max_tree_depth = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ scene upload
+int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<DObject>& objs, uint32_t* max_depth) {
+  const double inf = std::numeric_limits<double>::infinity();
+  objs.resize(d.n_objects);
+  struct Pending { uint32_t node, wide_index, depth; };
+  std::deque<Pending> fifo;
+  auto empty_box = [&](double* b) { for (int k = 0; k < 3; k++) { b[k] = inf; b[3 + k] = -inf; } };
+  std::vector<uint8_t> seen(d.n_nodes, 0);
+  for (uint32_t i = 0; i < d.n_objects; i++) {
+    const rh_object& o = d.objects[i];
+    DObject& t = objs[i];
+    memset(&t, 0, sizeof t);
+    memcpy(t.a, o.a, sizeof t.a);
+    memcpy(t.b, o.b, sizeof t.b);
+    memcpy(t.c, o.c, sizeof t.c);
+    t.kind = o.kind;
+    t.material = o.material;
+    t.root = kEmpty;
+    if (o.kind != RH_OBJ_PLANE && o.kind != RH_OBJ_SPHERE && o.kind != RH_OBJ_MESH)
+      return rh::set_error(RH_ERR_ARG, "rh_scene_create: unknown object kind");
+    if (o.material < 0 || (uint32_t)o.material >= d.n_materials)
+      return rh::set_error(RH_ERR_ARG, "rh_scene_create: object material index out of range");
+    t.is_emitter = d.materials[o.material].kind == RH_MAT_EMMIT;
+    if (o.kind == RH_OBJ_MESH && o.root != RH_NO_NODE) {
+      if (o.root >= d.n_nodes) return rh::set_error(RH_ERR_ARG, "rh_scene_create: mesh root out of range");
+      // the leaves of one mesh must occupy increasing triangle slots in left-to-right order:
+      // the slot order carries the reference's tie rule (KDTree.hs:109-115)
+      std::vector<std::pair<uint32_t, uint32_t>> dfs{{o.root, 0u}};
+      uint32_t last_first = 0;
+      bool any_leaf = false;
+      while (!dfs.empty()) {
+        auto [ni, depth] = dfs.back();
+        dfs.pop_back();
+        if (ni >= d.n_nodes || seen[ni]) return rh::set_error(RH_ERR_ARG, "rh_scene_create: node index out of range or shared");
+        seen[ni] = 1;
+        *max_depth = std::max(*max_depth, depth);
+        const rh_node& nd = d.nodes[ni];
+        if (nd.is_leaf) {
+          if ((uint64_t)nd.left + nd.right > d.n_tris) return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaf range out of bounds");
+          if (nd.right >= kLeafBit) return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaf too large");
+          if (any_leaf && nd.left < last_first)
+            return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaves must store their triangles in left-to-right leaf order");
+          last_first = nd.left;
+          any_leaf = true;
+        } else {
+          if (nd.right != RH_NO_NODE) dfs.push_back({nd.right, depth + 1});
+          if (nd.left != RH_NO_NODE) dfs.push_back({nd.left, depth + 1});
+        }
+      }
+      if (*max_depth + 4 > (uint32_t)kStack) return rh::set_error(RH_ERR_ARG, "rh_scene_create: tree deeper than 100 levels");
+      // synthetic super-root: slot 0 = the root itself (its box is tested like any other, KDTree.hs:96-103)
+      t.root = (uint32_t)wide.size();
+      WideNode w{};
+      empty_box(w.box);
+      empty_box(w.box + 6);
+      w.child[0] = w.child[1] = kEmpty;
+      wide.push_back(w);
+      fifo.push_back({o.root, t.root, 0});
+    }
+  }
+  // level order over all meshes: fill each wide node's two child slots, queue inner children
+  // `fifo` entries mean: node `node` is the (only) real child of wide record `wide_index` slot 0 when depth==0,
+  // otherwise the record `wide_index` IS the inner node `node`.
+  std::deque<Pending> work;
+  auto child_ref = [&](uint32_t ni, WideNode& w, int slot, uint32_t depth) {
+    double* box = w.box + 6 * slot;
+    if (ni == RH_NO_NODE) {
+      empty_box(box);
+      w.child[slot] = kEmpty;
+      return;
+    }
+    const rh_node& nd = d.nodes[ni];
+    memcpy(box, nd.lo, 3 * sizeof(double));
+    memcpy(box + 3, nd.hi, 3 * sizeof(double));
+    if (nd.is_leaf) {
+      w.child[slot] = kLeafBit | nd.right;
+      w.first[slot] = nd.left;
+    } else {
+      work.push_back({ni, 0, depth + 1});  // wide_index assigned when popped
+      w.child[slot] = 0xFFFFFFFEu;         // patched below
+    }
+  };
+  // First the super-roots (already in `wide`), then breadth-first.
+  struct Patch { uint32_t wide_index; int slot; };
+  std::deque<Patch> patches;
+  for (const Pending& p : fifo) {
+    size_t before = work.size();
+    child_ref(p.node, wide[p.wide_index], 0, 0);
+    if (work.size() > before) patches.push_back({p.wide_index, 0});
+  }
+  while (!work.empty()) {
+    Pending p = work.front();
+    work.pop_front();
+    Patch pa = patches.front();
+    patches.pop_front();
+    const uint32_t wi = (uint32_t)wide.size();
+    if (wi >= 0x7FFFFFF0u) return rh::set_error(RH_ERR_ARG, "rh_scene_create: too many nodes");
+    wide[pa.wide_index].child[pa.slot] = wi;
+    wide.push_back(WideNode{});
+    const rh_node& nd = d.nodes[p.node];
+    WideNode w{};
+    size_t before = work.size();
+    child_ref(nd.left, w, 0, p.depth);
+    if (work.size() > before) patches.push_back({wi, 0});
+    before = work.size();
+    child_ref(nd.right, w, 1, p.depth);
+    if (work.size() > before) patches.push_back({wi, 1});
+    wide[wi] = w;
+  }
+  return RH_OK;
+}
+
+template <class T>
+int upload(DevBuf& b, const T* src, size_t n) {
+  int rc = b.reserve(std::max<size_t>(n * sizeof(T), 256));
+  if (rc) return rc;
+  if (n) RH_CUDA(cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RH_OK;
+}
+
+int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
+  if (!d || !out) return rh::set_error(RH_ERR_ARG, "rh_scene_create: null argument");
+  if (d->n_materials > 0x7fff) return rh::set_error(RH_ERR_ARG, "rh_scene_create: more than 32767 materials");
+  if ((d->n_nodes && !d->nodes) || (d->n_tris && (!d->tris || !d->tri_shade)) || (d->n_objects && !d->objects) ||
+      (d->n_materials && !d->materials) || (d->n_lights && !d->lights))
+    return rh::set_error(RH_ERR_ARG, "rh_scene_create: null array with non-zero count");
+  for (uint32_t i = 0; i < d->n_materials; i++) {
+    const rh_material& m = d->materials[i];
+    if (m.kind < RH_MAT_MIRROR || m.kind > RH_MAT_SHOWUV) return rh::set_error(RH_ERR_ARG, "rh_scene_create: unknown material kind");
+    if ((m.kind == RH_MAT_DIFFUSE || m.kind == RH_MAT_PLASTIC)) {
+      if (m.cmap_kind < RH_CMAP_FLAT || m.cmap_kind > RH_CMAP_TEXTURE)
+        return rh::set_error(RH_ERR_ARG, "rh_scene_create: unknown colour-map kind");
+      if (m.cmap_kind == RH_CMAP_TEXTURE) {
+        if (m.texture < 0 || (uint32_t)m.texture >= d->n_textures)
+          return rh::set_error(RH_ERR_ARG, "rh_scene_create: texture index out of range");
+        const rh_texture& t = d->textures[m.texture];
+        if (t.w <= 0 || t.h <= 0 || t.offset + (uint64_t)t.w * t.h > d->n_texels)
+          return rh::set_error(RH_ERR_ARG, "rh_scene_create: texture outside the texel array");
+      }
+    }
+  }
+  for (uint32_t i = 0; i < d->n_lights; i++)
+    if (d->lights[i].kind != RH_LIGHT_DIRECTIONAL && d->lights[i].kind != RH_LIGHT_POINT)
+      return rh::set_error(RH_ERR_ARG, "rh_scene_create: unknown light kind");
+  std::vector<WideNode> wide;
+  std::vector<DObject> objs;
+  uint32_t depth = 0;
+  try {
+    int rc = build_wide(*d, wide, objs, &depth);
+    if (rc) return rc;
+  } catch (const std::bad_alloc&) {
+    return rh::set_error(RH_ERR_OOM, "rh_scene_create: out of host memory");
+  }
+  RH_CUDA(cudaSetDevice(D->dev));
+  auto S = std::make_unique<rh_scene>();
+  S->device = D;
+  S->max_tree_depth = depth;
+  int rc;
+  if ((rc = upload(S->wide, wide.data(), wide.size()))) return rc;
+  if ((rc = upload(S->tris, d->tris, d->n_tris))) return rc;
+  if ((rc = upload(S->shade, d->tri_shade, d->n_tris))) return rc;
+  if ((rc = upload(S->objects, objs.data(), objs.size()))) return rc;
+  if ((rc = upload(S->materials, d->materials, d->n_materials))) return rc;
+  if ((rc = upload(S->lights, d->lights, d->n_lights))) return rc;
+  if ((rc = upload(S->textures, d->textures, d->n_textures))) return rc;
+  if ((rc = upload(S->texels, d->texels, (size_t)d->n_texels * 3))) return rc;
+  SceneView& v = S->view;
+  v.wide = (const WideNode*)S->wide.p;
+  v.tris = (const rh_tri*)S->tris.p;
+  v.shade = (const rh_tri_shade*)S->shade.p;
+  v.objects = (const DObject*)S->objects.p;
+  v.materials = (const rh_material*)S->materials.p;
+  v.lights = (const rh_light*)S->lights.p;
+  v.textures = (const rh_texture*)S->textures.p;
+  v.texels = (const double*)S->texels.p;
+  v.n_wide = (uint32_t)wide.size();
+  v.n_tris = d->n_tris;
+  v.n_objects = d->n_objects;
+  v.n_materials = d->n_materials;
+  v.n_lights = d->n_lights;
+  v.n_textures = d->n_textures;
+  v.n_smem_nodes = std::min<uint32_t>(v.n_wide, kSmemNodes);
+  v.tables_in_smem = (d->n_objects <= (uint32_t)kSmemObjects && d->n_materials <= (uint32_t)kSmemObjects &&
+                      d->n_lights <= (uint32_t)kSmemLights);
+  *out = S.release();
+  return RH_OK;
+}
+
+void scene_destroy(rh_scene* s) {
+  if (!s) return;
+  if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
+  for (DevBuf* b : {&s->wide, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels}) b->release();
+  delete s;
+}
+
+// ------------------------------------------------------------------ camera (Projection.hs:22-46, Mat.hs:83-93)
+struct HV { double x, y, z; };
+HV hsub(HV a, HV b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+HV hcross(HV a, HV b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+HV hnormalize(HV v) {
+  double s = 1 / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  return {s * v.x, s * v.y, s * v.z};
+}
+
+CameraParams make_camera(const rh_camera& c, int width, int height) {
+  CameraParams p{};
+  const double w = (double)width, h = (double)height;
+  HV pos{c.position[0], c.position[1], c.position[2]}, tgt{c.target[0], c.target[1], c.target[2]}, tup{c.up[0], c.up[1], c.up[2]};
+  HV forward = hnormalize(hsub(tgt, pos));      // Mat.hs:89-93
+  HV right = hnormalize(hcross(tup, forward));
+  HV up = hcross(forward, right);
+  // fromColumns right up forward (Mat.hs:83-87), row-major
+  p.m[0] = right.x; p.m[1] = up.x; p.m[2] = forward.x;
+  p.m[3] = right.y; p.m[4] = up.y; p.m[5] = forward.y;
+  p.m[6] = right.z; p.m[7] = up.z; p.m[8] = forward.z;
+  p.pos[0] = pos.x; p.pos[1] = pos.y; p.pos[2] = pos.z;
+  p.w = w;
+  p.h = h;
+  p.half_w = w / 2;
+  p.half_h = h / 2;
+  const double aspect = w / h;  // aspectSize, Projection.hs:41-46
+  if (aspect > 1) { p.apw = w; p.aph = w / aspect; }
+  else { p.apw = aspect * h; p.aph = h; }
+  p.f = 0.5 * h / (std::tan(0.5) * c.fovy);  // Projection.hs:35 — `tan 0.5 * fovy`
+  p.projection = c.projection;
+  return p;
+}
+
+// ------------------------------------------------------------------ render
+struct Launch {
+  static void count() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+};
+
+int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const rh_render_opts* o, uint8_t* rgb_out,
+              int32_t* hit_ids_out, rh_stats* stats) {
+  if (!scene || !camera || !o || !rgb_out) return rh::set_error(RH_ERR_ARG, "rh_render: null argument");
+  if (scene->device != D) return rh::set_error(RH_ERR_ARG, "rh_render: scene lives on another device context");
+  const int W = o->width, H = o->height, spp = o->spp;
+  if (W <= 0 || H <= 0 || spp <= 0 || o->max_depth < 0 || o->max_depth > kMaxDepth)
+    return rh::set_error(RH_ERR_ARG, "rh_render: bad width/height/spp/max_depth");
+  if (camera->projection != RH_PROJ_ORTHOGRAPHIC && camera->projection != RH_PROJ_PERSPECTIVE)
+    return rh::set_error(RH_ERR_ARG, "rh_render: unknown projection");
+  const int G = o->shard_count <= 0 ? 1 : o->shard_count;
+  if (o->shard_index < 0 || o->shard_index >= G) return rh::set_error(RH_ERR_ARG, "rh_render: shard_index out of range");
+  const int bh = o->band_height > 0 ? o->band_height : rh_default_band_height(H, G);
+  const int rows_local = rh_shard_rows(H, G, bh);
+  const int mode = o->offset_mode;
+  if (mode < RH_OFFSETS_NONE || mode > RH_OFFSETS_TILED_F64) return rh::set_error(RH_ERR_ARG, "rh_render: bad offset_mode");
+  if (mode != RH_OFFSETS_NONE && !o->offsets) return rh::set_error(RH_ERR_ARG, "rh_render: offsets is null");
+  if (mode == RH_OFFSETS_TILED_F64 && o->offset_tile <= 0) return rh::set_error(RH_ERR_ARG, "rh_render: offset_tile must be > 0");
+  if ((uint64_t)W * spp > 0x7fffffffu) return rh::set_error(RH_ERR_ARG, "rh_render: row too large");
+  const bool want_ids = (o->flags & RH_FLAG_HIT_IDS) != 0;
+  if (want_ids && !hit_ids_out) return rh::set_error(RH_ERR_ARG, "rh_render: RH_FLAG_HIT_IDS without hit_ids_out");
+  const bool dev_out = (o->flags & RH_FLAG_DEVICE_OUT) != 0;
+  const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
+  const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
+  const bool profile = (o->flags & RH_FLAG_PROFILE) != 0;
+
+  RH_CUDA(cudaSetDevice(D->dev));
+  const CameraParams cam = make_camera(*camera, W, H);
+  const size_t row_samples = (size_t)W * spp;
+  const size_t want_chunk = o->chunk_samples > 0 ? (size_t)o->chunk_samples : ((size_t)8 << 20);
+  const int rows_per_chunk = (int)std::max<size_t>(1, std::min<size_t>(want_chunk / row_samples, (size_t)rows_local));
+  const int n_chunks = (rows_local + rows_per_chunk - 1) / rows_per_chunk;
+  const size_t chunk_samples = (size_t)rows_per_chunk * row_samples;
+  if (chunk_samples > 0x7fffffffu) return rh::set_error(RH_ERR_ARG, "rh_render: chunk too large");
+  const int n_passes = 2 * o->max_depth + 1;
+  const size_t off_elem = (mode == RH_OFFSETS_F32) ? sizeof(float) * 2 : sizeof(double) * 2;
+
+  int rc;
+  uint8_t* d_rgb;
+  const size_t rgb_bytes = (size_t)rows_local * W * 3;
+  if (dev_out) d_rgb = rgb_out;
+  else {
+    if ((rc = D->rgb.reserve(rgb_bytes))) return rc;
+    d_rgb = (uint8_t*)D->rgb.p;
+  }
+  int2* d_ids = nullptr;
+  const size_t ids_bytes = (size_t)rows_local * row_samples * sizeof(int2);
+  if (want_ids) {
+    if (dev_out) d_ids = (int2*)hit_ids_out;
+    else {
+      if ((rc = D->ids.reserve(ids_bytes))) return rc;
+      d_ids = (int2*)D->ids.p;
+    }
+  }
+  if ((rc = D->accum.reserve(chunk_samples * 3 * sizeof(double)))) return rc;
+  if ((rc = D->ctl.reserve((size_t)n_chunks * sizeof(ChunkCtl)))) return rc;
+  if ((rc = D->counters.reserve(sizeof(FrameCounters)))) return rc;
+  const size_t pinned_need = (size_t)n_chunks * sizeof(ChunkCtl) + sizeof(FrameCounters);
+  if (D->pinned_bytes < pinned_need) {
+    if (D->pinned) cudaFreeHost(D->pinned);
+    D->pinned = nullptr;
+    D->pinned_bytes = 0;
+    RH_CUDA(cudaMallocHost(&D->pinned, pinned_need));
+    D->pinned_bytes = pinned_need;
+  }
+  // sample offsets
+  const void* d_offsets = nullptr;
+  int off_index = kOffIndexLocal;
+  bool stream_offsets = false;
+  if (mode == RH_OFFSETS_TILED_F64) {
+    const size_t bytes = (size_t)o->offset_tile * o->offset_tile * spp * off_elem;
+    if (dev_off) d_offsets = o->offsets;
+    else {
+      if ((rc = D->offsets[0].reserve(bytes))) return rc;
+      d_offsets = D->offsets[0].p;
+    }
+  } else if (mode != RH_OFFSETS_NONE) {
+    if (dev_off) {
+      d_offsets = o->offsets;
+      off_index = kOffIndexGlobal;
+    } else {
+      stream_offsets = true;
+      for (int k = 0; k < 2; k++)
+        if ((rc = D->offsets[k].reserve(chunk_samples * off_elem))) return rc;
+    }
+  }
+
+  uint32_t factor = 2;  // queue capacity = factor * chunk samples; doubled when a chunk overflows
+  for (;;) {
+    const size_t cap = std::min<size_t>((size_t)factor * chunk_samples, 0x7ffffff0u);
+    for (int k = 0; k < 2; k++)
+      if ((rc = D->rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
+    if ((rc = D->shq.reserve(cap * 5 * sizeof(double2)))) return rc;
+    if ((rc = D->shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
+
+    size_t ev_used = 0;
+    auto prof_event = [&]() -> cudaEvent_t {
+      if (ev_used == D->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        D->prof_events.push_back(e);
+      }
+      cudaEvent_t e = D->prof_events[ev_used++];
+      cudaEventRecord(e, D->stream);
+      return e;
+    };
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+
+    RH_CUDA(cudaEventRecord(D->ev_begin, D->stream));
+    RH_CUDA(cudaMemsetAsync(D->ctl.p, 0, (size_t)n_chunks * sizeof(ChunkCtl), D->stream));
+    RH_CUDA(cudaMemsetAsync(D->counters.p, 0, sizeof(FrameCounters), D->stream));
+    if (mode == RH_OFFSETS_TILED_F64 && !dev_off)
+      RH_CUDA(cudaMemcpyAsync((void*)d_offsets, o->offsets, (size_t)o->offset_tile * o->offset_tile * spp * off_elem,
+                              cudaMemcpyHostToDevice, D->stream));
+    uint32_t launches = 0;
+    size_t upload_bytes = 0;
+
+    for (int ck = 0; ck < n_chunks; ck++) {
+      const int first_row = ck * rows_per_chunk;
+      const int n_rows = std::min(rows_per_chunk, rows_local - first_row);
+      ChunkParams P{};
+      P.first_row = first_row;
+      P.n_rows = n_rows;
+      P.n_samples = (uint32_t)((size_t)n_rows * row_samples);
+      P.spp = spp;
+      P.width = W;
+      P.height = H;
+      P.shard_index = o->shard_index;
+      P.shard_count = G;
+      P.band_height = bh;
+      P.max_depth = o->max_depth;
+      P.offset_mode = mode;
+      P.offset_index = off_index;
+      P.offset_tile = o->offset_tile;
+      P.offsets = d_offsets;
+      P.accum = (double*)D->accum.p;
+      P.accum_stride = (uint32_t)chunk_samples;
+      P.hit_ids = d_ids;
+      P.rgb = d_rgb;
+      P.ctl = (ChunkCtl*)D->ctl.p + ck;
+      P.counters = (FrameCounters*)D->counters.p;
+      P.q_shadow.plane = (double2*)D->shq.p;
+      P.q_shadow.sample = (uint32_t*)D->shq_sample.p;
+      P.q_shadow.capacity = (uint32_t)cap;
+
+      if (stream_offsets) {
+        // upload this chunk's rows (runs of image rows that are contiguous inside one band) on the copy stream
+        const int b = ck & 1;
+        if (ck >= 2) RH_CUDA(cudaStreamWaitEvent(D->copy_stream, D->ev_done[b], 0));
+        int lr = first_row;
+        while (lr < first_row + n_rows) {
+          const int lb = lr / bh, rib = lr % bh;
+          const int run = std::min(bh - rib, first_row + n_rows - lr);
+          const long long grow = ((long long)lb * G + o->shard_index) * bh + rib;
+          const long long rows_ok = std::max<long long>(0, std::min<long long>(run, (long long)H - grow));
+          if (rows_ok > 0) {
+            const size_t bytes = (size_t)rows_ok * row_samples * off_elem;
+            RH_CUDA(cudaMemcpyAsync((char*)D->offsets[b].p + (size_t)(lr - first_row) * row_samples * off_elem,
+                                    (const char*)o->offsets + (size_t)grow * row_samples * off_elem, bytes,
+                                    cudaMemcpyHostToDevice, D->copy_stream));
+            upload_bytes += bytes;
+          }
+          lr += run;
+        }
+        RH_CUDA(cudaEventRecord(D->ev_up[b], D->copy_stream));
+        RH_CUDA(cudaStreamWaitEvent(D->stream, D->ev_up[b], 0));
+        P.offsets = D->offsets[b].p;
+      }
+
+      RH_CUDA(cudaMemsetAsync(D->accum.p, 0, chunk_samples * 3 * sizeof(double), D->stream));
+      for (int pass = 0; pass < n_passes; pass++) {
+        P.pass = pass;
+        P.q_in.plane = (double2*)D->rayq[(pass + 1) & 1].p;
+        P.q_in.capacity = (uint32_t)cap;
+        P.q_out.plane = (double2*)D->rayq[pass & 1].p;
+        P.q_out.capacity = (uint32_t)cap;  // (the last pass cannot emit: every ray in it has depth == maxDepth)
+        cudaEvent_t a = nullptr;
+        if (profile) a = prof_event();
+        launch_trace(scene->view, cam, P, counting, D->grid_trace[counting], D->stream);
+        if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
+        launch_shadow(scene->view, P, counting, D->grid_shadow[counting], D->stream);
+        if (profile) spans.push_back({a, prof_event(), 1});
+        launches += 2;
+      }
+      cudaEvent_t a = nullptr;
+      if (profile) a = prof_event();
+      launch_resolve(P, D->stream);
+      if (profile) spans.push_back({a, prof_event(), 2});
+      launches += 1;
+      if (stream_offsets) RH_CUDA(cudaEventRecord(D->ev_done[ck & 1], D->stream));
+    }
+    RH_CUDA(cudaGetLastError());
+    RH_CUDA(cudaMemcpyAsync(D->pinned, D->ctl.p, (size_t)n_chunks * sizeof(ChunkCtl), cudaMemcpyDeviceToHost, D->stream));
+    RH_CUDA(cudaMemcpyAsync((char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl), D->counters.p, sizeof(FrameCounters),
+                            cudaMemcpyDeviceToHost, D->stream));
+    if (!dev_out) {
+      RH_CUDA(cudaMemcpyAsync(rgb_out, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, D->stream));
+      if (want_ids) RH_CUDA(cudaMemcpyAsync(hit_ids_out, d_ids, ids_bytes, cudaMemcpyDeviceToHost, D->stream));
+    }
+    RH_CUDA(cudaEventRecord(D->ev_end, D->stream));
+    RH_CUDA(cudaStreamSynchronize(D->stream));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+
+    const ChunkCtl* ctl = (const ChunkCtl*)D->pinned;
+    bool overflow = false;
+    for (int ck = 0; ck < n_chunks; ck++) overflow |= ctl[ck].overflow != 0;
+    if (overflow) {
+      if ((size_t)factor * chunk_samples >= 0x7ffffff0u || factor >= (1u << 16))
+        return rh::set_error(RH_ERR_OVERFLOW, "rh_render: ray queue overflow; lower chunk_samples");
+      factor *= 2;
+      continue;
+    }
+    if (stats) {
+      memset(stats, 0, sizeof *stats);
+      const FrameCounters* fc = (const FrameCounters*)((const char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl));
+      uint64_t shadow_tasks = 0;
+      for (int ck = 0; ck < n_chunks; ck++)
+        for (int p = 0; p < n_passes; p++) shadow_tasks += ctl[ck].shadow_count[p];
+      // padding rows of the last band trace nothing
+      uint64_t real_rows = 0;
+      for (int lr = 0; lr < rows_local; lr++) {
+        const long long grow = ((long long)(lr / bh) * G + o->shard_index) * bh + lr % bh;
+        if (grow < H) real_rows++;
+      }
+      stats->rays_primary = real_rows * row_samples;
+      stats->rays_reflect = fc->rays_reflect;
+      stats->rays_probe = fc->rays_probe;
+      stats->rays_exit = fc->rays_exit;
+      stats->rays_shadow = shadow_tasks * scene->view.n_lights;  // one shadowIntersection per light (RayHs.hs:89-97)
+      stats->box_tests = fc->box_tests;
+      stats->tri_tests = fc->tri_tests;
+      stats->prim_tests = fc->prim_tests;
+      stats->shade_fetches = fc->shade_fetches;
+      stats->texel_fetches = fc->texel_fetches;
+      stats->node_visits = fc->node_visits;
+      stats->shadow_tasks = shadow_tasks;
+      stats->upload_bytes = upload_bytes;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
+      stats->ms_total = ms;
+      for (const Span& s : spans) {
+        float m = 0;
+        cudaEventElapsedTime(&m, s.a, s.b);
+        if (s.kind == 0) { stats->ms_trace += m; stats->trace_launches++; }
+        else if (s.kind == 1) { stats->ms_shadow += m; stats->shadow_launches++; }
+        else stats->ms_resolve += m;
+      }
+      stats->kernel_launches = launches;
+      stats->chunks = (uint32_t)n_chunks;
+      stats->negative_channels = (uint32_t)std::min<unsigned long long>(fc->negative_channels, 0xffffffffu);
+      stats->queue_factor = factor;
+    }
+    return RH_OK;
+  }
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* rh_last_error(void) { return rh::g_err.c_str(); }
+int rh_abi_version(void) { return RH_ABI_VERSION; }
+uint64_t rh_launch_count(void) { return g_launches.load(); }
+
+int rh_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev) return rh::set_error(RH_ERR_STATE, "rh_init: already initialised");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return rh::set_error(RH_ERR_CUDA, std::string("rh_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (device < 0) RH_CUDA(cudaGetDevice(&device));
+  if (device >= n) return rh::set_error(RH_ERR_ARG, "rh_init: device index out of range");
+  auto d = std::make_unique<Device>();
+  int rc = d->open(device);
+  if (rc) { d->close(); return rc; }
+  g_dev = std::move(d);
+  return RH_OK;
+}
+
+void rh_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev) g_dev->close();
+  g_dev.reset();
+}
+
+int rh_scene_create(const rh_scene_desc* desc, rh_scene** out) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_scene_create: call rh_init first");
+  return scene_create_on(g_dev.get(), desc, out);
+}
+void rh_scene_destroy(rh_scene* scene) { scene_destroy(scene); }
+
+int rh_render(const rh_scene* scene, const rh_camera* camera, const rh_render_opts* opts, uint8_t* rgb_out,
+              int32_t* hit_ids_out, rh_stats* stats) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_render: call rh_init first");
+  return render_on(g_dev.get(), scene, camera, opts, rgb_out, hit_ids_out, stats);
+}
+
+int rh_default_band_height(int height, int shard_count) {
+  if (shard_count <= 1) return height > 0 ? height : 1;
+  // interleave bands so that every shard sees every part of the frame
+  int bh = 16;
+  while (bh > 1 && height / (bh * shard_count) < 4) bh /= 2;
+  return bh;
+}
+int rh_shard_rows(int height, int shard_count, int band_height) {
+  if (height <= 0 || shard_count <= 0 || band_height <= 0) return 0;
+  const int n_bands = (height + band_height - 1) / band_height;
+  return ((n_bands + shard_count - 1) / shard_count) * band_height;
+}
+
+int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int width, int height, int shard_count,
+                          int band_height) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_deinterleave_bands: call rh_init first");
+  if (!gathered_dev || !out_dev || width <= 0 || height <= 0 || shard_count <= 0 || band_height <= 0)
+    return rh::set_error(RH_ERR_ARG, "rh_deinterleave_bands: bad argument");
+  RH_CUDA(cudaSetDevice(g_dev->dev));
+  launch_deinterleave(gathered_dev, out_dev, width, height, shard_count, band_height, g_dev->stream);
+  g_launches.fetch_add(1);
+  RH_CUDA(cudaGetLastError());
+  RH_CUDA(cudaStreamSynchronize(g_dev->stream));
+  return RH_OK;
+}
+
+int rh_bench_gather(uint64_t bytes, int iters, double* gbs_out) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_bench_gather: call rh_init first");
+  if (bytes < 128 || iters <= 0 || !gbs_out) return rh::set_error(RH_ERR_ARG, "rh_bench_gather: bad argument");
+  Device* D = g_dev.get();
+  RH_CUDA(cudaSetDevice(D->dev));
+  void* buf = nullptr;
+  double2* sink = nullptr;
+  RH_CUDA(cudaMalloc(&buf, bytes));
+  RH_CUDA(cudaMalloc(&sink, 64));
+  RH_CUDA(cudaMemsetAsync(buf, 0, bytes, D->stream));
+  const int block = 256, grid = D->n_sms * 8;
+  const uint32_t loads = 64;
+  launch_gather_bench((const double2*)buf, bytes / 128, loads, sink, grid, block, D->stream);  // warm-up
+  RH_CUDA(cudaEventRecord(D->ev_begin, D->stream));
+  for (int i = 0; i < iters; i++) launch_gather_bench((const double2*)buf, bytes / 128, loads, sink, grid, block, D->stream);
+  RH_CUDA(cudaEventRecord(D->ev_end, D->stream));
+  RH_CUDA(cudaStreamSynchronize(D->stream));
+  g_launches.fetch_add(iters + 1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
+  *gbs_out = (double)grid * block * loads * 128.0 * iters / (ms * 1e-3) / 1e9;
+  cudaFree(buf);
+  cudaFree(sink);
+  RH_CUDA(cudaGetLastError());
+  return RH_OK;
+}
+
+int rh_bench_dfma(int iters, double* tflops_out) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_bench_dfma: call rh_init first");
+  if (iters <= 0 || !tflops_out) return rh::set_error(RH_ERR_ARG, "rh_bench_dfma: bad argument");
+  Device* D = g_dev.get();
+  RH_CUDA(cudaSetDevice(D->dev));
+  double* sink = nullptr;
+  RH_CUDA(cudaMalloc(&sink, 64));
+  const int block = 256, grid = D->n_sms * 8;
+  launch_dfma_bench(sink, iters, grid, block, D->stream);
+  RH_CUDA(cudaEventRecord(D->ev_begin, D->stream));
+  launch_dfma_bench(sink, iters, grid, block, D->stream);
+  RH_CUDA(cudaEventRecord(D->ev_end, D->stream));
+  RH_CUDA(cudaStreamSynchronize(D->stream));
+  g_launches.fetch_add(2);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
+  *tflops_out = (double)grid * block * 8.0 * iters * 2.0 / (ms * 1e-3) / 1e12;
+  cudaFree(sink);
+  RH_CUDA(cudaGetLastError());
+  return RH_OK;
+}
+
+}  // extern "C"
