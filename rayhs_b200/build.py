@@ -8,6 +8,7 @@ only because tests/, smoke() and bench.py's CPU-baseline legs need the checker.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -37,11 +38,27 @@ CXX_SOURCES = ["frontend.cpp", "host_build.cpp"]
 HEADERS = [os.path.join(CSRC, h) for h in ("device_types.cuh", "common.h")] + [os.path.join(ROOT, "include", "rayhs_b200.h")]
 
 
-def _stale(target: str, deps: list[str]) -> bool:
-    if not os.path.exists(target):
+def _digest(deps: list[str], flags: list[str]) -> str:
+    h = hashlib.sha256(" ".join(flags).encode())
+    for d in deps:
+        if os.path.exists(d):
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target: str, deps: list[str], flags: list[str]) -> bool:
+    """Content-based: the target's .stamp holds the digest of the sources and flags it was built from
+    (mtimes do not survive the copy to the GPU box; the stamp travels with the .so)."""
+    if not os.path.exists(target) or not os.path.exists(target + ".stamp"):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(target + ".stamp") as f:
+        return f.read().strip() != _digest(deps, flags)
+
+
+def _stamp(target: str, deps: list[str], flags: list[str]) -> None:
+    with open(target + ".stamp", "w") as f:
+        f.write(_digest(deps, flags))
 
 
 def _run(cmd: list[str], log: str | None = None) -> None:
@@ -55,34 +72,43 @@ def _run(cmd: list[str], log: str | None = None) -> None:
 
 
 def build_library(force: bool = False) -> str:
+    all_src = [os.path.join(CSRC, s) for s in CUDA_SOURCES + CXX_SOURCES] + HEADERS
+    all_flags = NVCC_FLAGS + CXX_FLAGS
+    if not force and not _stale(LIB, all_src, all_flags):
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     objs = []
     for src in CUDA_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
-        if force or _stale(o, [s] + HEADERS):
+        if force or _stale(o, [s] + HEADERS, NVCC_FLAGS):
             _run([NVCC, *NVCC_FLAGS, "-c", s, "-o", o], log=os.path.join(OBJ, src + ".ptxas.log"))
+            _stamp(o, [s] + HEADERS, NVCC_FLAGS)
         objs.append(o)
     for src in CXX_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
-        if force or _stale(o, [s] + HEADERS):
+        if force or _stale(o, [s] + HEADERS, CXX_FLAGS):
             _run([CXX, *CXX_FLAGS, "-c", s, "-o", o])
+            _stamp(o, [s] + HEADERS, CXX_FLAGS)
         objs.append(o)
-    if force or _stale(LIB, objs):
-        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lpthread", "-ldl"])
+    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lpthread", "-ldl"])
+    _stamp(LIB, all_src, all_flags)
     return LIB
 
 
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "rayhs_main.cpp")
-    if os.path.exists(src) and (force or _stale(CLI, [src, LIB] + HEADERS)):
+    if os.path.exists(src) and (force or _stale(CLI, [src] + HEADERS, CXX_FLAGS)):
         _run([CXX, *CXX_FLAGS, src, "-o", CLI, "-L" + os.path.dirname(LIB), "-lrayhs_b200", "-Wl,-rpath,$ORIGIN"])
+        _stamp(CLI, [src] + HEADERS, CXX_FLAGS)
     return CLI
 
 
 def build_oracle(force: bool = False) -> str:
     os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
-    if force or _stale(ORACLE_LIB, [ORACLE_SRC, HEADERS[-1]]):
-        _run([CXX, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", ORACLE_SRC, "-o", ORACLE_LIB, "-lpthread"])
+    flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared"]
+    if force or _stale(ORACLE_LIB, [ORACLE_SRC, HEADERS[-1]], flags):
+        _run([CXX, *flags, ORACLE_SRC, "-o", ORACLE_LIB, "-lpthread"])
+        _stamp(ORACLE_LIB, [ORACLE_SRC, HEADERS[-1]], flags)
     return ORACLE_LIB
 
 
