@@ -236,12 +236,18 @@ typedef struct rh_stats {
   uint64_t rays_exit;     /* transmitted child, RayHs.hs:143                    */
   uint64_t rays_shadow;   /* RayHs.hs:93                                        */
   uint64_t shadow_tasks;  /* shaded Diffuse/Plastic hits (each folds over all lights) */
-  uint64_t box_tests;     /* RH_FLAG_COUNT only: child boxes tested              */
-  uint64_t tri_tests;     /* RH_FLAG_COUNT only: triangle records tested         */
-  uint64_t prim_tests;    /* RH_FLAG_COUNT only: sphere / plane tests            */
-  uint64_t shade_fetches; /* RH_FLAG_COUNT only: winning triangle shading records read */
-  uint64_t texel_fetches; /* RH_FLAG_COUNT only                                  */
-  uint64_t node_visits;   /* RH_FLAG_COUNT only: 128-byte wide-node records read */
+  uint64_t queued_rays;   /* ray-queue entries written and read back (reflect + probe + exit) */
+  /* RH_FLAG_COUNT only; the first six are the closest-hit (trace) kernel's */
+  uint64_t box_tests;     /* child boxes tested                                  */
+  uint64_t tri_tests;     /* triangle records tested                             */
+  uint64_t prim_tests;    /* sphere / plane tests                                */
+  uint64_t shade_fetches; /* winning triangle shading records read               */
+  uint64_t texel_fetches;
+  uint64_t node_visits;   /* 128-byte wide-node records read                     */
+  uint64_t shadow_box_tests; /* the same four for the shadow (any-hit) kernel    */
+  uint64_t shadow_tri_tests;
+  uint64_t shadow_prim_tests;
+  uint64_t shadow_node_visits;
   uint64_t upload_bytes;  /* sample-offset bytes copied host -> device           */
   double ms_total;        /* CUDA events around the whole call's device work (uploads and read-back included) */
   double ms_trace;        /* RH_FLAG_PROFILE only: closest-hit + shade kernels   */

@@ -112,6 +112,13 @@ def build_oracle(force: bool = False) -> str:
     return ORACLE_LIB
 
 
+def build_oracle_ref() -> None:
+    """oracle/_ref would hold the reference's own implementation compiled from /root/reference.  The
+    reference is pure Haskell (22 .hs files, no C sources) and GHC is not in this image, so there is
+    nothing to build; the oracle stays a restatement ("port")."""
+    return None
+
+
 def build_all(force: bool = False) -> None:
     build_library(force)
     build_cli(force)

@@ -93,9 +93,11 @@ class rh_render_opts(C.Structure):
 
 class rh_stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_probe", C.c_uint64),
-                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("shadow_tasks", C.c_uint64),
+                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("shadow_tasks", C.c_uint64), ("queued_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("shade_fetches", C.c_uint64), ("texel_fetches", C.c_uint64), ("node_visits", C.c_uint64),
+                ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
+                ("shadow_node_visits", C.c_uint64),
                 ("upload_bytes", C.c_uint64), ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_resolve", C.c_double), ("trace_launches", C.c_uint32), ("shadow_launches", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("negative_channels", C.c_uint32),

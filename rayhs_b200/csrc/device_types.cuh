@@ -76,12 +76,12 @@ struct ChunkCtl {
 };
 
 // Frame-level counters (zeroed per rh_render).
+struct KernelCounters {  // RH_FLAG_COUNT only
+  unsigned long long box_tests, tri_tests, prim_tests, node_visits, shade_fetches, texel_fetches;
+};
 struct FrameCounters {
-  unsigned long long rays_reflect, rays_probe, rays_exit, shadow_tasks;
-  unsigned long long box_tests, tri_tests, prim_tests, shade_fetches, texel_fetches;
-  unsigned long long negative_channels;
-  unsigned long long node_visits;
-  unsigned long long pad_;
+  unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;
+  KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow_kernel
 };
 
 // SoA-of-16-byte planes so that a warp's compacted pushes are fully coalesced.

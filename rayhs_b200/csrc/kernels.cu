@@ -120,11 +120,12 @@ struct Cnt<false> {
   if constexpr (COUNT) cnt.field += (n)
 
 template <bool COUNT>
-__device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc) {
+__device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc, int which) {
   if constexpr (COUNT) {
+    KernelCounters* kc = &fc->k[which];
     unsigned long long* src[6] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel};
-    unsigned long long* dst[6] = {&fc->box_tests, &fc->tri_tests, &fc->prim_tests, &fc->node_visits, &fc->shade_fetches,
-                                  &fc->texel_fetches};
+    unsigned long long* dst[6] = {&kc->box_tests, &kc->tri_tests, &kc->prim_tests, &kc->node_visits, &kc->shade_fetches,
+                                  &kc->texel_fetches};
     for (int k = 0; k < 6; k++) {
       unsigned long long v = *src[k];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ S
     if (n_probe) atomicAdd(&P.counters->rays_probe, n_probe);
     if (n_exit) atomicAdd(&P.counters->rays_exit, n_exit);
   }
-  flush_counters<COUNT>(cnt, P.counters);
+  flush_counters<COUNT>(cnt, P.counters, 0);
 }
 
 // ------------------------------------------------------------------ K3: accumDiffuse (RayHs.hs:89-97)
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ 
     const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
     accumulate(P, sbits & 0x7fffffffu, w, total);
   }
-  flush_counters<COUNT>(cnt, P.counters);
+  flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)

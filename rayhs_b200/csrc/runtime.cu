@@ -602,12 +602,18 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->rays_probe = fc->rays_probe;
       stats->rays_exit = fc->rays_exit;
       stats->rays_shadow = shadow_tasks * scene->view.n_lights;  // one shadowIntersection per light (RayHs.hs:89-97)
-      stats->box_tests = fc->box_tests;
-      stats->tri_tests = fc->tri_tests;
-      stats->prim_tests = fc->prim_tests;
-      stats->shade_fetches = fc->shade_fetches;
-      stats->texel_fetches = fc->texel_fetches;
-      stats->node_visits = fc->node_visits;
+      stats->box_tests = fc->k[0].box_tests;
+      stats->tri_tests = fc->k[0].tri_tests;
+      stats->prim_tests = fc->k[0].prim_tests;
+      stats->shade_fetches = fc->k[0].shade_fetches;
+      stats->texel_fetches = fc->k[0].texel_fetches;
+      stats->node_visits = fc->k[0].node_visits;
+      stats->shadow_box_tests = fc->k[1].box_tests;
+      stats->shadow_tri_tests = fc->k[1].tri_tests;
+      stats->shadow_prim_tests = fc->k[1].prim_tests;
+      stats->shadow_node_visits = fc->k[1].node_visits;
+      for (int ck = 0; ck < n_chunks; ck++)
+        for (int p = 1; p < n_passes; p++) stats->queued_rays += std::min<uint64_t>(ctl[ck].ray_count[p], cap);
       stats->shadow_tasks = shadow_tasks;
       stats->upload_bytes = upload_bytes;
       float ms = 0;

@@ -200,9 +200,10 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
 def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offset_tile: int = 0, shard_index: int = 0,
                   shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0, count: bool = False,
                   profile: bool = False) -> dict:
-    """rh_render with DEVICE buffers (torch CUDA tensors): `rgb_dev` uint8 [rows, width, 3], `offsets_dev`
-    full-frame [height*width, spp, 2] float64/float32 (or the [tile*tile, spp, 2] tile).  The caller's
-    stream must have finished producing `offsets_dev`; the call returns after the frame is complete."""
+    """rh_render into a DEVICE framebuffer (torch CUDA uint8 tensor [rows, width, 3]).  `offsets_dev` is the
+    full-frame [height*width, spp, 2] float64/float32 stream (or the [tile*tile, spp, 2] tile), either a CUDA
+    tensor (already uploaded) or a pinned CPU tensor (uploaded chunk by chunk inside the call).  The call
+    returns after the frame is complete."""
     import torch
 
     L = lib()
@@ -212,7 +213,7 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     if tuple(rgb_dev.shape) != (rows, job.width, 3) or rgb_dev.dtype != torch.uint8 or not rgb_dev.is_cuda:
         raise ValueError("rgb_dev must be a CUDA uint8 tensor of shape [rows, width, 3]")
     flags = capi.RH_FLAG_DEVICE_OUT | (capi.RH_FLAG_COUNT if count else 0) | (capi.RH_FLAG_PROFILE if profile else 0)
-    if off is not None:
+    if off is not None and off.is_cuda:
         flags |= capi.RH_FLAG_DEVICE_OFFSETS
         torch.cuda.current_stream().synchronize()
     o = _opts(job, spp, mode, off.data_ptr() if off is not None else None, offset_tile, shard_index, shard_count, bh,
