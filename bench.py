@@ -94,12 +94,12 @@ class ClockSampler:
 
 def algorithmic_bytes(st: dict, spp_bytes: int) -> dict:
     """bytes the two traversal kernels must fetch/store per frame, from the
-    instrumented (RH_FLAG_COUNT) kernels' own counters.  Record sizes: wide node 128 B (two child
-    boxes), triangle 80 B, object record 96 B, shading record 128 B, texel 24 B, ray-queue entry
-    64 B, shadow task 84 B."""
-    trace = (128 * st["node_visits"] + 80 * st["tri_tests"] + 96 * st["prim_tests"] + 128 * st["shade_fetches"]
+    instrumented (RH_FLAG_COUNT) kernels' own counters.  Record sizes: wide node 64 B (two float child
+    boxes; the exact double record counts as two), triangle 80 B, object record 96 B, shading record
+    128 B, texel 24 B, ray-queue entry 64 B, shadow task 84 B."""
+    trace = (64 * st["node_visits"] + 80 * st["tri_tests"] + 96 * st["prim_tests"] + 128 * st["shade_fetches"]
              + 24 * st["texel_fetches"] + spp_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 84 * st["shadow_tasks"])
-    shadow = (128 * st["shadow_node_visits"] + 80 * st["shadow_tri_tests"] + 96 * st["shadow_prim_tests"]
+    shadow = (64 * st["shadow_node_visits"] + 80 * st["shadow_tri_tests"] + 96 * st["shadow_prim_tests"]
               + 84 * st["shadow_tasks"] + 24 * st["shadow_tasks"])
     return {"trace": trace, "shadow": shadow}
 
@@ -318,7 +318,8 @@ def main():
                         "h2d_bytes_per_step": int(stats_e2e[-1]["upload_bytes"]), "d2h_bytes_per_step": int((H if G > 1 else rows) * W * 3)},
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
                 "rays_per_frame": rays, "frame_ms": ms_dev,
-                "rays_by_class_rank0": {k: int(st[k]) for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow")},
+                "rays_by_class_rank0": {k: int(st[k]) for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow",
+                                                                "rays_shadow_culled")},
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if G > 1:

@@ -224,7 +224,9 @@ enum {
   RH_FLAG_DEVICE_OUT = 2,   /* rgb_out / hit_ids_out are DEVICE pointers on the current device */
   RH_FLAG_DEVICE_OFFSETS = 4, /* offsets is a DEVICE pointer (already uploaded, full-frame layout) */
   RH_FLAG_COUNT = 8,         /* run the instrumented kernels: fills box_tests .. texel_fetches (slower) */
-  RH_FLAG_PROFILE = 16       /* bracket every launch with CUDA events: fills ms_trace / ms_shadow / ms_resolve */
+  RH_FLAG_PROFILE = 16,      /* bracket every launch with CUDA events: fills ms_trace / ms_shadow / ms_resolve */
+  RH_FLAG_EXACT_BOXES = 32   /* validation: the reference's double slab test at every box instead of the
+                                conservative float cull (same image) */
 };
 
 /* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
@@ -235,6 +237,8 @@ typedef struct rh_stats {
   uint64_t rays_probe;    /* interior probe of Transparent, RayHs.hs:140        */
   uint64_t rays_exit;     /* transmitted child, RayHs.hs:143                    */
   uint64_t rays_shadow;   /* RayHs.hs:93                                        */
+  uint64_t rays_shadow_culled; /* of rays_shadow: light at or below the shading horizon (l.n <= 0), Lambert term
+                                  exactly 0, occlusion query skipped                                   */
   uint64_t shadow_tasks;  /* shaded Diffuse/Plastic hits (each folds over all lights) */
   uint64_t queued_rays;   /* ray-queue entries written and read back (reflect + probe + exit) */
   /* RH_FLAG_COUNT only; the first six are the closest-hit (trace) kernel's */

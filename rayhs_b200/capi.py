@@ -21,7 +21,7 @@ RH_CMAP_FLAT, RH_CMAP_CHECKER, RH_CMAP_TEXTURE = 0, 1, 2
 RH_LIGHT_DIRECTIONAL, RH_LIGHT_POINT = 0, 1
 RH_PROJ_ORTHOGRAPHIC, RH_PROJ_PERSPECTIVE = 0, 1
 RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64 = 0, 1, 2, 3
-RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE = 1, 2, 4, 8, 16
+RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE, RH_FLAG_EXACT_BOXES = 1, 2, 4, 8, 16, 32
 RH_NO_NODE = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -93,7 +93,7 @@ class rh_render_opts(C.Structure):
 
 class rh_stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_probe", C.c_uint64),
-                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("shadow_tasks", C.c_uint64), ("queued_rays", C.c_uint64),
+                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_shadow_culled", C.c_uint64), ("shadow_tasks", C.c_uint64), ("queued_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("shade_fetches", C.c_uint64), ("texel_fetches", C.c_uint64), ("node_visits", C.c_uint64),
                 ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),

@@ -12,7 +12,7 @@ constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 31
 constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
 constexpr int kStack = 104;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82)
-constexpr int kSmemNodes = 224;             // top wide nodes staged in shared memory (28 KB)
+constexpr int kSmemNodes = 448;             // top wide (fp32) nodes staged in shared memory (28 KB)
 constexpr int kSmemObjects = 64;            // object / material tables staged when the scene has at most this many
 constexpr int kSmemLights = 16;
 constexpr int kBlock = 128;
@@ -31,6 +31,16 @@ struct __align__(16) WideNode {
 };
 static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
 
+// 64-byte culling copy of a WideNode: the same two child boxes rounded OUTWARD to float.  The fp32
+// slab test on it is conservative (never rejects a box the double test of KDTree.hs:39-56 accepts,
+// see kernels.cu), so it only decides which triangles get the exact double test.
+struct __align__(16) WideNode32 {
+  float box[12];
+  uint32_t child[2];
+  uint32_t first[2];
+};
+static_assert(sizeof(WideNode32) == 64, "WideNode32 must be 64 bytes");
+
 // Object table entry (device copy of rh_object with the wide super-root index).
 struct __align__(16) DObject {
   double a[3], b[3], c[3];
@@ -42,7 +52,8 @@ struct __align__(16) DObject {
 static_assert(sizeof(DObject) == 96, "DObject must be 96 bytes");
 
 struct SceneView {
-  const WideNode* wide;
+  const WideNode* wide;      // exact double boxes: rays with a zero direction component, RH_FLAG_EXACT_BOXES
+  const WideNode32* wide32;  // conservative float boxes: everything else
   const rh_tri* tris;
   const rh_tri_shade* shade;
   const DObject* objects;
@@ -53,6 +64,8 @@ struct SceneView {
   uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables
+  float abs_max;            // largest |coordinate| of any mesh box (pads the fp32 slab test)
+  uint32_t pad_;
 };
 
 // Camera with everything `rayFromPixel` recomputes per pixel hoisted to the host
@@ -81,6 +94,7 @@ struct KernelCounters {  // RH_FLAG_COUNT only
 };
 struct FrameCounters {
   unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;
+  unsigned long long shadow_culled, pad_;  // (hit, light) pairs with l.n <= 0: Lambert term is exactly 0, query skipped
   KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow_kernel
 };
 
@@ -113,6 +127,8 @@ struct ChunkParams {
   int32_t offset_index;   // kOffIndex*: per-pixel offsets indexed by chunk-local or full-frame pixel
   int32_t offset_tile;
   int32_t pass;           // wavefront pass (0 = primary)
+  int32_t exact_boxes;    // RH_FLAG_EXACT_BOXES: double slab test for every ray (validation)
+  int32_t pad2_;
   const void* offsets;    // device
   double* accum;          // 3 planes of accum_stride (r,g,b), chunk-local sample order
   uint32_t accum_stride;

@@ -69,7 +69,7 @@ __device__ __forceinline__ Ray rayEps(V3 p, V3 n) { return Ray{p + mul(kEps, n),
 
 // ------------------------------------------------------------------ shared-memory staging
 struct SmemTables {
-  WideNode nodes[kSmemNodes];
+  WideNode32 nodes[kSmemNodes];
   DObject objects[kSmemObjects];
   rh_material materials[kSmemObjects];
   rh_light lights[kSmemLights];
@@ -92,7 +92,7 @@ struct Ctx {
 };
 
 __device__ __forceinline__ void stage_tables(SmemTables& sm, const SceneView& S, Ctx& cx) {
-  copy16(sm.nodes, S.wide, S.n_smem_nodes * (uint32_t)sizeof(WideNode));
+  copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
   if (S.tables_in_smem) {
     copy16(sm.objects, S.objects, S.n_objects * (uint32_t)sizeof(DObject));
     copy16(sm.materials, S.materials, S.n_materials * (uint32_t)sizeof(rh_material));
@@ -149,6 +149,53 @@ __device__ __forceinline__ bool slab(const Ray& r, const V3& inv, double lx, dou
   return !(tmax < 0 || tmin > tmax);
 }
 
+// Conservative float version of the same test, used only to CULL.  The boxes are the double boxes
+// rounded outward; the ray origin is widened to [o - e, o + e] with
+//   e = 2^-21 * (max|o_k| + largest |box coordinate| in the scene),
+// which covers the float rounding of the origin, of 1/d, of origin*(1/d) and of the fused
+// multiply-add (five roundings, each <= 2^-24 relative to |o| + |plane|; e allows eight).  `lo` always pairs with o+e and `hi` with o-e: for
+// either sign of d that moves the entry distance down and the exit distance up.  So whenever the
+// exact test passes, this one passes; the converse errors only make the traversal look at a few
+// more triangles, each of which then gets the exact double test.  Rays with a zero (or denormal)
+// direction component never come here (the reference's inf/NaN arithmetic decides those exactly).
+struct RayF {
+  float ix, iy, iz;     // 1 / d
+  float pix, piy, piz;  // (o + e) * (1/d)
+  float mix, miy, miz;  // (o - e) * (1/d)
+};
+
+__device__ __forceinline__ bool degenerate_dir(const V3& d) {
+  const double a = fmin(fmin(fabs(d.x), fabs(d.y)), fabs(d.z));
+  const double b = fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z));
+  return !(a > 1e-30) || !(b < 1e30);
+}
+
+__device__ __forceinline__ RayF make_rayf(const Ray& r, float abs_max) {
+  RayF f;
+  const double e = 4.76837158203125e-07 * (fmax(fmax(fabs(r.o.x), fabs(r.o.y)), fabs(r.o.z)) + (double)abs_max);
+  f.ix = (float)(1.0 / r.d.x);
+  f.iy = (float)(1.0 / r.d.y);
+  f.iz = (float)(1.0 / r.d.z);
+  f.pix = (float)(r.o.x + e) * f.ix;
+  f.piy = (float)(r.o.y + e) * f.iy;
+  f.piz = (float)(r.o.z + e) * f.iz;
+  f.mix = (float)(r.o.x - e) * f.ix;
+  f.miy = (float)(r.o.y - e) * f.iy;
+  f.miz = (float)(r.o.z - e) * f.iz;
+  return f;
+}
+
+// t = plane * (1/d) - origin * (1/d) as one fused multiply-add per plane (an explicit intrinsic:
+// -fmad=false only stops the compiler from fusing the reference's double arithmetic).
+__device__ __forceinline__ bool slab32(const RayF& f, float lx, float ly, float lz, float hx, float hy, float hz, float& tmin) {
+  const float t1 = __fmaf_rn(lx, f.ix, -f.pix), t2 = __fmaf_rn(hx, f.ix, -f.mix);
+  const float t3 = __fmaf_rn(ly, f.iy, -f.piy), t4 = __fmaf_rn(hy, f.iy, -f.miy);
+  const float t5 = __fmaf_rn(lz, f.iz, -f.piz), t6 = __fmaf_rn(hz, f.iz, -f.miz);
+  tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+  const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+  return !(tmax < 0.0f || tmin > tmax);
+}
+
 // Closest-hit candidate: key (t asc, leaf desc, position-in-leaf asc) inside one mesh
 // (KDTree.hs:109-115 right child wins ties; Geometry.hs:54-57 first minimum inside a leaf),
 // strict `<` across objects (RayHs.hs:67-71 first object wins ties).
@@ -184,26 +231,126 @@ struct AnyHit {
   }
 };
 
-__device__ __forceinline__ const double2* node_ptr(const Ctx& cx, uint32_t idx) {
-  return idx < cx.S->n_smem_nodes ? (const double2*)&cx.sm->nodes[idx] : (const double2*)&cx.S->wide[idx];
+// Mesh.hs:59-82 triangleIntersection over the `count` triangles of one leaf (Geometry.hs:54-57).
+// The accept/reject decision is the reference's expression evaluated on the reference's values
+// of det, u, v, t.  Before the division, a triangle is dropped early only when that expression is
+// certain to reject it: with s = sign(det), u = idet*un and |idet*|det| - 1| <= 2^-52,
+//   s*un < -1e-100            =>  u < 0        s*un > |det|(1+1e-12)        =>  u > 1
+//   s*vn < -1e-100            =>  v < 0        s*(un+vn) > |det|(1+1e-12)   =>  u+v > 1
+//   s*tn < |det|*eps(1-1e-12) =>  t < eps      s*tn > |det|*bound           =>  t > best t (or beyond the light)
+// (the 1e-100 guard keeps idet*un away from underflow to -0, which `u < 0` would not reject).
+template <bool COUNT, class Sink>
+__device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint32_t first, uint32_t count, const Ray& r,
+                                          Sink& sink, double& bound, Cnt<COUNT>& cnt) {
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t slot = first + k;
+    const double2* tp = (const double2*)(tris + slot);
+    const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+    const double e2z = __ldg((const double*)(tp + 4));
+    RH_CNT(tri, 1);
+    const V3 p0 = mk(a.x, a.y, b.x), e1 = mk(b.y, c.x, c.y), e2 = mk(d.x, d.y, e2z);
+    const V3 p = cross(r.d, e2);
+    const double det = dot(e1, p);
+    const double adet = fabs(det);
+    if (adet < kEps) continue;
+    const bool safe = adet < 1e100;
+    const V3 t0 = r.o - p0;
+    const double un = dot(t0, p);
+    const double sun = det < 0 ? -un : un;
+    const double over = adet * 1.000000000001;
+    if (safe && (sun < -1e-100 || sun > over)) continue;
+    const V3 q = cross(t0, e1);
+    const double vn = dot(r.d, q);
+    const double svn = det < 0 ? -vn : vn;
+    if (safe && (svn < -1e-100 || sun + svn > over)) continue;
+    const double tn = dot(e2, q);
+    const double stn = det < 0 ? -tn : tn;
+    if (safe && (stn < adet * (kEps * 0.999999999999) || stn > adet * bound)) continue;
+    const double idet = 1 / det;
+    const double u = idet * un;
+    const double v = idet * vn;
+    const double t = idet * tn;
+    if (u < 0 || u > 1 || v < 0 || (u + v) > 1 || t < kEps) continue;
+    if (sink.offer(r, t, u, v, slot, first, bound)) return true;
+  }
+  return false;
 }
 
-// KDTree.hs:96-107 rayInter, ordered and pruned.  Every box the reference would test on the
-// way to a triangle is tested here with the same arithmetic; subtrees are skipped only when
-// their entry distance exceeds `bound` (the best t so far, or the light distance).
-// Returns true when the candidate sink asked to stop (any-hit).
+// KDTree.hs:96-107 rayInter, ordered and pruned, culling with the conservative float boxes.
+// Subtrees are skipped only when their entry distance exceeds `bound` (the best t so far times
+// 1 + 1e-7, or the light distance).  Returns true when the sink asked to stop (any-hit).
 template <bool COUNT, class Sink>
-__device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const V3& inv, double& bound, Sink& sink,
+__device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const RayF& f, double& bound, Sink& sink,
                                          uint2* stack, Cnt<COUNT>& cnt) {
+  int sp = 0;
+  uint32_t ref = root, first = 0;
+  const rh_tri* tris = cx.S->tris;
+  const uint32_t n_smem = cx.S->n_smem_nodes;
+  for (;;) {
+    if (!(ref & kLeafBit)) {
+      const float4* np = ref < n_smem ? (const float4*)&cx.sm->nodes[ref] : (const float4*)&cx.S->wide32[ref];
+      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
+      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
+      RH_CNT(nodes, 1);
+      const float fb = __double2float_ru(bound);
+      bool h0 = false, h1 = false;
+      float tm0 = 0, tm1 = 0;
+      if (cw.x != kEmpty) {
+        RH_CNT(box, 1);
+        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > fb);
+      }
+      if (cw.y != kEmpty) {
+        RH_CNT(box, 1);
+        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > fb);
+      }
+      if (h0 && h1) {
+        if (tm1 < tm0) {
+          stack[sp++] = make_uint2(cw.x, cw.z);
+          ref = cw.y;
+          first = cw.w;
+        } else {
+          stack[sp++] = make_uint2(cw.y, cw.w);
+          ref = cw.x;
+          first = cw.z;
+        }
+        continue;
+      }
+      if (h0) {
+        ref = cw.x;
+        first = cw.z;
+        continue;
+      }
+      if (h1) {
+        ref = cw.y;
+        first = cw.w;
+        continue;
+      }
+    } else {
+      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+    }
+    if (sp == 0) return false;
+    const uint2 e = stack[--sp];
+    ref = e.x;
+    first = e.y;
+  }
+}
+
+// The same walk with the reference's own double slab test (GHC min/max NaN semantics included):
+// rays with a zero direction component (centre row/column of the image) and
+// RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line.
+template <bool COUNT, class Sink>
+__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, uint2* stack,
+                                            Cnt<COUNT>& cnt) {
+  const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
   int sp = 0;
   uint32_t ref = root, first = 0;
   const rh_tri* tris = cx.S->tris;
   for (;;) {
     if (!(ref & kLeafBit)) {
-      const double2* np = node_ptr(cx, ref);
+      const double2* np = (const double2*)&cx.S->wide[ref];
       const double2 b0 = np[0], b1 = np[1], b2 = np[2], b3 = np[3], b4 = np[4], b5 = np[5];
-      const uint4 cw = *(const uint4*)(np + 6);  // child0, child1, first0, first1
-      RH_CNT(nodes, 1);
+      const uint4 cw = *(const uint4*)(np + 6);
+      RH_CNT(nodes, 2);  // a 128-byte record = two 64-byte units
       bool h0 = false, h1 = false;
       double tm0 = 0, tm1 = 0;
       if (cw.x != kEmpty) {
@@ -237,26 +384,7 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
         continue;
       }
     } else {
-      const uint32_t count = ref & ~kLeafBit;
-      for (uint32_t k = 0; k < count; k++) {
-        const uint32_t slot = first + k;
-        const double2* tp = (const double2*)(tris + slot);
-        const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
-        const double e2z = __ldg((const double*)(tp + 4));
-        RH_CNT(tri, 1);
-        // Mesh.hs:59-82 triangleIntersection
-        const V3 p0 = mk(a.x, a.y, b.x), e1 = mk(b.y, c.x, c.y), e2 = mk(d.x, d.y, e2z);
-        const V3 p = cross(r.d, e2);
-        const double det = dot(e1, p);
-        const double idet = 1 / det;
-        const V3 t0 = r.o - p0;
-        const double u = idet * dot(t0, p);
-        const V3 q = cross(t0, e1);
-        const double v = idet * dot(r.d, q);
-        const double t = idet * dot(e2, q);
-        if (fabs(det) < kEps || u < 0 || u > 1 || v < 0 || (u + v) > 1 || t < kEps) continue;
-        if (sink.offer(r, t, u, v, slot, first, bound)) return true;
-      }
+      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
     }
     if (sp == 0) return false;
     const uint2 e = stack[--sp];
@@ -265,12 +393,18 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
   }
 }
 
-// Geometry.hs:70-79 (plane) — returns the hit time only; position/normal/uv are rebuilt by the shader.
-__device__ __forceinline__ bool plane_time(const Ray& r, const DObject& ob, double& time) {
+// Geometry.hs:70-79 (plane): hit iff |d.n| > 0 and time = n.(p-o) / (d.n) > 0.  The quotient is
+// only formed when it can matter: opposite signs (or a zero numerator) give time <= 0 exactly, and
+// |num| > limit*|den| gives time > limit (limit = best t so far, or the light distance with its slack).
+__device__ __forceinline__ bool plane_time(const Ray& r, const DObject& ob, double limit, double& time) {
   const V3 p = ld3(ob.a), n = ld3(ob.b);
   const double dDotn = dot(r.d, n);
-  time = dot(n, p - r.o) / dDotn;
-  return fabs(dDotn) > 0 && time > 0;
+  const double num = dot(n, p - r.o);
+  if (!(fabs(dDotn) > 0)) return false;
+  if ((num > 0) != (dDotn > 0) && num == num) return false;  // quotient <= 0 (or -0): `time > 0` fails
+  if (fabs(num) > limit * fabs(dDotn) * 1.000000000001) return false;
+  time = num / dDotn;
+  return time > 0;
 }
 // Geometry.hs:81-95 (sphere): first positive root.
 __device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, double& time) {
@@ -296,8 +430,9 @@ __device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, dou
 
 // RayHs.hs:58-71 closestIntersection over the object list.
 template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, Closest& best, uint2* stack, Cnt<COUNT>& cnt) {
-  const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
+__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, uint2* stack,
+                                            Cnt<COUNT>& cnt) {
+  const RayF f = make_rayf(r, cx.S->abs_max);
   best.t = __longlong_as_double(0x7ff0000000000000LL);
   best.u = best.v = 0;
   best.slot = best.leaf_first = 0;
@@ -311,11 +446,14 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, Closest
       if (root == kEmpty) continue;
       best.cur_obj = (int)i;
       double bound = best.t * kPruneSlack;
-      traverse<COUNT>(cx, root, r, inv, bound, best, stack, cnt);
+      if (exact)
+        traverse_exact<COUNT>(cx, root, r, bound, best, stack, cnt);
+      else
+        traverse<COUNT>(cx, root, r, f, bound, best, stack, cnt);
     } else {
       double time;
       RH_CNT(prim, 1);
-      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, time) : sphere_time(r, ob, time);
+      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, best.t, time) : sphere_time(r, ob, time);
       if (hit && time < best.t) {
         best.t = time;
         best.obj = (int)i;
@@ -326,8 +464,9 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, Closest
 
 // RayHs.hs:74-87 shadowIntersection: true when some non-emitter object has a hit in front of the light.
 template <bool COUNT>
-__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, const rh_light& L, uint2* stack, Cnt<COUNT>& cnt) {
-  const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
+__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, uint2* stack,
+                                         Cnt<COUNT>& cnt) {
+  const RayF f = make_rayf(r, cx.S->abs_max);
   AnyHit sink;
   sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
   sink.lpos = ld3(L.vec);
@@ -344,11 +483,13 @@ __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, const rh_l
       const uint32_t root = ob.root;
       if (root == kEmpty) continue;
       double bound = far;
-      if (traverse<COUNT>(cx, root, r, inv, bound, sink, stack, cnt)) return true;
+      const bool hit = exact ? traverse_exact<COUNT>(cx, root, r, bound, sink, stack, cnt)
+                             : traverse<COUNT>(cx, root, r, f, bound, sink, stack, cnt);
+      if (hit) return true;
     } else {
       double time;
       RH_CNT(prim, 1);
-      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, time) : sphere_time(r, ob, time);
+      const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, far, time) : sphere_time(r, ob, time);
       if (hit && sink.in_front(r, time)) return true;
     }
   }
@@ -704,7 +845,7 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ S
 
     Closest best;
     best.obj = -1;
-    if (valid) closest_hit<COUNT>(cx, r, best, stack, cnt);
+    if (valid) closest_hit<COUNT>(cx, r, P.exact_boxes || degenerate_dir(r.d), best, stack, cnt);
 
     if (primary && valid && P.hit_ids) {
       int tri = -1;
@@ -754,6 +895,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ 
   ChunkCtl* ctl = P.ctl;
   const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
   const size_t cap = P.q_shadow.capacity;
+  unsigned long long n_culled = 0;
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&ctl->shadow_cursor[P.pass], 32u);
@@ -781,12 +923,22 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ 
         ld = mul(1 / dd, lp - p);
         lc = mul(falloff, ld3(L.color));
       }
-      const bool shadowed = occluded<COUNT>(cx, rayEps(p, ld), L, stack, cnt);
-      if (!shadowed) acc = acc + mul(hs_max(dot(ld, n), 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+      // diffuse (Material.hs:31-33) = (max (l.n) 0 / pi) * (cd (*) lc): exactly zero when l.n <= 0, whether
+      // or not the point is shadowed, so the occlusion query cannot change the sum and is skipped.
+      const double ldn = dot(ld, n);
+      if (ldn <= 0) {
+        n_culled++;
+        continue;
+      }
+      const Ray sr = rayEps(p, ld);
+      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || degenerate_dir(sr.d), L, stack, cnt);
+      if (!shadowed) acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));
     }
     const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
     accumulate(P, sbits & 0x7fffffffu, w, total);
   }
+  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
+  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 

@@ -133,7 +133,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, tris, shade, objects, materials, lights, textures, texels;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels;
   SceneView view{};
   uint32_t max_tree_depth = 0;
 };
@@ -298,7 +298,32 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   S->device = D;
   S->max_tree_depth = depth;
   int rc;
+  // conservative float copy of the boxes: lower bounds rounded down, upper bounds rounded up
+  std::vector<WideNode32> wide32(wide.size());
+  float abs_max = 0.f;
+  for (size_t i = 0; i < wide.size(); i++) {
+    const WideNode& w = wide[i];
+    WideNode32& n = wide32[i];
+    for (int c = 0; c < 2; c++) {
+      for (int k = 0; k < 3; k++) {
+        const double lo = w.box[6 * c + k], hi = w.box[6 * c + 3 + k];
+        float flo = (float)lo, fhi = (float)hi;
+        if ((double)flo > lo) flo = std::nextafterf(flo, -std::numeric_limits<float>::infinity());
+        if ((double)fhi < hi) fhi = std::nextafterf(fhi, std::numeric_limits<float>::infinity());
+        n.box[6 * c + k] = flo;
+        n.box[6 * c + 3 + k] = fhi;
+        if (w.child[c] != kEmpty) {
+          if (!(std::fabs(lo) < 1e30) || !(std::fabs(hi) < 1e30))
+            return rh::set_error(RH_ERR_ARG, "rh_scene_create: box coordinate is not finite or exceeds 1e30");
+          abs_max = std::max(abs_max, std::max(std::fabs(flo), std::fabs(fhi)));
+        }
+      }
+      n.child[c] = w.child[c];
+      n.first[c] = w.first[c];
+    }
+  }
   if ((rc = upload(S->wide, wide.data(), wide.size()))) return rc;
+  if ((rc = upload(S->wide32, wide32.data(), wide32.size()))) return rc;
   if ((rc = upload(S->tris, d->tris, d->n_tris))) return rc;
   if ((rc = upload(S->shade, d->tri_shade, d->n_tris))) return rc;
   if ((rc = upload(S->objects, objs.data(), objs.size()))) return rc;
@@ -308,6 +333,8 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   if ((rc = upload(S->texels, d->texels, (size_t)d->n_texels * 3))) return rc;
   SceneView& v = S->view;
   v.wide = (const WideNode*)S->wide.p;
+  v.wide32 = (const WideNode32*)S->wide32.p;
+  v.abs_max = abs_max;
   v.tris = (const rh_tri*)S->tris.p;
   v.shade = (const rh_tri_shade*)S->shade.p;
   v.objects = (const DObject*)S->objects.p;
@@ -331,7 +358,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
 void scene_destroy(rh_scene* s) {
   if (!s) return;
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
-  for (DevBuf* b : {&s->wide, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels}) b->release();
+  for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels}) b->release();
   delete s;
 }
 
@@ -397,6 +424,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
   const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
   const bool profile = (o->flags & RH_FLAG_PROFILE) != 0;
+  const bool exact_boxes = (o->flags & RH_FLAG_EXACT_BOXES) != 0;
 
   RH_CUDA(cudaSetDevice(D->dev));
   const CameraParams cam = make_camera(*camera, W, H);
@@ -504,6 +532,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.shard_count = G;
       P.band_height = bh;
       P.max_depth = o->max_depth;
+      P.exact_boxes = exact_boxes ? 1 : 0;
       P.offset_mode = mode;
       P.offset_index = off_index;
       P.offset_tile = o->offset_tile;
@@ -615,6 +644,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       for (int ck = 0; ck < n_chunks; ck++)
         for (int p = 1; p < n_passes; p++) stats->queued_rays += std::min<uint64_t>(ctl[ck].ray_count[p], cap);
       stats->shadow_tasks = shadow_tasks;
+      stats->rays_shadow_culled = fc->shadow_culled;
       stats->upload_bytes = upload_bytes;
       float ms = 0;
       cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);

@@ -173,7 +173,7 @@ def _offset_mode(offsets, tile: int):
 
 def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, want_hit_ids: bool = False,
            shard_index: int = 0, shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0,
-           count: bool = False, profile: bool = False, out: np.ndarray | None = None) -> Image:
+           count: bool = False, profile: bool = False, exact_boxes: bool = False, out: np.ndarray | None = None) -> Image:
     """One rh_render call with HOST buffers (numpy or pinned torch CPU tensors for `offsets`).
     Returns the shard-compact RGB8 rows when shard_count > 1."""
     L = lib()
@@ -187,7 +187,8 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
             raise ValueError(f"offsets has {have} values, expected {need}")
     bh = band_height or L.rh_default_band_height(job.height, shard_count)
     rows = L.rh_shard_rows(job.height, shard_count, bh)
-    flags = (capi.RH_FLAG_HIT_IDS if want_hit_ids else 0) | (capi.RH_FLAG_COUNT if count else 0) | (capi.RH_FLAG_PROFILE if profile else 0)
+    flags = ((capi.RH_FLAG_HIT_IDS if want_hit_ids else 0) | (capi.RH_FLAG_COUNT if count else 0)
+             | (capi.RH_FLAG_PROFILE if profile else 0) | (capi.RH_FLAG_EXACT_BOXES if exact_boxes else 0))
     o = _opts(job, spp, mode, off_ptr, offset_tile, shard_index, shard_count, bh, chunk_samples, flags)
     rgb = out if out is not None else np.empty((rows, job.width, 3), dtype=np.uint8)
     ids = np.empty((rows, job.width, spp, 2), dtype=np.int32) if want_hit_ids else None
@@ -221,6 +222,17 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     st = capi.rh_stats()
     check(L.rh_render(job.scene.device, C.byref(job.camera), C.byref(o), rgb_dev.data_ptr(), None, C.byref(st)))
     return st.as_dict()
+
+
+def shard_global_rows(height: int, shard_index: int, shard_count: int, band_height: int) -> list[int]:
+    """Image rows of one shard, in shard-compact order (SURVEY 8e): band b = row // band_height belongs to
+    shard b % shard_count.  Padding rows of the last band are reported as -1."""
+    rows = lib().rh_shard_rows(height, shard_count, band_height)
+    out = []
+    for lr in range(rows):
+        g = ((lr // band_height) * shard_count + shard_index) * band_height + lr % band_height
+        out.append(g if g < height else -1)
+    return out
 
 
 def assemble_bands(parts: list[np.ndarray], height: int, band_height: int) -> np.ndarray:

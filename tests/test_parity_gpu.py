@@ -63,3 +63,19 @@ def test_chunking_and_shards_give_identical_bytes():
         # transparent forks accumulate with atomics: allow the documented 1-LSB wobble, nothing more
         m = compare_images(full, base)
         assert m["maxdiff"] <= 1 and m["exact"] > 0.9999, (G, m)
+
+
+@pytest.mark.parametrize("name", ["cornellBox", "dragon_full", "outScene"])
+def test_float_cull_equals_exact_boxes(name):
+    """The conservative float box cull must give the same hits and bytes as the reference's double slab
+    test at every box (RH_FLAG_EXACT_BOXES), at a resolution large enough to matter."""
+    sc = load_scene(name)
+    w, h = 960, 540
+    job = rh.renderingFromScene(sc, w, h)
+    fast = rh.render(job, want_hit_ids=True)
+    exact = rh.render(job, want_hit_ids=True, exact_boxes=True)
+    assert np.array_equal(fast.hit_ids, exact.hit_ids)
+    m = compare_images(fast.pixels, exact.pixels)
+    assert m["maxdiff"] <= 1 and m["exact"] >= 0.99999, m
+    for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"):
+        assert fast.stats[k] == exact.stats[k], k
