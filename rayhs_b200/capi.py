@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librayhs_b200.so")
+LIB_PATH = os.environ.get("RAYHS_B200_LIB") or os.path.join(_HERE, "librayhs_b200.so")  # override: A/B builds only
 
 # error classes
 RH_OK, RH_ERR_ARG, RH_ERR_CUDA, RH_ERR_NCCL, RH_ERR_OOM, RH_ERR_STATE, RH_ERR_IO, RH_ERR_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7

@@ -12,10 +12,27 @@ constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 31
 constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
 constexpr int kStack = 104;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82)
-constexpr int kSmemNodes = 448;             // top wide (fp32) nodes staged in shared memory (28 KB)
+#ifndef RH_SMEM_NODES
+#define RH_SMEM_NODES 448
+#endif
+constexpr int kSmemNodes = RH_SMEM_NODES;   // top wide (fp32) nodes staged in shared memory (64 B each)
 constexpr int kSmemObjects = 64;            // object / material tables staged when the scene has at most this many
 constexpr int kSmemLights = 16;
-constexpr int kBlock = 128;
+constexpr int kBlock = 128;                // resolve kernel
+#ifndef RH_TRACE_BLOCK
+#define RH_TRACE_BLOCK 768
+#define RH_TRACE_MINB 1
+#define RH_SHADOW_BLOCK 768
+#define RH_SHADOW_MINB 1
+#endif
+#ifndef RH_SHADOW_T
+#define RH_SHADOW_T 4   // shaded hits per lane per warp batch in the pooled shadow kernel
+#endif
+#ifndef RH_SHADOW_POOL
+#define RH_SHADOW_POOL 1
+#endif
+constexpr int kTraceBlock = RH_TRACE_BLOCK, kTraceMinBlocks = RH_TRACE_MINB;      // one 768-thread block per SM: 24 warps at <= 85 registers, tables staged once per SM (measured best, profiles/README.md)
+constexpr int kShadowBlock = RH_SHADOW_BLOCK, kShadowMinBlocks = RH_SHADOW_MINB;
 
 // 128-byte "wide" node: one record per inner tree node holding BOTH child boxes, so a
 // visit is one 128-byte line (4 sectors) and every box is still tested exactly once,
@@ -147,6 +164,7 @@ void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int gri
 void launch_resolve(const ChunkParams& P, void* stream);
 void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
                          void* stream);
+int configure_kernels();  // opt in to > 48 KB dynamic shared memory; returns a cudaError_t
 int trace_blocks_per_sm(bool count);
 int shadow_blocks_per_sm(bool count);
 // micro-benchmarks

@@ -75,7 +75,8 @@ struct SmemTables {
   rh_light lights[kSmemLights];
 };
 static_assert(sizeof(rh_material) == 96 && sizeof(rh_light) == 64, "table record sizes");
-static_assert(sizeof(SmemTables) <= 48 * 1024, "static shared memory budget");
+static_assert(sizeof(SmemTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
+extern __shared__ __align__(16) unsigned char rh_smem[];  // SmemTables, then per-warp pools (shadow kernel)
 
 __device__ __forceinline__ void copy16(void* dst, const void* src, uint32_t bytes) {
   uint4* d = (uint4*)dst;
@@ -152,8 +153,8 @@ __device__ __forceinline__ bool slab(const Ray& r, const V3& inv, double lx, dou
 // Conservative float version of the same test, used only to CULL.  The boxes are the double boxes
 // rounded outward; the ray origin is widened to [o - e, o + e] with
 //   e = 2^-21 * (max|o_k| + largest |box coordinate| in the scene),
-// which covers the float rounding of the origin, of 1/d, of origin*(1/d) and of the fused
-// multiply-add (five roundings, each <= 2^-24 relative to |o| + |plane|; e allows eight).  `lo` always pairs with o+e and `hi` with o-e: for
+// which covers the float roundings of the origin, of o +- e, of d, of 1/d, of origin*(1/d) and of
+// the fused multiply-add (seven roundings, each <= 2^-24 relative to |o| + |plane|; e allows eight).  `lo` always pairs with o+e and `hi` with o-e: for
 // either sign of d that moves the entry distance down and the exit distance up.  So whenever the
 // exact test passes, this one passes; the converse errors only make the traversal look at a few
 // more triangles, each of which then gets the exact double test.  Rays with a zero (or denormal)
@@ -172,16 +173,17 @@ __device__ __forceinline__ bool degenerate_dir(const V3& d) {
 
 __device__ __forceinline__ RayF make_rayf(const Ray& r, float abs_max) {
   RayF f;
-  const double e = 4.76837158203125e-07 * (fmax(fmax(fabs(r.o.x), fabs(r.o.y)), fabs(r.o.z)) + (double)abs_max);
-  f.ix = (float)(1.0 / r.d.x);
-  f.iy = (float)(1.0 / r.d.y);
-  f.iz = (float)(1.0 / r.d.z);
-  f.pix = (float)(r.o.x + e) * f.ix;
-  f.piy = (float)(r.o.y + e) * f.iy;
-  f.piz = (float)(r.o.z + e) * f.iz;
-  f.mix = (float)(r.o.x - e) * f.ix;
-  f.miy = (float)(r.o.y - e) * f.iy;
-  f.miz = (float)(r.o.z - e) * f.iz;
+  const float e = 4.76837158203125e-07f * ((float)fmax(fmax(fabs(r.o.x), fabs(r.o.y)), fabs(r.o.z)) * 1.0000002f + abs_max);
+  f.ix = __frcp_rn((float)r.d.x);  // two roundings (d -> float, reciprocal): still inside e's budget of eight
+  f.iy = __frcp_rn((float)r.d.y);
+  f.iz = __frcp_rn((float)r.d.z);
+  const float ox = (float)r.o.x, oy = (float)r.o.y, oz = (float)r.o.z;
+  f.pix = (ox + e) * f.ix;
+  f.piy = (oy + e) * f.iy;
+  f.piz = (oz + e) * f.iz;
+  f.mix = (ox - e) * f.ix;
+  f.miy = (oy - e) * f.iy;
+  f.miz = (oz - e) * f.iz;
   return f;
 }
 
@@ -278,16 +280,19 @@ __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint3
 
 // KDTree.hs:96-107 rayInter, ordered and pruned, culling with the conservative float boxes.
 // Subtrees are skipped only when their entry distance exceeds `bound` (the best t so far times
-// 1 + 1e-7, or the light distance).  Returns true when the sink asked to stop (any-hit).
+// 1 + 1e-7, or the light distance), both when they are first met and again when they are popped.
+// "while-while" form: a lane that reaches a leaf waits at the end of the inner loop until the
+// other lanes of its warp hold a leaf too (or are done), so the long triangle loop runs with as
+// many lanes as possible.  Returns true when the sink asked to stop (any-hit).
 template <bool COUNT, class Sink>
 __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const RayF& f, double& bound, Sink& sink,
-                                         uint2* stack, Cnt<COUNT>& cnt) {
+                                         uint4* stack, Cnt<COUNT>& cnt) {
   int sp = 0;
   uint32_t ref = root, first = 0;
   const rh_tri* tris = cx.S->tris;
   const uint32_t n_smem = cx.S->n_smem_nodes;
   for (;;) {
-    if (!(ref & kLeafBit)) {
+    while (!(ref & kLeafBit)) {
       const float4* np = ref < n_smem ? (const float4*)&cx.sm->nodes[ref] : (const float4*)&cx.S->wide32[ref];
       const float4 b0 = np[0], b1 = np[1], b2 = np[2];
       const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
@@ -305,31 +310,37 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
       }
       if (h0 && h1) {
         if (tm1 < tm0) {
-          stack[sp++] = make_uint2(cw.x, cw.z);
+          stack[sp++] = make_uint4(cw.x, cw.z, __float_as_uint(tm0), 0);
           ref = cw.y;
           first = cw.w;
         } else {
-          stack[sp++] = make_uint2(cw.y, cw.w);
+          stack[sp++] = make_uint4(cw.y, cw.w, __float_as_uint(tm1), 0);
           ref = cw.x;
           first = cw.z;
         }
-        continue;
-      }
-      if (h0) {
+      } else if (h0) {
         ref = cw.x;
         first = cw.z;
-        continue;
-      }
-      if (h1) {
+      } else if (h1) {
         ref = cw.y;
         first = cw.w;
-        continue;
+      } else {
+        uint4 e;
+        do {
+          if (sp == 0) return false;
+          e = stack[--sp];
+        } while (__uint_as_float(e.z) > fb);
+        ref = e.x;
+        first = e.y;
       }
-    } else {
-      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
     }
-    if (sp == 0) return false;
-    const uint2 e = stack[--sp];
+    if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+    const float fb = __double2float_ru(bound);
+    uint4 e;
+    do {
+      if (sp == 0) return false;
+      e = stack[--sp];
+    } while (__uint_as_float(e.z) > fb);
     ref = e.x;
     first = e.y;
   }
@@ -339,7 +350,7 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
 // rays with a zero direction component (centre row/column of the image) and
 // RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line.
 template <bool COUNT, class Sink>
-__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, uint2* stack,
+__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, uint4* stack,
                                             Cnt<COUNT>& cnt) {
   const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
   int sp = 0;
@@ -363,11 +374,11 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       }
       if (h0 && h1) {
         if (tm1 < tm0) {
-          stack[sp++] = make_uint2(cw.x, cw.z);
+          stack[sp++] = make_uint4(cw.x, cw.z, 0, 0);
           ref = cw.y;
           first = cw.w;
         } else {
-          stack[sp++] = make_uint2(cw.y, cw.w);
+          stack[sp++] = make_uint4(cw.y, cw.w, 0, 0);
           ref = cw.x;
           first = cw.z;
         }
@@ -387,7 +398,7 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
     }
     if (sp == 0) return false;
-    const uint2 e = stack[--sp];
+    const uint4 e = stack[--sp];
     ref = e.x;
     first = e.y;
   }
@@ -430,7 +441,7 @@ __device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, dou
 
 // RayHs.hs:58-71 closestIntersection over the object list.
 template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, uint2* stack,
+__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, uint4* stack,
                                             Cnt<COUNT>& cnt) {
   const RayF f = make_rayf(r, cx.S->abs_max);
   best.t = __longlong_as_double(0x7ff0000000000000LL);
@@ -464,7 +475,7 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
 
 // RayHs.hs:74-87 shadowIntersection: true when some non-emitter object has a hit in front of the light.
 template <bool COUNT>
-__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, uint2* stack,
+__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, uint4* stack,
                                          Cnt<COUNT>& cnt) {
   const RayF f = make_rayf(r, cx.S->abs_max);
   AnyHit sink;
@@ -771,13 +782,13 @@ __device__ __forceinline__ Ray camera_ray(const CameraParams& cam, double px, do
 
 // ------------------------------------------------------------------ K1/K2/K4/K5
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ SceneView S,
+__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(const __grid_constant__ SceneView S,
                                                        const __grid_constant__ CameraParams cam,
                                                        const __grid_constant__ ChunkParams P) {
-  __shared__ SmemTables sm;
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
   Ctx cx;
   stage_tables(sm, S, cx);
-  uint2 stack[kStack];
+  uint4 stack[kStack];
   Cnt<COUNT> cnt;
   cnt.zero();
   const uint32_t lane = threadIdx.x & 31;
@@ -882,13 +893,54 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ S
 }
 
 // ------------------------------------------------------------------ K3: accumDiffuse (RayHs.hs:89-97)
+// Light.hs:12-17
+__device__ __forceinline__ void light_at(const rh_light& L, const V3& p, V3& ld, V3& lc) {
+  if (L.kind == RH_LIGHT_DIRECTIONAL) {  // Light.hs:14
+    ld = ld3(L.vec);
+    lc = ld3(L.color);
+  } else {  // Light.hs:15-17
+    const V3 lp = ld3(L.vec);
+    const double dd = sqrt(sqrDist(lp, p));
+    const double s = 1.0 + dd / L.radius;
+    const double falloff = 1.0 / (s * s);
+    ld = mul(1 / dd, lp - p);
+    lc = mul(falloff, ld3(L.color));
+  }
+}
+__device__ __forceinline__ V3 light_dir(const rh_light& L, const V3& p) {
+  if (L.kind == RH_LIGHT_DIRECTIONAL) return ld3(L.vec);
+  const V3 lp = ld3(L.vec);
+  const double dd = sqrt(sqrDist(lp, p));  // dist, Vec.hs:122
+  return mul(1 / dd, lp - p);
+}
+
+// Shadow-ray setup shared by the phases below: the same arithmetic every time, so the same ray.
+struct ShadowRay {
+  Ray r;
+  AnyHit sink;
+  double far;
+};
+__device__ __forceinline__ ShadowRay make_shadow_ray(const rh_light& L, const V3& p, const V3& ld) {
+  ShadowRay s;
+  s.r = rayEps(p, ld);  // RayHs.hs:93
+  s.sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
+  s.sink.lpos = ld3(L.vec);
+  s.sink.dl2 = s.sink.directional ? 0.0 : sqrDist(s.r.o, s.sink.lpos);
+  // Hits farther than the light cannot be in front of it.  A point light's direction is unit to
+  // 1e-15 and the origin sits 1e-6 along it, so the light is at t = |L - o| (1 +- 1e-15) < sqrt(dl2) * 1.000001.
+  s.far = s.sink.directional ? __longlong_as_double(0x7ff0000000000000LL) : sqrt(s.sink.dl2) * 1.000001;
+  return s;
+}
+
+// Simple form: one shaded hit per lane, lights in sequence, each query run to completion.
+// Used when the scene has more than 32 lights (the pooled kernel keeps one visibility bit per light).
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ SceneView S,
-                                                        const __grid_constant__ ChunkParams P) {
-  __shared__ SmemTables sm;
+__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_simple(const __grid_constant__ SceneView S,
+                                                                                       const __grid_constant__ ChunkParams P) {
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
   Ctx cx;
   stage_tables(sm, S, cx);
-  uint2 stack[kStack];
+  uint4 stack[kStack];
   Cnt<COUNT> cnt;
   cnt.zero();
   const uint32_t lane = threadIdx.x & 31;
@@ -912,17 +964,7 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ 
     for (uint32_t li = 0; li < S.n_lights; li++) {
       const rh_light& L = cx.lights[li];
       V3 ld, lc;
-      if (L.kind == RH_LIGHT_DIRECTIONAL) {  // Light.hs:14
-        ld = ld3(L.vec);
-        lc = ld3(L.color);
-      } else {  // Light.hs:15-17
-        const V3 lp = ld3(L.vec);
-        const double dd = sqrt(sqrDist(lp, p));
-        const double s = 1.0 + dd / L.radius;
-        const double falloff = 1.0 / (s * s);
-        ld = mul(1 / dd, lp - p);
-        lc = mul(falloff, ld3(L.color));
-      }
+      light_at(L, p, ld, lc);
       // diffuse (Material.hs:31-33) = (max (l.n) 0 / pi) * (cd (*) lc): exactly zero when l.n <= 0, whether
       // or not the point is shadowed, so the occlusion query cannot change the sum and is skipped.
       const double ldn = dot(ld, n);
@@ -936,6 +978,180 @@ __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ 
     }
     const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
     accumulate(P, sbits & 0x7fffffffu, w, total);
+  }
+  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
+  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
+  flush_counters<COUNT>(cnt, P.counters, 1);
+}
+
+// Pooled form.  Most shadow rays never reach a triangle: the light is below the horizon, a
+// wall plane answers, or the ray misses every mesh's root box.  Running those in the same loop
+// as the rays that do walk a tree leaves most lanes of a warp idle (ncu: 16.6 active threads per
+// instruction in the dragon region).  So each warp takes kShadowT*32 shaded hits at a time and,
+// light by light (rays towards one light from neighbouring samples stay coherent),
+//   phase 1  every lane settles the cheap cases of its own hits for that light and appends the
+//            hits that need a tree walk to a warp-local pool in shared memory
+//            (ballot + prefix-popcount compaction);
+//   phase 2  the pool is walked in full rounds of 32, every lane on a ray that needs it; what is
+//            left over (< 32) stays pooled and joins the next light's rays.  An occluded pair
+//            sets its bit in the hit's visibility word (shared-memory atomicOr);
+//   phase 3  every lane folds the lights of its own hits in order (accumDiffuse's foldl) with
+//            those bits and adds w * (ambient + sum) to the sample.
+constexpr int kShadowT = RH_SHADOW_T;
+struct ShadowWarpSmem {
+  uint32_t vis[32 * kShadowT];       // bit li: light li is occluded for this hit
+  uint16_t pool[32 * kShadowT + 32]; // hit-in-batch | light << 8
+};
+static_assert(32 * kShadowT <= 256, "pool entries keep the hit index in 8 bits");
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(const __grid_constant__ SceneView S,
+                                                                                const __grid_constant__ ChunkParams P) {
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
+  ShadowWarpSmem* wsm = reinterpret_cast<ShadowWarpSmem*>(rh_smem + sizeof(SmemTables));
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  uint4 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  const uint32_t lane = threadIdx.x & 31;
+  ShadowWarpSmem& ws = wsm[threadIdx.x >> 5];
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
+  const size_t cap = P.q_shadow.capacity;
+  const uint32_t n_lights = S.n_lights, n_objects = S.n_objects;
+  const double2* qp = P.q_shadow.plane;
+  unsigned long long n_culled = 0;
+
+  // phase 2 body: one pooled (hit, light) pair
+  auto walk = [&](uint32_t base, uint32_t e) {
+    const uint32_t j = e & 0xff, li = e >> 8;
+    const uint32_t item = base + j;
+    const double2 a = qp[item], b = qp[cap + item];
+    const V3 p = mk(a.x, a.y, b.x);
+    const rh_light& L = cx.lights[li];
+    const ShadowRay sr = make_shadow_ray(L, p, light_dir(L, p));
+    const bool exact = P.exact_boxes || degenerate_dir(sr.r.d);
+    const RayF f = make_rayf(sr.r, S.abs_max);
+    bool hit = false;
+    for (uint32_t oi = 0; oi < n_objects && !hit; oi++) {
+      const DObject& ob = cx.objects[oi];
+      if (ob.kind != RH_OBJ_MESH || ob.is_emitter || ob.root == kEmpty) continue;
+      double bound = sr.far;
+      AnyHit sink = sr.sink;
+      hit = exact ? traverse_exact<COUNT>(cx, ob.root, sr.r, bound, sink, stack, cnt)
+                  : traverse<COUNT>(cx, ob.root, sr.r, f, bound, sink, stack, cnt);
+    }
+    if (hit) atomicOr(&ws.vis[j], 1u << li);
+  };
+
+  const uint32_t total_warps = gridDim.x * (kShadowBlock / 32);
+  for (;;) {
+    // guided self-scheduling: large batches (fuller pool rounds) while plenty of work is left, single
+    // rows of 32 near the end of the queue and for small launches, so no warp ends up with a long tail
+    uint32_t base = 0, T = 1;
+    if (lane == 0) {
+      const uint32_t seen = *(volatile uint32_t*)&ctl->shadow_cursor[P.pass];
+      const uint32_t left = seen < n_items ? n_items - seen : 0;
+      T = min((uint32_t)kShadowT, max(1u, left / (total_warps * 32u * 2u)));
+      base = atomicAdd(&ctl->shadow_cursor[P.pass], 32u * T);
+    }
+    base = __shfl_sync(kFull, base, 0);
+    T = __shfl_sync(kFull, T, 0);
+    if (base >= n_items) break;
+    const uint32_t n_here = min(32u * T, n_items - base);
+    for (uint32_t t = 0; t < T; t++) ws.vis[t * 32 + lane] = 0;
+    uint32_t pool_n = 0;
+    for (uint32_t li = 0; li < n_lights; li++) {
+      const rh_light& L = cx.lights[li];
+      // ---- phase 1: cheap cases, pool the rest
+      for (uint32_t t = 0; t < T; t++) {
+        const uint32_t j = t * 32 + lane;
+        bool need_walk = false;
+        if (j < n_here) {
+          const uint32_t item = base + j;
+          const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
+          const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
+          const V3 ld = light_dir(L, p);
+          if (dot(ld, n) <= 0) {
+            n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
+          } else {
+            const ShadowRay sr = make_shadow_ray(L, p, ld);
+            const bool exact = P.exact_boxes || degenerate_dir(sr.r.d);
+            const RayF f = make_rayf(sr.r, S.abs_max);
+            const float ffar = __double2float_ru(sr.far);
+            bool shadowed = false;
+            for (uint32_t oi = 0; oi < n_objects && !shadowed; oi++) {
+              const DObject& ob = cx.objects[oi];
+              if (ob.is_emitter) continue;  // isOccluder, RayHs.hs:81-82
+              const int kind = ob.kind;
+              if (kind == RH_OBJ_MESH) {
+                const uint32_t root = ob.root;
+                if (root == kEmpty || need_walk) continue;
+                if (exact) {
+                  need_walk = true;
+                } else {  // the mesh's own box (slot 0 of its super-root)
+                  const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
+                  const float4 b0 = np[0], b1 = np[1];
+                  float tm;
+                  RH_CNT(nodes, 1);
+                  RH_CNT(box, 1);
+                  need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
+                }
+              } else {
+                double time;
+                RH_CNT(prim, 1);
+                const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(sr.r, ob, sr.far, time) : sphere_time(sr.r, ob, time);
+                shadowed = hit && sr.sink.in_front(sr.r, time);
+              }
+            }
+            if (shadowed) {
+              ws.vis[j] |= 1u << li;  // only this lane touches vis[j] during phase 1
+              need_walk = false;
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(kFull, need_walk);
+        if (need_walk) ws.pool[pool_n + __popc(m & ((1u << lane) - 1))] = (uint16_t)(j | (li << 8));
+        pool_n += __popc(m);
+      }
+      __syncwarp();
+      // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
+      const bool last = (li + 1 == n_lights);
+      const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
+      for (uint32_t i = lane; i < n_full; i += 32) walk(base, ws.pool[i]);
+      __syncwarp();
+      const uint32_t rem = pool_n - n_full;
+      uint16_t keep = 0;
+      if (lane < rem) keep = ws.pool[n_full + lane];
+      __syncwarp();
+      if (lane < rem) ws.pool[lane] = keep;
+      pool_n = rem;
+      __syncwarp();
+    }
+    // ---- phase 3: accumDiffuse's fold over the lights, in order
+    for (uint32_t t = 0; t < T; t++) {
+      const uint32_t j = t * 32 + lane;
+      if (j >= n_here) continue;
+      const uint32_t item = base + j;
+      const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
+      const uint32_t sbits = P.q_shadow.sample[item];
+      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+      const double w = e.y;
+      const uint32_t vis = ws.vis[j];
+      V3 acc = mk(0, 0, 0);  // foldl ... black lts
+      for (uint32_t li = 0; li < n_lights; li++) {
+        if ((vis >> li) & 1u) continue;  // Just _ -> black
+        V3 ld, lc;
+        light_at(cx.lights[li], p, ld, lc);
+        const double ldn = dot(ld, n);
+        if (ldn <= 0) continue;
+        acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+      }
+      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
+      accumulate(P, sbits & 0x7fffffffu, w, total);
+    }
+    __syncwarp();
   }
   for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
   if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
@@ -1050,17 +1266,41 @@ __global__ void dfma_bench_kernel(double* sink, int iters) {
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
+constexpr size_t kTraceSmem = sizeof(SmemTables);
+constexpr size_t kShadowSmem = sizeof(SmemTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem);
+
+int configure_kernels() {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn, size_t bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  set((const void*)trace_kernel<true>, kTraceSmem);
+  set((const void*)trace_kernel<false>, kTraceSmem);
+  set((const void*)shadow_kernel<true>, kShadowSmem);
+  set((const void*)shadow_kernel<false>, kShadowSmem);
+  set((const void*)shadow_kernel_simple<true>, kShadowSmem);
+  set((const void*)shadow_kernel_simple<false>, kShadowSmem);
+  return (int)e;
+}
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
   if (count)
-    trace_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, cam, P);
+    trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, (cudaStream_t)stream>>>(S, cam, P);
   else
-    trace_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, cam, P);
+    trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, (cudaStream_t)stream>>>(S, cam, P);
 }
 void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream) {
-  if (count)
-    shadow_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, P);
-  else
-    shadow_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(S, P);
+  const bool simple = S.n_lights > 32 || RH_SHADOW_POOL == 0;
+  if (simple) {
+    if (count)
+      shadow_kernel_simple<true><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
+    else
+      shadow_kernel_simple<false><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
+  } else {
+    if (count)
+      shadow_kernel<true><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
+    else
+      shadow_kernel<false><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
+  }
 }
 void launch_resolve(const ChunkParams& P, void* stream) {
   const uint32_t n_pixels = P.n_rows * P.width;
@@ -1077,17 +1317,17 @@ void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int h
 int trace_blocks_per_sm(bool count) {
   int n = 0;
   if (count)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<true>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<true>, kTraceBlock, kTraceSmem);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<false>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<false>, kTraceBlock, kTraceSmem);
   return n;
 }
 int shadow_blocks_per_sm(bool count) {
   int n = 0;
   if (count)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<true>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<true>, kShadowBlock, kShadowSmem);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<false>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<false>, kShadowBlock, kShadowSmem);
   return n;
 }
 void launch_gather_bench(const double2* buf, uint64_t n_records, uint32_t loads_per_thread, double2* sink, int grid, int block,

@@ -100,6 +100,7 @@ struct Device {
       RH_CUDA(cudaEventCreateWithFlags(&ev_up[k], cudaEventDisableTiming));
       RH_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
     }
+    RH_CUDA((cudaError_t)configure_kernels());
     for (int c = 0; c < 2; c++) {
       grid_trace[c] = n_sms * std::max(1, trace_blocks_per_sm(c != 0));
       grid_shadow[c] = n_sms * std::max(1, shadow_blocks_per_sm(c != 0));
