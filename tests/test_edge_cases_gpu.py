@@ -1,0 +1,139 @@
+"""GPU parity on hand-built scenes that reach the code paths the shipped scenes do not: empty inputs,
+Empty tree children, every material kind, both projections, > 32 lights (simple shadow kernel),
+> 64 objects (tables read from global memory), deep recursion with Transparent forks, the synthetic C5 scene."""
+import numpy as np
+import pytest
+
+import rayhs_b200 as rh
+from oracle.orc import OracleScene
+from tests.util import RawScene, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def both(rs, w, h, depth=None, spp=1, offsets=None, **kw):
+    depth = rs.max_depth if depth is None else depth
+    job = rh.Rendering(rs, rs.camera, w, h, depth)
+    img = rh.render(job, spp=spp, offsets=offsets, want_hit_ids=True, **kw)
+    ref = OracleScene(rs.raw).render(rs.camera, w, h, depth, spp=spp, offsets=offsets)
+    assert np.array_equal(img.hit_ids.reshape(h, w, spp, 2), ref["hit_ids"]), "hit ids"
+    assert_parity(img.pixels, ref["rgb_u8"])
+    got = tuple(img.stats[k] for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"))
+    want = tuple(ref["rays"][k] for k in ("primary", "reflect", "probe", "exit", "shadow"))
+    assert got == want, (got, want)
+    return img, ref
+
+
+QUAD = dict(positions=[(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)], normals=[(0, 0, -1)] * 4,
+            uvs=[(0, 0), (1, 0), (1, 1), (0, 1)], indices=[0, 1, 2, 0, 2, 3])
+
+
+def grid_mesh(n, z=0.0, wobble=0.0, seed=1):
+    """n x n quads (2 n^2 triangles) on [-1,1]^2: enough triangles for a real tree (>= 20 per split)."""
+    rng = np.random.RandomState(seed)
+    xs = np.linspace(-1, 1, n + 1)
+    pos = np.array([(x, y, z + wobble * rng.uniform(-1, 1)) for y in xs for x in xs])
+    nrm = np.tile((0.0, 0.0, -1.0), (len(pos), 1)) + 0.2 * rng.uniform(-1, 1, size=(len(pos), 3))
+    uv = (pos[:, :2] + 1) / 2
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i
+            idx += [a, a + 1, a + n + 2, a, a + n + 2, a + n + 1]
+    return dict(positions=pos, normals=nrm, uvs=uv, indices=idx)
+
+
+def test_empty_scene_and_no_lights():
+    rs = RawScene([], [{"kind": "diffuse"}], [])
+    img, _ = both(rs, 33, 17)
+    assert not img.pixels.any()
+    rs = RawScene([{"kind": "sphere", "center": (0, 0, 0), "radius": 1.0}], [{"kind": "diffuse", "color1": (0.5, 1.0, 2.0)}], [])
+    img, _ = both(rs, 40, 40)
+    assert tuple(img.pixels[20, 20]) == (25, 51, 102)  # ambient only: 0.2 * cd
+
+
+def test_mesh_without_triangles_is_empty_tree():
+    rs = RawScene([{"kind": "mesh", "positions": np.zeros((0, 3)), "indices": []},
+                   {"kind": "plane", "point": (0, 0, 2), "normal": (0, 0, -1), "tangent": (1, 0, 0)}],
+                  [{"kind": "diffuse"}], [{"kind": "point", "vec": (0, 1, 0), "color": (5, 5, 5), "radius": 1.0}])
+    both(rs, 32, 24)
+
+
+def test_all_material_kinds_and_transparent_recursion():
+    mats = [{"kind": "diffuse", "color1": (0.9, 0.2, 0.2)}, {"kind": "plastic", "ior": 1.9, "color1": (0.2, 0.9, 0.2)},
+            {"kind": "mirror", "ior": 4.0}, {"kind": "emmit", "color1": (3, 2, 1)}, {"kind": "transparent", "ior": 1.5},
+            {"kind": "shownormal"}, {"kind": "showuv"},
+            {"kind": "plastic", "ior": 1.3, "cmap": "checker", "color1": (1, 1, 1), "color2": (0.1, 0.1, 0.1), "size": 0.4}]
+    objs = [{"kind": "sphere", "center": (-1.5 + 0.75 * i, 0.2 * (i % 2), 0.5), "radius": 0.33, "material": i} for i in range(7)]
+    objs += [{"kind": "sphere", "center": (0.0, 0.9, 0.0), "radius": 0.4, "material": 4},    # transparent in front of transparent
+             {"kind": "plane", "point": (0, -0.6, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 7},
+             {"kind": "plane", "point": (0, 0, 3), "normal": (0, 0, -1), "tangent": (1, 0, 0), "material": 0},
+             dict(kind="mesh", material=1, **grid_mesh(8, z=1.5, wobble=0.05))]
+    lights = [{"kind": "point", "vec": (0, 2, -1), "color": (20, 20, 20), "radius": 0.5},
+              {"kind": "directional", "vec": (0.3, -1, 0.5), "color": (0.6, 0.6, 0.7)}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0, 0.3, -3), "target": (0, 0, 0.5)})
+    for depth in (0, 1, 3, 5):
+        img, ref = both(rs, 160, 120, depth=depth)
+    assert ref["rays"]["probe"] > 0 and ref["rays"]["exit"] > 0 and ref["rays"]["reflect"] > 0
+
+
+def test_orthographic_camera_and_uv_mesh_texture():
+    tex = np.random.RandomState(3).uniform(0, 1, size=(5, 7, 3))
+    mats = [{"kind": "diffuse", "cmap": "texture", "texture": 0}, {"kind": "plastic", "cmap": "texture", "texture": 0, "ior": 1.5}]
+    objs = [dict(kind="mesh", material=0, **grid_mesh(6, z=0.3, wobble=0.1)),
+            {"kind": "sphere", "center": (0, 0, -0.5), "radius": 0.5, "material": 1}]
+    lights = [{"kind": "directional", "vec": (0.2, 0.3, 1.0), "color": (1.5, 1.5, 1.5)}]
+    # Projection.hs:30-32: the orthographic view plane is in PIXEL units, so keep the scene pixel-sized
+    for o in objs:
+        if o["kind"] == "mesh":
+            o["positions"] = np.asarray(o["positions"]) * 30
+        else:
+            o["center"] = tuple(30 * c for c in o["center"])
+            o["radius"] *= 30
+    rs = RawScene(objs, mats, lights, textures=[tex],
+                  camera={"position": (3, 2, -80), "target": (0, 0, 0), "projection": "orthographic"})
+    both(rs, 96, 64)
+
+
+def test_more_than_32_lights_uses_the_simple_shadow_kernel():
+    rng = np.random.RandomState(5)
+    lights = [{"kind": "point", "vec": tuple(rng.uniform(-1, 1, 3) * (1.5, 0.5, 1.5) + (0, 1.5, 0)), "color": (0.4, 0.4, 0.4),
+               "radius": 0.5} for _ in range(40)]
+    objs = [{"kind": "plane", "point": (0, -0.5, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0)},
+            dict(kind="mesh", material=0, **grid_mesh(5, z=0.0, wobble=0.2)),
+            {"kind": "sphere", "center": (0.5, 0, 0), "radius": 0.3}]
+    rs = RawScene(objs, [{"kind": "diffuse", "color1": (0.8, 0.8, 0.8)}], lights, camera={"position": (0, 1, -3)})
+    both(rs, 80, 60)
+
+
+def test_more_than_64_objects_reads_tables_from_global_memory():
+    rng = np.random.RandomState(9)
+    mats = [{"kind": k, "ior": 1.5, "color1": tuple(rng.uniform(0.2, 1, 3))} for k in ("diffuse", "plastic", "mirror")] * 30
+    objs = [{"kind": "sphere", "center": tuple(rng.uniform(-1, 1, 3)), "radius": float(rng.uniform(0.03, 0.12)), "material": i % 90}
+            for i in range(150)]
+    objs.append({"kind": "plane", "point": (0, -1.2, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 0})
+    lights = [{"kind": "point", "vec": (0, 3, -2), "color": (60, 60, 60), "radius": 0.5}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0, 0, -4)})
+    both(rs, 120, 90)
+
+
+def test_synthetic_stress_scene_small():
+    """BASELINE.json configs[4] at reduced size: random triangles + spheres + checker floor, dragon.json camera/lights."""
+    sc = rh.Scene.synthetic(30000, 40)
+    w, h = 192, 108
+    job = rh.renderingFromScene(sc, w, h)
+    img = rh.render(job, want_hit_ids=True)
+    ref = OracleScene(sc.raw).render(sc.camera, w, h, sc.max_depth)
+    assert np.array_equal(img.hit_ids.reshape(h, w, 2), ref["hit_ids"].reshape(h, w, 2))
+    assert_parity(img.pixels, ref["rgb_u8"])
+
+
+def test_centre_row_and_column_rays_take_the_exact_path():
+    """Rays with a zero direction component (App. A-N1): cube faces at the camera's x and y, NaN slab arithmetic."""
+    c = dict(positions=[(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)],
+             indices=[0, 1, 2, 0, 2, 3, 4, 6, 5, 4, 7, 6, 0, 4, 5, 0, 5, 1, 3, 2, 6, 3, 6, 7, 0, 3, 7, 0, 7, 4, 1, 5, 6, 1, 6, 2])
+    g = grid_mesh(6, z=2.0)   # vertices on x = 0 and y = 0 lines, splits land exactly on the centre ray
+    rs = RawScene([dict(kind="mesh", material=0, **c), dict(kind="mesh", material=0, **g)], [{"kind": "diffuse"}],
+                  [{"kind": "point", "vec": (0, 0, -1), "color": (3, 3, 3), "radius": 1.0}])
+    both(rs, 64, 64)
+    both(rs, 65, 63)

@@ -1,0 +1,63 @@
+"""GPU parity at BASELINE.json's full sizes.  The oracle cannot render these frames in seconds, so it renders a
+bounded sample of rows of the SAME frame (same camera, same offsets) and those rows must match; on top of that,
+size-independent properties of the path: the bytes do not depend on the chunking or on the shard count."""
+import numpy as np
+import pytest
+
+import rayhs_b200 as rh
+from tests.util import assert_parity, compare_images, load_scene, oracle_for
+
+pytestmark = pytest.mark.gpu
+
+
+def check_rows(name, w, h, spp, row_step, seed=24):
+    sc = load_scene(name)
+    job = rh.renderingFromScene(sc, w, h)
+    off = rh.sample_offsets(w * h, spp, seed) if spp > 1 else None
+    img = rh.render(job, spp=spp, offsets=off, want_hit_ids=(spp == 1))
+    ref = oracle_for(sc).render(sc.camera, w, h, sc.max_depth, spp=spp, offsets=off, rows=(row_step // 2, h, row_step),
+                                want_ids=(spp == 1))
+    rows = np.arange(row_step // 2, h, row_step)
+    m = assert_parity(img.pixels[rows], ref["rgb_u8"][rows], name)
+    if spp == 1:
+        assert np.array_equal(img.hit_ids[rows].reshape(len(rows), w, 2), ref["hit_ids"][rows].reshape(len(rows), w, 2))
+    return img, m
+
+
+def test_c1_cornell_box_native_resolution_full_frame():
+    """configs[0]: data/cornellBox.json at 512x512, 1 spp — the whole frame against the oracle."""
+    sc = load_scene("cornellBox")
+    assert (sc.width, sc.height) == (512, 512)
+    job = rh.renderingFromScene(sc)
+    img = rh.rayTrace(job, want_hit_ids=True)
+    ref = oracle_for(sc).render(sc.camera, 512, 512, sc.max_depth)
+    assert np.array_equal(img.hit_ids.reshape(512, 512, 2), ref["hit_ids"].reshape(512, 512, 2))
+    m = assert_parity(img.pixels, ref["rgb_u8"])
+    assert m["exact"] > 0.9999
+    assert tuple(img.pixels[256, 256]) == (199, 199, 199)   # SURVEY App. D known answer
+
+
+@pytest.mark.parametrize("name", ["texture", "transform", "dragon_low"])
+def test_c2_c3_at_1920x1080(name):
+    """configs[1], configs[2]: every 24th row of the 1920x1080 frame against the oracle."""
+    check_rows(name, 1920, 1080, 1, 24)
+
+
+def test_c4_dragon_4k_16spp_rows_and_invariances():
+    """configs[3]: dragon full-res at 3840x2160, 16 spp — every 108th row against the oracle; then the frame must not
+    change with the chunk size or with an 8-way band split (same offsets)."""
+    w, h, spp = 3840, 2160, 16
+    img, m = check_rows("dragon_full", w, h, spp, 108)
+    sc = load_scene("dragon_full")
+    job = rh.renderingFromScene(sc, w, h)
+    off = rh.sample_offsets(w * h, spp, 24)
+    small = rh.render(job, spp=spp, offsets=off, chunk_samples=3 << 20)
+    assert np.array_equal(small.pixels, img.pixels)
+    G, bh = 8, 16
+    parts = [rh.render(job, spp=spp, offsets=off, shard_index=g, shard_count=G, band_height=bh).pixels for g in range(G)]
+    full = rh.assemble_bands(parts, h, bh)
+    assert np.array_equal(full, img.pixels)
+    # tiled offsets (declared deviation for throughput runs): same image statistics, not the same bytes
+    tile = rh.sample_offsets(64 * 64, spp, 24)
+    t = rh.render(job, spp=spp, offsets=tile, offset_tile=64)
+    assert compare_images(t.pixels, img.pixels)["psnr"] > 35
