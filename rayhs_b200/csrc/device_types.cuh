@@ -11,7 +11,7 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;    // KDTree.hs:61 `Empty`
 constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 31 bits = triangle count
 constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
-constexpr int kStack = 104;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82)
+constexpr int kStack = 112;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82) + leaf refinement levels
 #ifndef RH_SMEM_NODES
 #define RH_SMEM_NODES 448
 #endif
@@ -42,10 +42,14 @@ constexpr int kShadowBlock = RH_SHADOW_BLOCK, kShadowMinBlocks = RH_SHADOW_MINB;
 struct __align__(16) WideNode {
   double box[12];     // child0 lo.xyz hi.xyz, child1 lo.xyz hi.xyz
   uint32_t child[2];  // kEmpty | kLeafBit|count | wide-node index
-  uint32_t first[2];  // leaf child: first triangle slot.  Slots follow left-to-right leaf order, so
-                      // `first` also carries the reference's tie rule (KDTree.hs:109-115).
-  uint32_t pad_[4];
+  uint32_t first[2];  // leaf child: first triangle slot
+  uint32_t refine;    // bit c: child c's box is a culling refinement inside a reference leaf (not a reference box)
+  uint32_t pad_[3];
 };
+#ifndef RH_SUBLEAF
+#define RH_SUBLEAF 4  // reference leaves (< 20 triangles) are refined down to at most this many triangles per cull leaf
+#endif
+constexpr uint32_t kSubLeaf = RH_SUBLEAF;
 static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
 
 // 64-byte culling copy of a WideNode: the same two child boxes rounded OUTWARD to float.  The fp32

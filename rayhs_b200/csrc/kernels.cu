@@ -200,18 +200,26 @@ __device__ __forceinline__ bool slab32(const RayF& f, float lx, float ly, float 
 
 // Closest-hit candidate: key (t asc, leaf desc, position-in-leaf asc) inside one mesh
 // (KDTree.hs:109-115 right child wins ties; Geometry.hs:54-57 first minimum inside a leaf),
-// strict `<` across objects (RayHs.hs:67-71 first object wins ties).
+// strict `<` across objects (RayHs.hs:67-71 first object wins ties).  The device triangle record
+// carries both order keys: `pad_` = first slot of the reference leaf (leaves are numbered left to
+// right by it), `tri_id` = index in `triangles mesh`, which is also the order inside a leaf because
+// the build's list comprehensions keep the list order (KDTree.hs:85-88).  They are only read on an
+// exact tie in t.
 struct Closest {
   double t, u, v;
-  uint32_t slot, leaf_first;
+  uint32_t slot;
   int obj, cur_obj;
-  __device__ __forceinline__ bool offer(const Ray&, double tt, double uu, double vv, uint32_t s, uint32_t lf, double& bound) {
-    if (tt < t || (tt == t && obj == cur_obj && lf > leaf_first)) {
+  const rh_tri* tris;
+  __device__ __forceinline__ bool wins_tie(uint32_t s) const {
+    const uint2 mine = *(const uint2*)&tris[s].tri_id, held = *(const uint2*)&tris[slot].tri_id;  // (tri_id, leaf key)
+    return mine.y > held.y || (mine.y == held.y && mine.x < held.x);
+  }
+  __device__ __forceinline__ bool offer(const Ray&, double tt, double uu, double vv, uint32_t s, double& bound) {
+    if (tt < t || (tt == t && obj == cur_obj && wins_tie(s))) {
       t = tt;
       u = uu;
       v = vv;
       slot = s;
-      leaf_first = lf;
       obj = cur_obj;
       bound = tt * kPruneSlack;
     }
@@ -228,7 +236,7 @@ struct AnyHit {
     if (directional) return true;
     return dl2 > sqrDist(r.o, rayAt(r, tt));
   }
-  __device__ __forceinline__ bool offer(const Ray& r, double tt, double, double, uint32_t, uint32_t, double&) const {
+  __device__ __forceinline__ bool offer(const Ray& r, double tt, double, double, uint32_t, double&) const {
     return in_front(r, tt);
   }
 };
@@ -273,7 +281,7 @@ __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint3
     const double v = idet * vn;
     const double t = idet * tn;
     if (u < 0 || u > 1 || v < 0 || (u + v) > 1 || t < kEps) continue;
-    if (sink.offer(r, t, u, v, slot, first, bound)) return true;
+    if (sink.offer(r, t, u, v, slot, bound)) return true;
   }
   return false;
 }
@@ -361,16 +369,18 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       const double2* np = (const double2*)&cx.S->wide[ref];
       const double2 b0 = np[0], b1 = np[1], b2 = np[2], b3 = np[3], b4 = np[4], b5 = np[5];
       const uint4 cw = *(const uint4*)(np + 6);
+      const uint32_t refine = *(const uint32_t*)(np + 7);  // bit c: child c's box is a culling refinement inside a reference
+                                                           // leaf, not a box the reference tests: it always passes here
       RH_CNT(nodes, 2);  // a 128-byte record = two 64-byte units
       bool h0 = false, h1 = false;
       double tm0 = 0, tm1 = 0;
       if (cw.x != kEmpty) {
         RH_CNT(box, 1);
-        h0 = slab(r, inv, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, tm0) && !(tm0 > bound);
+        h0 = (refine & 1u) || (slab(r, inv, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, tm0) && !(tm0 > bound));
       }
       if (cw.y != kEmpty) {
         RH_CNT(box, 1);
-        h1 = slab(r, inv, b3.x, b3.y, b4.x, b4.y, b5.x, b5.y, tm1) && !(tm1 > bound);
+        h1 = (refine & 2u) || (slab(r, inv, b3.x, b3.y, b4.x, b4.y, b5.x, b5.y, tm1) && !(tm1 > bound));
       }
       if (h0 && h1) {
         if (tm1 < tm0) {
@@ -446,7 +456,8 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
   const RayF f = make_rayf(r, cx.S->abs_max);
   best.t = __longlong_as_double(0x7ff0000000000000LL);
   best.u = best.v = 0;
-  best.slot = best.leaf_first = 0;
+  best.slot = 0;
+  best.tris = cx.S->tris;
   best.obj = -1;
   const uint32_t n = cx.S->n_objects;
   for (uint32_t i = 0; i < n; i++) {
