@@ -82,6 +82,10 @@ struct SceneView {
   const rh_light* lights;
   const rh_texture* textures;
   const double* texels;
+  const uint32_t* lin_objs;     // objects scanned linearly in scene order (RayHs.hs:64-71): all of them, or all but the spheres
+  const uint32_t* sphere_refs;  // sphere tree leaves: object indices
+  uint32_t n_lin;
+  uint32_t sphere_root;         // super-root of the sphere tree or kEmpty (spheres are in lin_objs then)
   uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables

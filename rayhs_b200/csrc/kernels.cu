@@ -225,6 +225,16 @@ struct Closest {
     }
     return false;
   }
+  // A top-level sphere met while walking the sphere tree (any order): the reference's scan keeps the first
+  // object of the list among equal times (RayHs.hs:67-71), i.e. the lowest object index.
+  __device__ __forceinline__ bool offer_object(const Ray&, double tt, int o, double& bound) {
+    if (tt < t || (tt == t && o < obj)) {
+      t = tt;
+      obj = o;
+      bound = tt * kPruneSlack;
+    }
+    return false;
+  }
 };
 
 // Shadow candidate (RayHs.hs:74-87): any hit in front of the light ends the query.
@@ -239,6 +249,7 @@ struct AnyHit {
   __device__ __forceinline__ bool offer(const Ray& r, double tt, double, double, uint32_t, double&) const {
     return in_front(r, tt);
   }
+  __device__ __forceinline__ bool offer_object(const Ray& r, double tt, int, double&) const { return in_front(r, tt); }
 };
 
 // Mesh.hs:59-82 triangleIntersection over the `count` triangles of one leaf (Geometry.hs:54-57).
@@ -286,15 +297,34 @@ __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint3
   return false;
 }
 
+__device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, double& time);
+
+// Leaf of the sphere tree: `count` object indices at refs[first..]; each gets the reference's sphere test
+// (Geometry.hs:81-95).  Shadow queries skip emitters (isOccluder, RayHs.hs:81-82).
+template <bool COUNT, class Sink>
+__device__ __forceinline__ bool test_sphere_leaf(const Ctx& cx, uint32_t first, uint32_t count, const Ray& r, Sink& sink,
+                                                 double& bound, bool skip_emitters, Cnt<COUNT>& cnt) {
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t oi = __ldg(cx.S->sphere_refs + first + k);
+    const DObject& ob = cx.objects[oi];
+    if (skip_emitters && ob.is_emitter) continue;
+    RH_CNT(prim, 1);
+    double time;
+    if (sphere_time(r, ob, time) && sink.offer_object(r, time, (int)oi, bound)) return true;
+  }
+  return false;
+}
+
 // KDTree.hs:96-107 rayInter, ordered and pruned, culling with the conservative float boxes.
 // Subtrees are skipped only when their entry distance exceeds `bound` (the best t so far times
 // 1 + 1e-7, or the light distance), both when they are first met and again when they are popped.
 // "while-while" form: a lane that reaches a leaf waits at the end of the inner loop until the
 // other lanes of its warp hold a leaf too (or are done), so the long triangle loop runs with as
 // many lanes as possible.  Returns true when the sink asked to stop (any-hit).
-template <bool COUNT, class Sink>
+// SPHERES: the tree is the top-level sphere tree (leaves hold object indices) instead of a mesh tree.
+template <bool COUNT, class Sink, bool SPHERES = false>
 __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const RayF& f, double& bound, Sink& sink,
-                                         uint4* stack, Cnt<COUNT>& cnt) {
+                                         uint4* stack, Cnt<COUNT>& cnt, bool skip_emitters = false) {
   int sp = 0;
   uint32_t ref = root, first = 0;
   const rh_tri* tris = cx.S->tris;
@@ -342,7 +372,11 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
         first = e.y;
       }
     }
-    if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+    if constexpr (SPHERES) {
+      if (test_sphere_leaf<COUNT>(cx, first, ref & ~kLeafBit, r, sink, bound, skip_emitters, cnt)) return true;
+    } else {
+      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+    }
     const float fb = __double2float_ru(bound);
     uint4 e;
     do {
@@ -357,9 +391,9 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
 // The same walk with the reference's own double slab test (GHC min/max NaN semantics included):
 // rays with a zero direction component (centre row/column of the image) and
 // RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line.
-template <bool COUNT, class Sink>
+template <bool COUNT, class Sink, bool SPHERES = false>
 __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, uint4* stack,
-                                            Cnt<COUNT>& cnt) {
+                                            Cnt<COUNT>& cnt, bool skip_emitters = false) {
   const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
   int sp = 0;
   uint32_t ref = root, first = 0;
@@ -404,6 +438,8 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
         first = cw.w;
         continue;
       }
+    } else if constexpr (SPHERES) {
+      if (test_sphere_leaf<COUNT>(cx, first, ref & ~kLeafBit, r, sink, bound, skip_emitters, cnt)) return true;
     } else {
       if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
     }
@@ -459,8 +495,10 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
   best.slot = 0;
   best.tris = cx.S->tris;
   best.obj = -1;
-  const uint32_t n = cx.S->n_objects;
-  for (uint32_t i = 0; i < n; i++) {
+  const uint32_t sphere_root = cx.S->sphere_root;
+  const uint32_t n = cx.S->n_lin;  // == n_objects, in scene order, unless the spheres live in the sphere tree
+  for (uint32_t k = 0; k < n; k++) {
+    const uint32_t i = sphere_root == kEmpty ? k : __ldg(cx.S->lin_objs + k);
     const DObject& ob = cx.objects[i];
     const int kind = ob.kind;
     if (kind == RH_OBJ_MESH) {
@@ -482,6 +520,13 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
       }
     }
   }
+  if (sphere_root != kEmpty) {
+    double bound = best.t * kPruneSlack;
+    if (exact)
+      traverse_exact<COUNT, Closest, true>(cx, sphere_root, r, bound, best, stack, cnt);
+    else
+      traverse<COUNT, Closest, true>(cx, sphere_root, r, f, bound, best, stack, cnt);
+  }
 }
 
 // RayHs.hs:74-87 shadowIntersection: true when some non-emitter object has a hit in front of the light.
@@ -496,8 +541,10 @@ __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact
   // hits farther than the light cannot be in front of it; 1e-6 relative slack covers |d| != 1 rounding
   const double far = sink.directional ? __longlong_as_double(0x7ff0000000000000LL)
                                       : sqrt(sink.dl2) * 1.000001 / sqrt(dot(r.d, r.d));
-  const uint32_t n = cx.S->n_objects;
-  for (uint32_t i = 0; i < n; i++) {
+  const uint32_t sphere_root = cx.S->sphere_root;
+  const uint32_t n = cx.S->n_lin;
+  for (uint32_t k = 0; k < n; k++) {
+    const uint32_t i = sphere_root == kEmpty ? k : __ldg(cx.S->lin_objs + k);
     const DObject& ob = cx.objects[i];
     if (ob.is_emitter) continue;  // isOccluder, RayHs.hs:81-82
     const int kind = ob.kind;
@@ -514,6 +561,11 @@ __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact
       const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(r, ob, far, time) : sphere_time(r, ob, time);
       if (hit && sink.in_front(r, time)) return true;
     }
+  }
+  if (sphere_root != kEmpty) {
+    double bound = far;
+    return exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, stack, cnt, true)
+                 : traverse<COUNT, AnyHit, true>(cx, sphere_root, r, f, bound, sink, stack, cnt, true);
   }
   return false;
 }
@@ -1030,7 +1082,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
   ChunkCtl* ctl = P.ctl;
   const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
   const size_t cap = P.q_shadow.capacity;
-  const uint32_t n_lights = S.n_lights, n_objects = S.n_objects;
+  const uint32_t n_lights = S.n_lights, n_lin = S.n_lin, sphere_root = S.sphere_root;
   const double2* qp = P.q_shadow.plane;
   unsigned long long n_culled = 0;
 
@@ -1045,13 +1097,20 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
     const bool exact = P.exact_boxes || degenerate_dir(sr.r.d);
     const RayF f = make_rayf(sr.r, S.abs_max);
     bool hit = false;
-    for (uint32_t oi = 0; oi < n_objects && !hit; oi++) {
+    for (uint32_t k = 0; k < n_lin && !hit; k++) {
+      const uint32_t oi = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
       const DObject& ob = cx.objects[oi];
       if (ob.kind != RH_OBJ_MESH || ob.is_emitter || ob.root == kEmpty) continue;
       double bound = sr.far;
       AnyHit sink = sr.sink;
       hit = exact ? traverse_exact<COUNT>(cx, ob.root, sr.r, bound, sink, stack, cnt)
                   : traverse<COUNT>(cx, ob.root, sr.r, f, bound, sink, stack, cnt);
+    }
+    if (!hit && sphere_root != kEmpty) {
+      double bound = sr.far;
+      AnyHit sink = sr.sink;
+      hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, sr.r, bound, sink, stack, cnt, true)
+                  : traverse<COUNT, AnyHit, true>(cx, sphere_root, sr.r, f, bound, sink, stack, cnt, true);
     }
     if (hit) atomicOr(&ws.vis[j], 1u << li);
   };
@@ -1092,7 +1151,8 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
             const RayF f = make_rayf(sr.r, S.abs_max);
             const float ffar = __double2float_ru(sr.far);
             bool shadowed = false;
-            for (uint32_t oi = 0; oi < n_objects && !shadowed; oi++) {
+            for (uint32_t k = 0; k < n_lin && !shadowed; k++) {
+              const uint32_t oi = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
               const DObject& ob = cx.objects[oi];
               if (ob.is_emitter) continue;  // isOccluder, RayHs.hs:81-82
               const int kind = ob.kind;
@@ -1114,6 +1174,19 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
                 RH_CNT(prim, 1);
                 const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(sr.r, ob, sr.far, time) : sphere_time(sr.r, ob, time);
                 shadowed = hit && sr.sink.in_front(sr.r, time);
+              }
+            }
+            if (!shadowed && !need_walk && sphere_root != kEmpty) {  // the sphere tree's own box
+              if (exact) {
+                need_walk = true;
+              } else {
+                const float4* np =
+                    sphere_root < S.n_smem_nodes ? (const float4*)&sm.nodes[sphere_root] : (const float4*)&S.wide32[sphere_root];
+                const float4 b0 = np[0], b1 = np[1];
+                float tm;
+                RH_CNT(nodes, 1);
+                RH_CNT(box, 1);
+                need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
               }
             }
             if (shadowed) {

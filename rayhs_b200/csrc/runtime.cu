@@ -134,7 +134,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs;
   SceneView view{};
   uint32_t max_tree_depth = 0;
 };
@@ -142,13 +142,109 @@ struct rh_scene {
 namespace {
 
 // ------------------------------------------------------------------ scene upload
-int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<DObject>& objs, uint32_t* max_depth) {
+// Top-level spheres.  The reference scans the object list linearly (RayHs.hs:64-71), which is what the
+// kernels do too while the list is short.  A scene with many spheres (1 000) gets a
+// bounding-volume tree over them instead, walked like a mesh tree with the conservative float boxes; its
+// leaves hold object indices and every candidate still gets the reference's exact double test
+// (Geometry.hs:81-95).  The winner is the same: smallest time, lowest object index on a tie (RayHs.hs:67-71).
+// Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
+constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
+constexpr uint32_t kSphereLeaf = 4;
+constexpr uint32_t kSphereTreeFlag = 4;  // WideNode::refine bit 2: the record belongs to the sphere tree
+
+struct SphereTree {
+  std::vector<rh_node> nodes;
+  std::vector<uint32_t> refs;  // object indices in leaf order
+  uint32_t depth = 0;
+  struct Item { uint32_t obj; double c[3], lo[3], hi[3]; };
+
+  uint32_t build(std::vector<Item>& it, size_t b, size_t e, uint32_t d) {
+    depth = std::max(depth, d);
+    const double inf = std::numeric_limits<double>::infinity();
+    rh_node nd{};
+    double clo[3] = {inf, inf, inf}, chi[3] = {-inf, -inf, -inf};
+    for (int k = 0; k < 3; k++) { nd.lo[k] = inf; nd.hi[k] = -inf; }
+    for (size_t i = b; i < e; i++)
+      for (int k = 0; k < 3; k++) {
+        nd.lo[k] = std::min(nd.lo[k], it[i].lo[k]);
+        nd.hi[k] = std::max(nd.hi[k], it[i].hi[k]);
+        clo[k] = std::min(clo[k], it[i].c[k]);
+        chi[k] = std::max(chi[k], it[i].c[k]);
+      }
+    const uint32_t self = (uint32_t)nodes.size();
+    nodes.push_back(nd);
+    if (e - b <= kSphereLeaf) {
+      nodes[self].is_leaf = 1;
+      nodes[self].left = (uint32_t)refs.size();
+      nodes[self].right = (uint32_t)(e - b);
+      std::sort(it.begin() + b, it.begin() + e, [](const Item& x, const Item& y) { return x.obj < y.obj; });
+      for (size_t i = b; i < e; i++) refs.push_back(it[i].obj);
+      return self;
+    }
+    int axis = 0;
+    for (int k = 1; k < 3; k++)
+      if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+    const size_t mid = b + (e - b) / 2;
+    std::nth_element(it.begin() + b, it.begin() + mid, it.begin() + e,
+                     [axis](const Item& x, const Item& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.obj < y.obj); });
+    const uint32_t l = build(it, b, mid, d + 1);
+    const uint32_t r = build(it, mid, e, d + 1);
+    nodes[self].left = l;
+    nodes[self].right = r;
+    return self;
+  }
+
+  // Returns false (no tree) when there are too few spheres or one of them is not finite.
+  bool run(const rh_scene_desc& d) {
+    std::vector<Item> it;
+    for (uint32_t i = 0; i < d.n_objects; i++) {
+      const rh_object& o = d.objects[i];
+      if (o.kind != RH_OBJ_SPHERE) continue;
+      Item x;
+      x.obj = i;
+      const double r = std::fabs(o.b[0]);
+      double m = r;
+      for (int k = 0; k < 3; k++) m = std::max(m, std::fabs(o.a[k]));
+      if (!(m < 1e30)) return false;
+      const double pad = 1e-7 * m + 1e-300;
+      for (int k = 0; k < 3; k++) {
+        x.c[k] = o.a[k];
+        x.lo[k] = o.a[k] - r - pad;
+        x.hi[k] = o.a[k] + r + pad;
+      }
+      it.push_back(x);
+    }
+    if (it.size() < kSphereTreeMin) return false;
+    build(it, 0, it.size(), 0);
+    return true;
+  }
+};
+
+int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<DObject>& objs, uint32_t* max_depth,
+               std::vector<uint32_t>& lin_objs, std::vector<uint32_t>& sphere_refs, uint32_t* sphere_root) {
   const double inf = std::numeric_limits<double>::infinity();
   objs.resize(d.n_objects);
   struct Pending { uint32_t node, wide_index, depth; };
   std::deque<Pending> fifo;
   auto empty_box = [&](double* b) { for (int k = 0; k < 3; k++) { b[k] = inf; b[3 + k] = -inf; } };
   std::vector<uint8_t> seen(d.n_nodes, 0);
+  // node array the level-order pass below reads: the caller's nodes, then the sphere tree's
+  SphereTree st;
+  const bool sphere_tree = st.run(d);
+  std::vector<rh_node> merged;
+  const rh_node* all_nodes = d.nodes;
+  if (sphere_tree) {
+    merged.assign(d.nodes, d.nodes + d.n_nodes);
+    for (rh_node nd : st.nodes) {
+      if (!nd.is_leaf) { nd.left += d.n_nodes; nd.right += d.n_nodes; }
+      merged.push_back(nd);
+    }
+    all_nodes = merged.data();
+    sphere_refs = st.refs;
+    *max_depth = std::max(*max_depth, st.depth);
+  }
+  *sphere_root = kEmpty;
+  lin_objs.clear();
   for (uint32_t i = 0; i < d.n_objects; i++) {
     const rh_object& o = d.objects[i];
     DObject& t = objs[i];
@@ -164,6 +260,7 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
     if (o.material < 0 || (uint32_t)o.material >= d.n_materials)
       return rh::set_error(RH_ERR_ARG, "rh_scene_create: object material index out of range");
     t.is_emitter = d.materials[o.material].kind == RH_MAT_EMMIT;
+    if (!(sphere_tree && o.kind == RH_OBJ_SPHERE)) lin_objs.push_back(i);
     if (o.kind == RH_OBJ_MESH && o.root != RH_NO_NODE) {
       if (o.root >= d.n_nodes) return rh::set_error(RH_ERR_ARG, "rh_scene_create: mesh root out of range");
       // the leaves of one mesh must occupy increasing triangle slots in left-to-right order:
@@ -201,6 +298,16 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
       fifo.push_back({o.root, t.root, 0});
     }
   }
+  if (sphere_tree) {  // super-root of the sphere tree, after the meshes' super-roots
+    *sphere_root = (uint32_t)wide.size();
+    WideNode w{};
+    empty_box(w.box);
+    empty_box(w.box + 6);
+    w.child[0] = w.child[1] = kEmpty;
+    w.refine = kSphereTreeFlag | 3u;
+    wide.push_back(w);
+    fifo.push_back({d.n_nodes, *sphere_root, 0});
+  }
   // level order over all meshes: fill each wide node's two child slots, queue inner children
   // `fifo` entries mean: node `node` is the (only) real child of wide record `wide_index` slot 0 when depth==0,
   // otherwise the record `wide_index` IS the inner node `node`.
@@ -212,7 +319,7 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
       w.child[slot] = kEmpty;
       return;
     }
-    const rh_node& nd = d.nodes[ni];
+    const rh_node& nd = all_nodes[ni];
     memcpy(box, nd.lo, 3 * sizeof(double));
     memcpy(box + 3, nd.hi, 3 * sizeof(double));
     if (nd.is_leaf) {
@@ -240,8 +347,10 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
     if (wi >= 0x7FFFFFF0u) return rh::set_error(RH_ERR_ARG, "rh_scene_create: too many nodes");
     wide[pa.wide_index].child[pa.slot] = wi;
     wide.push_back(WideNode{});
-    const rh_node& nd = d.nodes[p.node];
+    const rh_node& nd = all_nodes[p.node];
     WideNode w{};
+    // boxes of the sphere tree are not boxes the reference tests: the exact walk passes them all (refine bits)
+    if (p.node >= d.n_nodes) w.refine = kSphereTreeFlag | 3u;
     size_t before = work.size();
     child_ref(nd.left, w, 0, p.depth);
     if (work.size() > before) patches.push_back({wi, 0});
@@ -334,7 +443,7 @@ struct Refiner {
     for (size_t w = 0; w < n_ref; w++)
       for (int c = 0; c < 2; c++) {
         const uint32_t ch = wide[w].child[c];
-        if (ch == kEmpty || !(ch & kLeafBit)) continue;
+        if (ch == kEmpty || !(ch & kLeafBit) || (wide[w].refine & kSphereTreeFlag)) continue;
         const uint32_t count = ch & ~kLeafBit, first = wide[w].first[c];
         for (uint32_t k = 0; k < count; k++) tris[first + k].pad_ = first;  // reference-leaf order key
         if (count <= kSubLeaf) continue;
@@ -419,8 +528,10 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   uint32_t depth = 0;
   std::vector<rh_tri> dtris;
   std::vector<rh_tri_shade> dshade;
+  std::vector<uint32_t> lin_objs, sphere_refs;
+  uint32_t sphere_root = kEmpty;
   try {
-    int rc = build_wide(*d, wide, objs, &depth);
+    int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
     if (rc) return rc;
     dtris.assign(d->tris, d->tris + d->n_tris);
     dshade.assign(d->tri_shade, d->tri_shade + d->n_tris);
@@ -469,6 +580,8 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   if ((rc = upload(S->lights, d->lights, d->n_lights))) return rc;
   if ((rc = upload(S->textures, d->textures, d->n_textures))) return rc;
   if ((rc = upload(S->texels, d->texels, (size_t)d->n_texels * 3))) return rc;
+  if ((rc = upload(S->lin_objs, lin_objs.data(), lin_objs.size()))) return rc;
+  if ((rc = upload(S->sphere_refs, sphere_refs.data(), sphere_refs.size()))) return rc;
   SceneView& v = S->view;
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
@@ -486,6 +599,10 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.n_materials = d->n_materials;
   v.n_lights = d->n_lights;
   v.n_textures = d->n_textures;
+  v.lin_objs = (const uint32_t*)S->lin_objs.p;
+  v.sphere_refs = (const uint32_t*)S->sphere_refs.p;
+  v.n_lin = (uint32_t)lin_objs.size();
+  v.sphere_root = sphere_root;
   v.n_smem_nodes = std::min<uint32_t>(v.n_wide, kSmemNodes);
   v.tables_in_smem = (d->n_objects <= (uint32_t)kSmemObjects && d->n_materials <= (uint32_t)kSmemObjects &&
                       d->n_lights <= (uint32_t)kSmemLights);
@@ -496,7 +613,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
 void scene_destroy(rh_scene* s) {
   if (!s) return;
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
-  for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels}) b->release();
+  for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels,
+                    &s->lin_objs, &s->sphere_refs})
+    b->release();
   delete s;
 }
 

@@ -117,6 +117,56 @@ def test_more_than_64_objects_reads_tables_from_global_memory():
     both(rs, 120, 90)
 
 
+def test_sphere_tree_ties_emitters_and_interleaved_objects():
+    """>= 16 top-level spheres are walked through the sphere tree (any order): coincident spheres must resolve to the
+    lowest object index (RayHs.hs:67-71), emitter spheres must not occlude (RayHs.hs:81-82), and planes / meshes placed
+    between the spheres in the object list keep their place in the tie order.  The exact-box walk (all spheres, like the
+    reference's scan) must give the same image."""
+    rng = np.random.RandomState(11)
+    mats = [{"kind": "diffuse", "color1": (0.9, 0.3, 0.2)}, {"kind": "plastic", "ior": 1.7, "color1": (0.2, 0.8, 0.3)},
+            {"kind": "mirror", "ior": 3.0}, {"kind": "emmit", "color1": (2, 2, 1)}, {"kind": "transparent", "ior": 1.4},
+            {"kind": "diffuse", "color1": (0.2, 0.3, 0.9)}]
+    objs = []
+    for i in range(60):
+        c = tuple(rng.uniform(-1.2, 1.2, 3) * (1, 0.7, 1))
+        r = float(rng.uniform(0.05, 0.25))
+        objs.append({"kind": "sphere", "center": c, "radius": r, "material": i % 5})
+        if i % 7 == 0:   # an identical sphere later in the list with another material: never visible
+            objs.append({"kind": "sphere", "center": c, "radius": r, "material": 5})
+        if i == 10:
+            objs.append({"kind": "plane", "point": (0, -0.9, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 1})
+        if i == 30:
+            objs.append(dict(kind="mesh", material=0, **grid_mesh(6, z=1.6, wobble=0.1)))
+    # a sphere tangent to the floor plane and one centred on a light (emitter): shadow-rule edge cases
+    objs.append({"kind": "sphere", "center": (0.3, -0.7, -0.4), "radius": 0.2, "material": 0})
+    objs.append({"kind": "sphere", "center": (0.0, 1.6, -0.5), "radius": 0.15, "material": 3})
+    lights = [{"kind": "point", "vec": (0.0, 1.6, -0.5), "color": (25, 25, 25), "radius": 0.5},
+              {"kind": "directional", "vec": (-0.4, 1.0, -0.6), "color": (0.5, 0.5, 0.6)}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0, 0.4, -3.5), "target": (0, 0, 0)})
+    img, ref = both(rs, 161, 121)
+    assert ref["rays"]["probe"] > 0 and ref["rays"]["reflect"] > 0
+    img2, _ = both(rs, 161, 121, exact_boxes=True)
+    assert np.array_equal(img.pixels, img2.pixels)
+    assert not (img.hit_ids[..., 0] >= 0).all() and (img.hit_ids[..., 0] >= 0).any()
+    ids = set(np.unique(img.hit_ids[..., 0]).tolist())
+    dup = [k for k, o in enumerate(objs) if o.get("material") == 5]
+    assert not ids.intersection(dup), "a coincident later sphere won a tie"
+
+
+def test_synthetic_stress_scene_sphere_tree_and_spp():
+    """configs[4] shape at reduced size with enough spheres for the sphere tree, 4 spp, hit ids and ray counts."""
+    sc = rh.Scene.synthetic(60000, 300)
+    w, h, spp = 160, 90, 4
+    off = rh.sample_offsets(w * h, spp, 24)
+    job = rh.renderingFromScene(sc, w, h)
+    img = rh.render(job, spp=spp, offsets=off, want_hit_ids=True)
+    ref = OracleScene(sc.raw).render(sc.camera, w, h, sc.max_depth, spp=spp, offsets=off)
+    assert np.array_equal(img.hit_ids.reshape(h, w, spp, 2), ref["hit_ids"])
+    assert_parity(img.pixels, ref["rgb_u8"])
+    got = tuple(img.stats[k] for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"))
+    assert got == tuple(ref["rays"][k] for k in ("primary", "reflect", "probe", "exit", "shadow"))
+
+
 def test_synthetic_stress_scene_small():
     """BASELINE.json configs[4] at reduced size: random triangles + spheres + checker floor, dragon.json camera/lights."""
     sc = rh.Scene.synthetic(30000, 40)
