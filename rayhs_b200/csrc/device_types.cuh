@@ -31,6 +31,9 @@ constexpr int kBlock = 128;                // resolve kernel
 #ifndef RH_SHADOW_POOL
 #define RH_SHADOW_POOL 1
 #endif
+#ifndef RH_SHADOW_FAST
+#define RH_SHADOW_FAST 1  // 0: always use the general pooled kernel (A/B and validation builds)
+#endif
 constexpr int kTraceBlock = RH_TRACE_BLOCK, kTraceMinBlocks = RH_TRACE_MINB;      // one 768-thread block per SM: 24 warps at <= 85 registers, tables staged once per SM (measured best, profiles/README.md)
 constexpr int kShadowBlock = RH_SHADOW_BLOCK, kShadowMinBlocks = RH_SHADOW_MINB;
 
@@ -72,6 +75,13 @@ struct __align__(16) DObject {
 };
 static_assert(sizeof(DObject) == 96, "DObject must be 96 bytes");
 
+// Occluder tables of the fast shadow kernel (shadowIntersection, RayHs.hs:74-82): the non-emitter planes and the
+// non-emitter spheres that are not in the sphere tree, as compact records staged in shared memory, and the
+// super-roots of the non-emitter, non-empty meshes.
+struct OccPlane { double p[3], n[3]; };   // Geometry.hs:62
+struct OccSphere { double c[3], r; };     // Geometry.hs:63
+constexpr int kOccPlanes = 16, kOccSpheres = 16, kOccMeshes = 8, kFastLights = 12;
+
 struct SceneView {
   const WideNode* wide;      // exact double boxes: rays with a zero direction component, RH_FLAG_EXACT_BOXES
   const WideNode32* wide32;  // conservative float boxes: everything else
@@ -86,6 +96,11 @@ struct SceneView {
   const uint32_t* sphere_refs;  // sphere tree leaves: object indices
   uint32_t n_lin;
   uint32_t sphere_root;         // super-root of the sphere tree or kEmpty (spheres are in lin_objs then)
+  const OccPlane* occ_planes;
+  const OccSphere* occ_spheres;
+  const uint32_t* occ_meshes;
+  uint32_t n_occ_planes, n_occ_spheres, n_occ_meshes;
+  uint32_t shadow_fast;         // the occluder tables and the lights fit the fast shadow kernel's shared-memory tables
   uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables

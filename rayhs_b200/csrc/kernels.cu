@@ -86,7 +86,7 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, uint32_t byte
 
 struct Ctx {
   const SceneView* S;
-  const SmemTables* sm;
+  const WideNode32* sm_nodes;  // the first S->n_smem_nodes records of S->wide32, staged in shared memory
   const DObject* objects;
   const rh_material* materials;
   const rh_light* lights;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void stage_tables(SmemTables& sm, const SceneView& S,
   }
   __syncthreads();
   cx.S = &S;
-  cx.sm = &sm;
+  cx.sm_nodes = sm.nodes;
   cx.objects = S.tables_in_smem ? sm.objects : S.objects;
   cx.materials = S.tables_in_smem ? sm.materials : S.materials;
   cx.lights = S.tables_in_smem ? sm.lights : S.lights;
@@ -165,19 +165,24 @@ struct RayF {
   float mix, miy, miz;  // (o - e) * (1/d)
 };
 
+// True unless every |component| lies in [2^-100, 2^100): such rays take the exact double walk (zero components are
+// the reference's inf/NaN case; the range keeps 1/d and the products of the float test finite and normal).
+// Decided on the exponent bits, three integer compares.
 __device__ __forceinline__ bool degenerate_dir(const V3& d) {
-  const double a = fmin(fmin(fabs(d.x), fabs(d.y)), fabs(d.z));
-  const double b = fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z));
-  return !(a > 1e-30) || !(b < 1e30);
+  const uint32_t lo = 0x39B00000u, span = 0x46300000u - 0x39B00000u;  // biased exponents 923 (2^-100) and 1123 (2^100)
+  const uint32_t hx = (uint32_t)__double2hiint(d.x) & 0x7fffffffu, hy = (uint32_t)__double2hiint(d.y) & 0x7fffffffu,
+                 hz = (uint32_t)__double2hiint(d.z) & 0x7fffffffu;
+  return !((hx - lo < span) & (hy - lo < span) & (hz - lo < span));
 }
 
 __device__ __forceinline__ RayF make_rayf(const Ray& r, float abs_max) {
   RayF f;
-  const float e = 4.76837158203125e-07f * ((float)fmax(fmax(fabs(r.o.x), fabs(r.o.y)), fabs(r.o.z)) * 1.0000002f + abs_max);
+  const float ox = (float)r.o.x, oy = (float)r.o.y, oz = (float)r.o.z;
+  // (float)max|o_k| == max|(float)o_k|: rounding is monotonic
+  const float e = 4.76837158203125e-07f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) * 1.0000002f + abs_max);
   f.ix = __frcp_rn((float)r.d.x);  // two roundings (d -> float, reciprocal): still inside e's budget of eight
   f.iy = __frcp_rn((float)r.d.y);
   f.iz = __frcp_rn((float)r.d.z);
-  const float ox = (float)r.o.x, oy = (float)r.o.y, oz = (float)r.o.z;
   f.pix = (ox + e) * f.ix;
   f.piy = (oy + e) * f.iy;
   f.piz = (oz + e) * f.iz;
@@ -331,7 +336,7 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
   const uint32_t n_smem = cx.S->n_smem_nodes;
   for (;;) {
     while (!(ref & kLeafBit)) {
-      const float4* np = ref < n_smem ? (const float4*)&cx.sm->nodes[ref] : (const float4*)&cx.S->wide32[ref];
+      const float4* np = ref < n_smem ? (const float4*)&cx.sm_nodes[ref] : (const float4*)&cx.S->wide32[ref];
       const float4 b0 = np[0], b1 = np[1], b2 = np[2];
       const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
       RH_CNT(nodes, 1);
@@ -1242,6 +1247,319 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
+// Fast form of the pooled kernel, for the common scene shape: at most kOccPlanes occluding planes, kOccSpheres
+// occluding spheres outside the sphere tree, kOccMeshes meshes and kFastLights lights (SceneView::shadow_fast).
+// Same three phases and the same arithmetic per (hit, light) pair, restructured around what ncu showed on the wall-only
+// chunks of the bench frame (profiles/r1e_*): fp64 math was a quarter of the issued instructions, the rest control
+// flow, generic loads and recomputation.  So
+//   * the occluder and light tables are compact shared-memory records read with LDS, without the per-object kind
+//     dispatch and emitter test;
+//   * the plane tests of a pair are straight-line: every plane gets the reference's two dot products
+//     (Geometry.hs:70-79), and a plane is dropped when `abs (d.n) > 0 && time > 0` is certain to fail or time is
+//     certain to lie beyond the light (the same three rejections as plane_time).  Planes that survive — none in a
+//     closed room — get the exact quotient and inFrontOfLight (RayHs.hs:84-87) in a cold loop;
+//   * phase 1 leaves the pair's Lambert factor and light falloff in shared memory, so phase 3 folds the lights
+//     (accumDiffuse's foldl, RayHs.hs:89-97) without recomputing lightAt (Light.hs:12-17).
+struct __align__(16) ShadowTables {
+  WideNode32 nodes[kSmemNodes];
+  OccPlane planes[kOccPlanes];
+  OccSphere spheres[kOccSpheres];
+  rh_light lights[kFastLights];
+  // Root boxes (the float cull boxes of the mesh super-roots and of the sphere tree, padded by 2e-6 + 1e-12 |x|) and,
+  // per (light, root), on which outer side of each slab the light lies: bit a = below lo[a], bit 3 + a = above hi[a].
+  double rootbox[kOccMeshes + 1][6];
+  uint32_t mesh_roots[kOccMeshes + 1];  // the sphere tree's super-root follows the meshes'
+  uint8_t light_side[kFastLights][kOccMeshes + 1];
+};
+static_assert(sizeof(ShadowTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
+
+__device__ __forceinline__ int fast_shadow_T(uint32_t n_lights) {  // hits per lane per batch: 6 KB of pair terms per warp
+  const int t = 12 / (int)(n_lights ? n_lights : 1);
+  return t < 1 ? 1 : (t > kShadowT ? kShadowT : t);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_fast(const __grid_constant__ SceneView S,
+                                                                                     const __grid_constant__ ChunkParams P) {
+  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
+  const uint32_t n_lights = S.n_lights, n_planes = S.n_occ_planes, n_spheres = S.n_occ_spheres, n_meshes = S.n_occ_meshes;
+  const uint32_t sphere_root = S.sphere_root;
+  const uint32_t Tmax = (uint32_t)fast_shadow_T(n_lights);
+  // per-warp regions after the tables: vis + pool (ShadowWarpSmem), then the pair terms
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kShadowBlock / 32;
+  ShadowWarpSmem& ws = reinterpret_cast<ShadowWarpSmem*>(rh_smem + sizeof(ShadowTables))[warp];
+  const uint32_t pairs_per_warp = 32u * Tmax * n_lights;
+  double2* terms = reinterpret_cast<double2*>(rh_smem + sizeof(ShadowTables) + n_warps * sizeof(ShadowWarpSmem)) +
+                   (size_t)warp * pairs_per_warp;  // [light][hit in batch] = (Lambert factor / pi, falloff)
+  copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
+  copy16(sm.planes, S.occ_planes, n_planes * (uint32_t)sizeof(OccPlane));
+  copy16(sm.spheres, S.occ_spheres, n_spheres * (uint32_t)sizeof(OccSphere));
+  copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
+  const uint32_t n_roots = n_meshes + (sphere_root != kEmpty ? 1u : 0u);
+  if (threadIdx.x < n_roots) {
+    const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : sphere_root;
+    sm.mesh_roots[threadIdx.x] = root;
+    const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
+    for (int a = 0; a < 3; a++) {
+      const double lo = (double)fb[a], hi = (double)fb[3 + a];
+      sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
+      sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_roots * n_lights) {
+    const uint32_t li = threadIdx.x / n_roots, m = threadIdx.x % n_roots;
+    uint32_t side = 0;
+    if (sm.lights[li].kind != RH_LIGHT_DIRECTIONAL)
+      for (int a = 0; a < 3; a++) {
+        if (sm.lights[li].vec[a] < sm.rootbox[m][a]) side |= 1u << a;
+        if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
+      }
+    sm.light_side[li][m] = (uint8_t)side;
+  }
+  __syncthreads();
+  Ctx cx;
+  cx.S = &S;
+  cx.sm_nodes = sm.nodes;
+  cx.objects = S.objects;  // sphere-tree leaves only
+  cx.materials = S.materials;
+  cx.lights = sm.lights;
+
+  uint4 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
+  const size_t cap = P.q_shadow.capacity;
+  const double2* qp = P.q_shadow.plane;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  unsigned long long n_culled = 0;
+
+  // The pair's light direction and shadow ray (Light.hs:12-17, RayHs.hs:93).  `far` bounds the distance from the
+  // ray origin to the light from above (|o - L| <= |o - p| + |p - L| = 1e-6 |ld| + dd); it only prunes — whether a
+  // hit is in front of the light is always decided by inFrontOfLight's own comparison.
+  struct Pair {
+    V3 ld, o, lp;
+    double dd, far;
+    bool directional;
+  };
+  auto make_pair = [&](const rh_light& L, const V3& p) {
+    Pair q;
+    q.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
+    q.lp = ld3(L.vec);
+    if (q.directional) {
+      q.ld = q.lp;
+      q.dd = 0;
+      q.far = kInf;
+    } else {
+      const V3 dv = q.lp - p;
+      q.dd = sqrt(sqrLen(dv));  // dist lightPos p = sqrt (sqrDist ..), Vec.hs:118-122: (lp - p).(lp - p)
+      q.ld = mul(1 / q.dd, dv);
+      q.far = (q.dd + kEps) * 1.000001;
+    }
+    q.o = p + mul(kEps, q.ld);  // rayEps, Geometry.hs:36
+    return q;
+  };
+
+  // phase 2 body: one pooled (hit, light) pair walks the mesh trees and the sphere tree
+  auto walk = [&](uint32_t base, uint32_t e) {
+    const uint32_t j = e & 0xff, li = e >> 8;
+    const uint32_t item = base + j;
+    const double2 a = qp[item], b = qp[cap + item];
+    const V3 p = mk(a.x, a.y, b.x);
+    const Pair q = make_pair(sm.lights[li], p);
+    Ray r;
+    r.o = q.o;
+    r.d = q.ld;
+    AnyHit sink;
+    sink.directional = q.directional;
+    sink.lpos = q.lp;
+    sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
+    const bool exact = P.exact_boxes || degenerate_dir(r.d);
+    const RayF f = make_rayf(r, S.abs_max);
+    bool hit = false;
+    for (uint32_t m = 0; m < n_meshes && !hit; m++) {
+      double bound = q.far;
+      hit = exact ? traverse_exact<COUNT>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt)
+                  : traverse<COUNT>(cx, sm.mesh_roots[m], r, f, bound, sink, stack, cnt);
+    }
+    if (!hit && sphere_root != kEmpty) {
+      double bound = q.far;
+      hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, stack, cnt, true)
+                  : traverse<COUNT, AnyHit, true>(cx, sphere_root, r, f, bound, sink, stack, cnt, true);
+    }
+    if (hit) atomicOr(&ws.vis[j], 1u << li);
+  };
+
+  const uint32_t total_warps = gridDim.x * n_warps;
+  // Guided self-scheduling, as in shadow_kernel.  (Claiming the next batch early, to overlap the cursor round trip
+  // with work, was measured 5 % slower: every warp then finishes one batch after the queue has run dry.)
+  auto claim = [&]() {
+    uint2 c = make_uint2(0, 1);
+    if (lane == 0) {
+      const uint32_t seen = *(volatile uint32_t*)&ctl->shadow_cursor[P.pass];
+      const uint32_t left = seen < n_items ? n_items - seen : 0;
+      c.y = min(Tmax, max(1u, left / (total_warps * 32u * 2u)));
+      c.x = atomicAdd(&ctl->shadow_cursor[P.pass], 32u * c.y);
+    }
+    return c;
+  };
+  for (;;) {
+    const uint2 now = claim();
+    const uint32_t base = __shfl_sync(kFull, now.x, 0), T = __shfl_sync(kFull, now.y, 0);
+    if (base >= n_items) break;
+    const uint32_t n_here = min(32u * T, n_items - base);
+    for (uint32_t t = 0; t < T; t++) ws.vis[t * 32 + lane] = 0;
+    uint32_t pool_n = 0;
+    for (uint32_t li = 0; li < n_lights; li++) {
+      const rh_light& L = sm.lights[li];
+      // ---- phase 1
+      for (uint32_t t = 0; t < T; t++) {
+        const uint32_t j = t * 32 + lane;
+        bool need_walk = false;
+        if (j < n_here) {
+          const uint32_t item = base + j;
+          const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
+          const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
+          const Pair q = make_pair(L, p);
+          const double ldn = dot(q.ld, n);
+          if (ldn <= 0) {
+            n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
+            ws.vis[j] |= 1u << li;  // (only this lane touches vis[j] during phase 1)
+          } else {
+            // lightAt's colour factor (Light.hs:16-17) and diffuse's scalar (Material.hs:31-33), for phase 3
+            double falloff = 1.0;
+            if (!q.directional) {
+              const double s = 1.0 + q.dd / L.radius;
+              falloff = 1.0 / (s * s);
+            }
+            terms[li * (32u * Tmax) + j] = make_double2(hs_max(ldn, 0) * kPiInv, falloff);
+            // planes, straight-line
+            uint32_t maybe = 0;
+            for (uint32_t k = 0; k < n_planes; k++) {
+              const double2* pl = (const double2*)&sm.planes[k];
+              const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
+              const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
+              RH_CNT(prim, 1);
+              const double den = dot(q.ld, pn);
+              const double num = dot(pn, pp - q.o);
+              const bool miss = !(fabs(den) > 0) | (((num > 0) != (den > 0)) & (num == num)) |
+                                (fabs(num) > q.far * fabs(den) * 1.000000000001);
+              maybe |= (miss ? 0u : 1u) << k;
+            }
+            bool shadowed = false;
+            Ray r;
+            r.o = q.o;
+            r.d = q.ld;
+            AnyHit sink;
+            sink.directional = q.directional;
+            sink.lpos = q.lp;
+            sink.dl2 = 0.0;
+            if (maybe | n_spheres) sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
+            while (maybe) {  // cold: exact quotient and inFrontOfLight for the surviving planes
+              const uint32_t k = __ffs(maybe) - 1;
+              maybe &= maybe - 1;
+              const V3 pp = ld3(sm.planes[k].p), pn = ld3(sm.planes[k].n);
+              const double time = dot(pn, pp - r.o) / dot(r.d, pn);
+              if (time > 0 && sink.in_front(r, time)) shadowed = true;
+            }
+            for (uint32_t k = 0; k < n_spheres && !shadowed; k++) {  // Geometry.hs:81-95
+              const V3 ct = ld3(sm.spheres[k].c);
+              const double rad = sm.spheres[k].r;
+              RH_CNT(prim, 1);
+              const double qa = dot(r.d, r.d);
+              const double qb = 2.0 * dot(r.d, r.o - ct);
+              const double qc = sqrLen(r.o - ct) - rad * rad;
+              const double delta = qb * qb - 4.0 * qa * qc;
+              if (delta < 0.0) continue;
+              const double t0 = 0.5 * ((-qb) - sqrt(delta)) / qa;
+              double time;
+              if (t0 > 0) time = t0;
+              else {
+                const double t1 = 0.5 * ((-qb) + sqrt(delta)) / qa;
+                if (!(t1 > 0)) continue;
+                time = t1;
+              }
+              shadowed = sink.in_front(r, time);
+            }
+            if (shadowed) {
+              ws.vis[j] |= 1u << li;
+            } else if (n_roots) {
+              // Only the part of the ray between its origin and the light can hold an occluder (inFrontOfLight).  The
+              // origin is within 1.000001e-6 of p in every coordinate, so when p and the light lie beyond the same face
+              // of a (padded) root box, that part is outside the box: nothing to walk.
+              bool may = P.exact_boxes != 0;
+              for (uint32_t m = 0; m < n_roots; m++) {
+                const double* rb = sm.rootbox[m];
+                const uint32_t side = (p.x < rb[0] ? 1u : 0u) | (p.y < rb[1] ? 2u : 0u) | (p.z < rb[2] ? 4u : 0u) |
+                                      (p.x > rb[3] ? 8u : 0u) | (p.y > rb[4] ? 16u : 0u) | (p.z > rb[5] ? 32u : 0u);
+                may |= (side & sm.light_side[li][m]) == 0;
+              }
+              // the root boxes themselves (slot 0 of each super-root)
+              if (!may) {
+              } else if (P.exact_boxes || degenerate_dir(r.d)) {
+                need_walk = true;
+              } else {
+                const RayF f = make_rayf(r, S.abs_max);
+                const float ffar = __double2float_ru(q.far);
+                for (uint32_t m = 0; m < n_roots && !need_walk; m++) {
+                  const uint32_t root = sm.mesh_roots[m];
+                  const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
+                  const float4 b0 = np[0], b1 = np[1];
+                  float tm;
+                  RH_CNT(nodes, 1);
+                  RH_CNT(box, 1);
+                  need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
+                }
+              }
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(kFull, need_walk);
+        if (need_walk) ws.pool[pool_n + __popc(m & ((1u << lane) - 1))] = (uint16_t)(j | (li << 8));
+        pool_n += __popc(m);
+      }
+      __syncwarp();
+      // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
+      const bool last = (li + 1 == n_lights);
+      const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
+      for (uint32_t i = lane; i < n_full; i += 32) walk(base, ws.pool[i]);
+      __syncwarp();
+      const uint32_t rem = pool_n - n_full;
+      uint16_t keep = 0;
+      if (lane < rem) keep = ws.pool[n_full + lane];
+      __syncwarp();
+      if (lane < rem) ws.pool[lane] = keep;
+      pool_n = rem;
+      __syncwarp();
+    }
+    // ---- phase 3: accumDiffuse's fold over the lights, in order
+    for (uint32_t t = 0; t < T; t++) {
+      const uint32_t j = t * 32 + lane;
+      if (j >= n_here) continue;
+      const uint32_t item = base + j;
+      const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
+      const uint32_t sbits = P.q_shadow.sample[item];
+      const V3 cd = mk(d.x, d.y, e.x);
+      const double w = e.y;
+      const uint32_t vis = ws.vis[j];
+      V3 acc = mk(0, 0, 0);  // foldl ... black lts
+      for (uint32_t li = 0; li < n_lights; li++) {
+        if ((vis >> li) & 1u) continue;  // Just _ -> black (or l.n <= 0: the term is exactly 0)
+        const double2 tm = terms[li * (32u * Tmax) + j];
+        const V3 lc = mul(tm.y, ld3(sm.lights[li].color));   // Light.hs:14, 17
+        acc = acc + mul(tm.x, cmul(cd, lc));                  // diffuse, Material.hs:31-33
+      }
+      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
+      accumulate(P, sbits & 0x7fffffffu, w, total);
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
+  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
+  flush_counters<COUNT>(cnt, P.counters, 1);
+}
+
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
 __device__ __forceinline__ int to_int_c(double c, bool& negative) {
   const double v = 255 * hs_min(c, 1);  // hs_min NaN 1 = 1
@@ -1352,6 +1670,10 @@ __global__ void dfma_bench_kernel(double* sink, int iters) {
 // ------------------------------------------------------------------ launchers
 constexpr size_t kTraceSmem = sizeof(SmemTables);
 constexpr size_t kShadowSmem = sizeof(SmemTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem);
+// fast kernel: tables + per-warp vis/pool + per-warp pair terms (at most 32 * kShadowT * 3 pairs of 16 bytes)
+constexpr size_t kShadowFastSmem =
+    sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * 12 * sizeof(double2));
+static_assert(kShadowFastSmem <= 227 * 1024, "fast shadow kernel shared memory");
 
 int configure_kernels() {
   cudaError_t e = cudaSuccess;
@@ -1362,6 +1684,8 @@ int configure_kernels() {
   set((const void*)trace_kernel<false>, kTraceSmem);
   set((const void*)shadow_kernel<true>, kShadowSmem);
   set((const void*)shadow_kernel<false>, kShadowSmem);
+  set((const void*)shadow_kernel_fast<true>, kShadowFastSmem);
+  set((const void*)shadow_kernel_fast<false>, kShadowFastSmem);
   set((const void*)shadow_kernel_simple<true>, kShadowSmem);
   set((const void*)shadow_kernel_simple<false>, kShadowSmem);
   return (int)e;
@@ -1374,7 +1698,12 @@ void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams
 }
 void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream) {
   const bool simple = S.n_lights > 32 || RH_SHADOW_POOL == 0;
-  if (simple) {
+  if (S.shadow_fast && RH_SHADOW_FAST && !simple) {
+    if (count)
+      shadow_kernel_fast<true><<<grid, kShadowBlock, kShadowFastSmem, (cudaStream_t)stream>>>(S, P);
+    else
+      shadow_kernel_fast<false><<<grid, kShadowBlock, kShadowFastSmem, (cudaStream_t)stream>>>(S, P);
+  } else if (simple) {
     if (count)
       shadow_kernel_simple<true><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
     else

@@ -134,7 +134,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes;
   SceneView view{};
   uint32_t max_tree_depth = 0;
 };
@@ -582,7 +582,39 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   if ((rc = upload(S->texels, d->texels, (size_t)d->n_texels * 3))) return rc;
   if ((rc = upload(S->lin_objs, lin_objs.data(), lin_objs.size()))) return rc;
   if ((rc = upload(S->sphere_refs, sphere_refs.data(), sphere_refs.size()))) return rc;
+  // occluder tables (isOccluder, RayHs.hs:81-82: everything but Emmit objects)
+  std::vector<OccPlane> occ_planes;
+  std::vector<OccSphere> occ_spheres;
+  std::vector<uint32_t> occ_meshes;
+  for (uint32_t i : lin_objs) {
+    const DObject& o = objs[i];
+    if (o.is_emitter) continue;
+    if (o.kind == RH_OBJ_PLANE) {
+      OccPlane q;
+      memcpy(q.p, o.a, sizeof q.p);
+      memcpy(q.n, o.b, sizeof q.n);
+      occ_planes.push_back(q);
+    } else if (o.kind == RH_OBJ_SPHERE) {
+      OccSphere q;
+      memcpy(q.c, o.a, sizeof q.c);
+      q.r = o.b[0];
+      occ_spheres.push_back(q);
+    } else if (o.root != kEmpty) {
+      occ_meshes.push_back(o.root);
+    }
+  }
+  if ((rc = upload(S->occ_planes, occ_planes.data(), occ_planes.size()))) return rc;
+  if ((rc = upload(S->occ_spheres, occ_spheres.data(), occ_spheres.size()))) return rc;
+  if ((rc = upload(S->occ_meshes, occ_meshes.data(), occ_meshes.size()))) return rc;
   SceneView& v = S->view;
+  v.occ_planes = (const OccPlane*)S->occ_planes.p;
+  v.occ_spheres = (const OccSphere*)S->occ_spheres.p;
+  v.occ_meshes = (const uint32_t*)S->occ_meshes.p;
+  v.n_occ_planes = (uint32_t)occ_planes.size();
+  v.n_occ_spheres = (uint32_t)occ_spheres.size();
+  v.n_occ_meshes = (uint32_t)occ_meshes.size();
+  v.shadow_fast = occ_planes.size() <= (size_t)kOccPlanes && occ_spheres.size() <= (size_t)kOccSpheres &&
+                  occ_meshes.size() <= (size_t)kOccMeshes && d->n_lights <= (uint32_t)kFastLights;
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
   v.abs_max = abs_max;
@@ -614,7 +646,7 @@ void scene_destroy(rh_scene* s) {
   if (!s) return;
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
   for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels,
-                    &s->lin_objs, &s->sphere_refs})
+                    &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes})
     b->release();
   delete s;
 }
