@@ -74,6 +74,7 @@ struct DevBuf {
 struct Device {
   int dev = -1;
   int n_sms = 0;
+  size_t total_mem = 0;
   cudaStream_t stream = nullptr;       // kernels
   cudaStream_t copy_stream = nullptr;  // sample-offset uploads
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -92,6 +93,7 @@ struct Device {
     if (prop.major < 10)
       return rh::set_error(RH_ERR_CUDA, std::string("rayhs_b200 needs an sm_100 device, found ") + prop.name);
     n_sms = prop.multiProcessorCount;
+    total_mem = prop.totalGlobalMem;
     RH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     RH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     RH_CUDA(cudaEventCreate(&ev_begin));
@@ -718,13 +720,36 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   RH_CUDA(cudaSetDevice(D->dev));
   const CameraParams cam = make_camera(*camera, W, H);
   const size_t row_samples = (size_t)W * spp;
-  const size_t want_chunk = o->chunk_samples > 0 ? (size_t)o->chunk_samples : ((size_t)8 << 20);
-  const int rows_per_chunk = (int)std::max<size_t>(1, std::min<size_t>(want_chunk / row_samples, (size_t)rows_local));
-  const int n_chunks = (rows_local + rows_per_chunk - 1) / rows_per_chunk;
-  const size_t chunk_samples = (size_t)rows_per_chunk * row_samples;
-  if (chunk_samples > 0x7fffffffu) return rh::set_error(RH_ERR_ARG, "rh_render: chunk too large");
   const int n_passes = 2 * o->max_depth + 1;
   const size_t off_elem = (mode == RH_OFFSETS_F32) ? sizeof(float) * 2 : sizeof(double) * 2;
+  const bool host_offsets =
+      (mode == RH_OFFSETS_F64 || mode == RH_OFFSETS_F32) && !(o->flags & RH_FLAG_DEVICE_OFFSETS);
+  // Chunk plan (whole rows).  The secondary passes of a chunk are short launches whose cost is set by their slowest
+  // warp, so the fewer and larger the chunks the better (measured on the bench frame with the offsets already in HBM:
+  // 16 chunks 65.5 ms, 8 chunks 59.1 ms, 4 chunks 57.0 ms, 1 chunk 55.0 ms).  Default: as large as 40 % of the device
+  // memory allows (~450 bytes of queues and accumulators per sample).  When the offsets stream in from the host, chunk
+  // k+1's upload overlaps chunk k's kernels, so the chunks stay moderate (16 Mi samples) and the first one, whose
+  // upload nothing can overlap, is small.
+  std::vector<int> plan;  // rows per chunk
+  {
+    size_t want = (size_t)o->chunk_samples, first = want;
+    if (o->chunk_samples <= 0) {
+      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4);
+      want = std::min<size_t>((size_t)(0.4 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
+      if (host_offsets) want = std::min<size_t>(want, (size_t)16 << 20);
+      first = host_offsets ? std::min<size_t>(want, (size_t)4 << 20) : want;
+    }
+    int row = 0;
+    while (row < rows_local) {
+      const size_t w = plan.empty() ? first : want;
+      const int n = (int)std::max<size_t>(1, std::min<size_t>(w / row_samples, (size_t)(rows_local - row)));
+      plan.push_back(n);
+      row += n;
+    }
+  }
+  const int n_chunks = (int)plan.size();
+  const size_t chunk_samples = (size_t)*std::max_element(plan.begin(), plan.end()) * row_samples;  // largest chunk
+  if (chunk_samples > 0x7fffffffu) return rh::set_error(RH_ERR_ARG, "rh_render: chunk too large");
 
   int rc;
   uint8_t* d_rgb;
@@ -807,9 +832,11 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     uint32_t launches = 0;
     size_t upload_bytes = 0;
 
+    int next_row = 0;
     for (int ck = 0; ck < n_chunks; ck++) {
-      const int first_row = ck * rows_per_chunk;
-      const int n_rows = std::min(rows_per_chunk, rows_local - first_row);
+      const int first_row = next_row;
+      const int n_rows = plan[ck];
+      next_row += n_rows;
       ChunkParams P{};
       P.first_row = first_row;
       P.n_rows = n_rows;
@@ -860,7 +887,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         P.offsets = D->offsets[b].p;
       }
 
-      RH_CUDA(cudaMemsetAsync(D->accum.p, 0, chunk_samples * 3 * sizeof(double), D->stream));
+      RH_CUDA(cudaMemset2DAsync(D->accum.p, chunk_samples * sizeof(double), 0, (size_t)P.n_samples * sizeof(double), 3, D->stream));
       for (int pass = 0; pass < n_passes; pass++) {
         P.pass = pass;
         P.q_in.plane = (double2*)D->rayq[(pass + 1) & 1].p;
