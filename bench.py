@@ -196,6 +196,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rh.init(local_rank)
     L = capi.lib()
@@ -303,6 +304,18 @@ def main():
                 "note": "working set (4.6 MB scene) is L2-resident: the achievable bound is the random 128-B gather rate, "
                         "reported beside the HBM copy peak"}
 
+    # N > 1: the assembled frame must be the frame one GPU renders alone (SURVEY 8e parity gate); checked on rank 0
+    # outside the timed region.  The bench scene has no Transparent forks, so the sums are order-independent.
+    assembled_ok = None
+    if G > 1:
+        step_device()
+        full_host.copy_(full_dev)
+        torch.cuda.synchronize()
+        if rank == 0:
+            solo = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            rh.render_device(job, solo, spp=spp, offsets_dev=off_dev)
+            assembled_ok = bool(torch.equal(solo.cpu(), full_host))
+
     cpu = None
     if rank == 0 and G == 1 and not args.no_cpu_baseline:
         v, sample, _ = oracle_sample(sc, W, H, spp, off_host.numpy(), 15.0)
@@ -321,6 +334,8 @@ def main():
                 "rays_by_class_rank0": {k: int(st[k]) for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow",
                                                                 "rays_shadow_culled")},
                 "roofline": roofline, "cpu_baseline": cpu}
+        if assembled_ok is not None:
+            line["assembled_frame_equals_single_gpu_frame"] = assembled_ok
         print(json.dumps(line), flush=True)
     if G > 1:
         dist.destroy_process_group()
