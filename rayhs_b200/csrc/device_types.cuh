@@ -134,7 +134,10 @@ struct KernelCounters {  // RH_FLAG_COUNT only
 };
 struct FrameCounters {
   unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;
-  unsigned long long shadow_culled, pad_;  // (hit, light) pairs with l.n <= 0: Lambert term is exactly 0, query skipped
+  unsigned long long shadow_culled;  // (hit, light) pairs with l.n <= 0: Lambert term is exactly 0, query skipped
+  unsigned long long exact_walks;    // RH_FLAG_COUNT: shadow rays that took the exact (double box) walk
+  unsigned long long max_walk_nodes; // RH_FLAG_COUNT: most node records one shadow ray visited
+  unsigned long long pad_;
   KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow_kernel
 };
 

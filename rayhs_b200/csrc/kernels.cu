@@ -165,14 +165,22 @@ struct RayF {
   float mix, miy, miz;  // (o - e) * (1/d)
 };
 
-// True unless every |component| lies in [2^-100, 2^100): such rays take the exact double walk (zero components are
-// the reference's inf/NaN case; the range keeps 1/d and the products of the float test finite and normal).
-// Decided on the exponent bits, three integer compares.
-__device__ __forceinline__ bool degenerate_dir(const V3& d) {
+// Which rays take the exact double walk instead of the conservative float cull:
+//  * a direction component outside [2^-100, 2^100) in magnitude: zero components are the reference's inf/NaN case
+//    (SURVEY App. A-N1), and the range keeps 1/d and the products of the float test finite and normal;
+//  * an origin farther from the coordinate origin than 4096 x the largest box coordinate (a reflection that left the
+//    scene along an unbounded plane and looks back at it): float cannot resolve the boxes from there — the widened
+//    test would pass every box and the ray would visit the whole tree (measured: 331 k nodes for one shadow ray of the
+//    1 M-triangle synthetic scene, a one-second tail) — while the double test culls as usual.
+// Decided on the exponent bits with integer compares.
+__device__ __forceinline__ bool needs_exact_walk(const Ray& r, float abs_max) {
   const uint32_t lo = 0x39B00000u, span = 0x46300000u - 0x39B00000u;  // biased exponents 923 (2^-100) and 1123 (2^100)
-  const uint32_t hx = (uint32_t)__double2hiint(d.x) & 0x7fffffffu, hy = (uint32_t)__double2hiint(d.y) & 0x7fffffffu,
-                 hz = (uint32_t)__double2hiint(d.z) & 0x7fffffffu;
-  return !((hx - lo < span) & (hy - lo < span) & (hz - lo < span));
+  const uint32_t hx = (uint32_t)__double2hiint(r.d.x) & 0x7fffffffu, hy = (uint32_t)__double2hiint(r.d.y) & 0x7fffffffu,
+                 hz = (uint32_t)__double2hiint(r.d.z) & 0x7fffffffu;
+  const uint32_t lim = (uint32_t)__double2hiint(4096.0 * (double)abs_max);
+  const uint32_t ox = (uint32_t)__double2hiint(r.o.x) & 0x7fffffffu, oy = (uint32_t)__double2hiint(r.o.y) & 0x7fffffffu,
+                 oz = (uint32_t)__double2hiint(r.o.z) & 0x7fffffffu;
+  return !((hx - lo < span) & (hy - lo < span) & (hz - lo < span) & (ox < lim) & (oy < lim) & (oz < lim));
 }
 
 __device__ __forceinline__ RayF make_rayf(const Ray& r, float abs_max) {
@@ -924,7 +932,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(con
 
     Closest best;
     best.obj = -1;
-    if (valid) closest_hit<COUNT>(cx, r, P.exact_boxes || degenerate_dir(r.d), best, stack, cnt);
+    if (valid) closest_hit<COUNT>(cx, r, P.exact_boxes || needs_exact_walk(r, S.abs_max), best, stack, cnt);
 
     if (primary && valid && P.hit_ids) {
       int tri = -1;
@@ -1041,7 +1049,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
         continue;
       }
       const Ray sr = rayEps(p, ld);
-      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || degenerate_dir(sr.d), L, stack, cnt);
+      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || needs_exact_walk(sr, S.abs_max), L, stack, cnt);
       if (!shadowed) acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));
     }
     const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
@@ -1099,7 +1107,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
     const V3 p = mk(a.x, a.y, b.x);
     const rh_light& L = cx.lights[li];
     const ShadowRay sr = make_shadow_ray(L, p, light_dir(L, p));
-    const bool exact = P.exact_boxes || degenerate_dir(sr.r.d);
+    const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S.abs_max);
     const RayF f = make_rayf(sr.r, S.abs_max);
     bool hit = false;
     for (uint32_t k = 0; k < n_lin && !hit; k++) {
@@ -1152,7 +1160,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
             n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
           } else {
             const ShadowRay sr = make_shadow_ray(L, p, ld);
-            const bool exact = P.exact_boxes || degenerate_dir(sr.r.d);
+            const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S.abs_max);
             const RayF f = make_rayf(sr.r, S.abs_max);
             const float ffar = __double2float_ru(sr.far);
             bool shadowed = false;
@@ -1375,14 +1383,20 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
     sink.directional = q.directional;
     sink.lpos = q.lp;
     sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
-    const bool exact = P.exact_boxes || degenerate_dir(r.d);
+    const bool exact = P.exact_boxes || needs_exact_walk(r, S.abs_max);
     const RayF f = make_rayf(r, S.abs_max);
     bool hit = false;
+    unsigned long long nodes_before = 0;
+    if constexpr (COUNT) {
+      nodes_before = cnt.nodes;
+      if (exact) atomicAdd(&P.counters->exact_walks, 1ull);
+    }
     for (uint32_t m = 0; m < n_meshes && !hit; m++) {
       double bound = q.far;
       hit = exact ? traverse_exact<COUNT>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt)
                   : traverse<COUNT>(cx, sm.mesh_roots[m], r, f, bound, sink, stack, cnt);
     }
+    if constexpr (COUNT) atomicMax(&P.counters->max_walk_nodes, cnt.nodes - nodes_before);
     if (!hit && sphere_root != kEmpty) {
       double bound = q.far;
       hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, stack, cnt, true)
@@ -1497,7 +1511,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
               }
               // the root boxes themselves (slot 0 of each super-root)
               if (!may) {
-              } else if (P.exact_boxes || degenerate_dir(r.d)) {
+              } else if (P.exact_boxes || needs_exact_walk(r, S.abs_max)) {
                 need_walk = true;
               } else {
                 const RayF f = make_rayf(r, S.abs_max);

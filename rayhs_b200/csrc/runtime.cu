@@ -961,6 +961,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         for (int p = 1; p < n_passes; p++) stats->queued_rays += std::min<uint64_t>(ctl[ck].ray_count[p], cap);
       stats->shadow_tasks = shadow_tasks;
       stats->rays_shadow_culled = fc->shadow_culled;
+      if (counting && getenv("RAYHS_B200_DEBUG"))
+        fprintf(stderr, "rayhs_b200: exact shadow walks %llu, most nodes visited by one shadow ray %llu\n", fc->exact_walks,
+                fc->max_walk_nodes);
       stats->upload_bytes = upload_bytes;
       float ms = 0;
       cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
