@@ -225,8 +225,12 @@ enum {
   RH_FLAG_DEVICE_OFFSETS = 4, /* offsets is a DEVICE pointer (already uploaded, full-frame layout) */
   RH_FLAG_COUNT = 8,         /* run the instrumented kernels: fills box_tests .. texel_fetches (slower) */
   RH_FLAG_PROFILE = 16,      /* bracket every launch with CUDA events: fills ms_trace / ms_shadow / ms_resolve */
-  RH_FLAG_EXACT_BOXES = 32   /* validation: the reference's double slab test at every box instead of the
+  RH_FLAG_EXACT_BOXES = 32,  /* validation: the reference's double slab test at every box instead of the
                                 conservative float cull (same image) */
+  /* Shadow-ray schedule (same image either way; DESIGN.md "Kernels").  Default: the library times both on the
+   * first two large frames of a scene and keeps the faster one for that scene. */
+  RH_FLAG_SHADOW_POOLED = 64, /* one kernel per pass, tree walks in warp-local rounds of 32 (coherent rays)   */
+  RH_FLAG_SHADOW_SPLIT = 128  /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
 };
 
 /* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
@@ -263,6 +267,8 @@ typedef struct rh_stats {
   uint32_t chunks;
   uint32_t negative_channels; /* pixels with a channel whose toIntC is < 0 before the RGB8 clamp (App. A-Q2) */
   uint32_t queue_factor;      /* ray-queue capacity / chunk samples that was needed */
+  uint32_t shadow_split;      /* 1: this frame used the split shadow schedule (RH_FLAG_SHADOW_SPLIT or auto)  */
+  uint32_t pad_;
 } rh_stats;
 
 typedef struct rh_scene rh_scene; /* opaque; owns device copies */

@@ -8,7 +8,9 @@
 namespace rhd {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;    // KDTree.hs:61 `Empty`
-constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 31 bits = triangle count
+constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 30 bits = triangle (or sphere) count
+constexpr uint32_t kSphereLeafBit = 0x40000000u;  // ... a leaf of the sphere tree: `first` indexes sphere_refs
+constexpr uint32_t kCountMask = 0x3FFFFFFFu;
 constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
 constexpr int kStack = 112;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82) + leaf refinement levels
@@ -30,6 +32,18 @@ constexpr int kBlock = 128;                // resolve kernel
 #endif
 #ifndef RH_SHADOW_POOL
 #define RH_SHADOW_POOL 1
+#endif
+#ifndef RH_WALK_BLOCK
+#define RH_WALK_BLOCK 640  // threads per block of the shadow walk kernel (one block per SM): 640 -> up to 102 registers (measured best of 512, 640, 768)
+#endif
+#ifndef RH_WALK_UNROLL
+#define RH_WALK_UNROLL 2
+#endif
+#ifndef RH_REFILL_MIN
+#define RH_REFILL_MIN 16
+#endif
+#ifndef RH_SHADOW_SPLIT
+#define RH_SHADOW_SPLIT 1  // 0: one pooled shadow kernel per pass instead of classify -> walk -> fold
 #endif
 #ifndef RH_SHADOW_FAST
 #define RH_SHADOW_FAST 1  // 0: always use the general pooled kernel (A/B and validation builds)
@@ -124,6 +138,9 @@ struct ChunkCtl {
   uint32_t shadow_count[kMaxPasses + 2];  // shadow tasks produced by pass k
   uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors
   uint32_t shadow_cursor[kMaxPasses + 2];
+  // split shadow pipeline: low word = deferred hits, high word = (hit, light) pairs queued for a tree walk
+  unsigned long long deferred_walk_count[kMaxPasses + 2];
+  uint32_t walk_cursor[kMaxPasses + 2];
   uint32_t overflow;
   uint32_t pad_[3];
 };
@@ -182,11 +199,19 @@ struct ChunkParams {
   FrameCounters* counters;
   RayQueue q_in, q_out;
   ShadowQueue q_shadow;
+  // split shadow pipeline (classify -> walk -> fold)
+  uint2* walk_q;          // (shadow-queue item, light) pairs whose ray enters a tree's root box
+  uint32_t* deferred_q;   // shadow-queue items with at least one queued pair
+  uint8_t* pair_flags;    // [item * n_lights + light]: 1 = the pair adds nothing (l.n <= 0 or occluded)
+  uint32_t walk_capacity;
+  uint32_t pad3_;
 };
 
 // Launchers (kernels.cu).  `count` selects the instrumented instantiation (box/tri counters).
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
-void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream);
+// split: classify -> walk -> fold (3 launches) instead of one pooled kernel; only when shadow_split_possible(S)
+void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream);
+bool shadow_split_possible(const SceneView& S);
 void launch_resolve(const ChunkParams& P, void* stream);
 void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
                          void* stream);

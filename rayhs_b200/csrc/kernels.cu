@@ -386,9 +386,9 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
       }
     }
     if constexpr (SPHERES) {
-      if (test_sphere_leaf<COUNT>(cx, first, ref & ~kLeafBit, r, sink, bound, skip_emitters, cnt)) return true;
+      if (test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, skip_emitters, cnt)) return true;
     } else {
-      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+      if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt)) return true;
     }
     const float fb = __double2float_ru(bound);
     uint4 e;
@@ -452,9 +452,9 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
         continue;
       }
     } else if constexpr (SPHERES) {
-      if (test_sphere_leaf<COUNT>(cx, first, ref & ~kLeafBit, r, sink, bound, skip_emitters, cnt)) return true;
+      if (test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, skip_emitters, cnt)) return true;
     } else {
-      if (test_leaf<COUNT>(tris, first, ref & ~kLeafBit, r, sink, bound, cnt)) return true;
+      if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt)) return true;
     }
     if (sp == 0) return false;
     const uint4 e = stack[--sp];
@@ -1574,6 +1574,479 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
+// ------------------------------------------------------------------ K3 split: classify -> walk -> fold
+// The same work as shadow_kernel_fast, cut at the two places where its warps lose lanes:
+//   classify  one thread per shaded hit, all lights: everything that needs no tree (l.n <= 0, planes, linear spheres,
+//             root boxes).  A hit whose lights are all settled is folded and accumulated on the spot (accumDiffuse,
+//             RayHs.hs:89-97).  Otherwise the hit goes to the deferred list, its settled lights are flagged, and every
+//             (hit, light) pair whose ray enters a root box goes to the walk queue.  Warps never diverge on tree work.
+//   walk      persistent warps over the walk queue with PER-LANE refill: a lane whose ray has ended (occluder found or
+//             stack empty) takes the next queued pair while its neighbours keep walking, so the long unoccluded rays
+//             no longer hold 31 idle lanes (ncu, pooled kernel: 16-22 active threads per instruction in the dragon
+//             chunks, 1.7 on the synthetic triangle soup).  The loop is warp-uniform — votes decide between the refill,
+//             inner-node and leaf steps — so the lanes reconverge at every step by construction.
+//   fold      one thread per deferred hit: lightAt + diffuse for the lights still unflagged, in order, then accumulate.
+__device__ __forceinline__ void stage_shadow_tables(ShadowTables& sm, const SceneView& S, bool with_nodes) {
+  const uint32_t n_meshes = S.n_occ_meshes, n_lights = S.n_lights;
+  if (with_nodes) copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
+  copy16(sm.planes, S.occ_planes, S.n_occ_planes * (uint32_t)sizeof(OccPlane));
+  copy16(sm.spheres, S.occ_spheres, S.n_occ_spheres * (uint32_t)sizeof(OccSphere));
+  copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
+  const uint32_t n_roots = n_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  if (threadIdx.x < n_roots) {
+    const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : S.sphere_root;
+    sm.mesh_roots[threadIdx.x] = root;
+    const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
+    for (int a = 0; a < 3; a++) {
+      const double lo = (double)fb[a], hi = (double)fb[3 + a];
+      sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
+      sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_roots * n_lights) {
+    const uint32_t li = threadIdx.x / n_roots, m = threadIdx.x % n_roots;
+    uint32_t side = 0;
+    if (sm.lights[li].kind != RH_LIGHT_DIRECTIONAL)
+      for (int a = 0; a < 3; a++) {
+        if (sm.lights[li].vec[a] < sm.rootbox[m][a]) side |= 1u << a;
+        if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
+      }
+    sm.light_side[li][m] = (uint8_t)side;
+  }
+  __syncthreads();
+}
+
+// Light direction and shadow ray of a (hit, light) pair (Light.hs:12-17, RayHs.hs:93).  `far` bounds the distance from
+// the ray origin to the light from above (|o - L| <= |o - p| + |p - L| = 1e-6 |ld| + dd); it only prunes — whether a hit
+// is in front of the light is always decided by inFrontOfLight's own comparison (dl2 = +inf for a directional light).
+struct LightPair {
+  V3 ld, o, lp;
+  double dd, far;
+  bool directional;
+};
+__device__ __forceinline__ LightPair make_light_pair(const rh_light& L, const V3& p) {
+  LightPair q;
+  q.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
+  q.lp = ld3(L.vec);
+  if (q.directional) {
+    q.ld = q.lp;
+    q.dd = 0;
+    q.far = __longlong_as_double(0x7ff0000000000000LL);
+  } else {
+    const V3 dv = q.lp - p;
+    q.dd = sqrt(sqrLen(dv));  // dist lightPos p, Vec.hs:118-122
+    q.ld = mul(1 / q.dd, dv);
+    q.far = (q.dd + kEps) * 1.000001;
+  }
+  q.o = p + mul(kEps, q.ld);  // rayEps, Geometry.hs:36
+  return q;
+}
+
+// Planes and linear spheres of shadowIntersection (RayHs.hs:74-87) for one pair; true = occluded.
+template <bool COUNT>
+__device__ __forceinline__ bool primitives_occlude(const ShadowTables& sm, uint32_t n_planes, uint32_t n_spheres,
+                                                   const LightPair& q, Cnt<COUNT>& cnt) {
+  uint32_t maybe = 0;
+  for (uint32_t k = 0; k < n_planes; k++) {  // straight-line: see shadow_kernel_fast
+    const double2* pl = (const double2*)&sm.planes[k];
+    const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
+    const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
+    RH_CNT(prim, 1);
+    const double den = dot(q.ld, pn);
+    const double num = dot(pn, pp - q.o);
+    const bool miss = !(fabs(den) > 0) | (((num > 0) != (den > 0)) & (num == num)) |
+                      (fabs(num) > q.far * fabs(den) * 1.000000000001);
+    maybe |= (miss ? 0u : 1u) << k;
+  }
+  if (!(maybe | n_spheres)) return false;
+  Ray r;
+  r.o = q.o;
+  r.d = q.ld;
+  AnyHit sink;
+  sink.directional = q.directional;
+  sink.lpos = q.lp;
+  sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
+  bool shadowed = false;
+  while (maybe) {  // cold: exact quotient and inFrontOfLight for the surviving planes (Geometry.hs:70-79)
+    const uint32_t k = __ffs(maybe) - 1;
+    maybe &= maybe - 1;
+    const V3 pp = ld3(sm.planes[k].p), pn = ld3(sm.planes[k].n);
+    const double time = dot(pn, pp - r.o) / dot(r.d, pn);
+    if (time > 0 && sink.in_front(r, time)) shadowed = true;
+  }
+  for (uint32_t k = 0; k < n_spheres && !shadowed; k++) {  // Geometry.hs:81-95
+    const V3 ct = ld3(sm.spheres[k].c);
+    const double rad = sm.spheres[k].r;
+    RH_CNT(prim, 1);
+    const double qa = dot(r.d, r.d);
+    const double qb = 2.0 * dot(r.d, r.o - ct);
+    const double qc = sqrLen(r.o - ct) - rad * rad;
+    const double delta = qb * qb - 4.0 * qa * qc;
+    if (delta < 0.0) continue;
+    const double t0 = 0.5 * ((-qb) - sqrt(delta)) / qa;
+    double time;
+    if (t0 > 0) time = t0;
+    else {
+      const double t1 = 0.5 * ((-qb) + sqrt(delta)) / qa;
+      if (!(t1 > 0)) continue;
+      time = t1;
+    }
+    shadowed = sink.in_front(r, time);
+  }
+  return shadowed;
+}
+
+// Does the pair's ray have to walk a tree?  Only the part of the ray between its origin and the light can hold an
+// occluder (inFrontOfLight).  The origin is within 1.000001e-6 of p in every coordinate, so when p and the light lie
+// beyond the same face of a (padded) root box, that part is outside the box; otherwise the root boxes get the float
+// slab test (slot 0 of each super-root).
+template <bool COUNT>
+__device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const SceneView& S, bool exact_boxes, uint32_t n_roots,
+                                                uint32_t li, const V3& p, const LightPair& q, Cnt<COUNT>& cnt) {
+  bool may = exact_boxes;
+  for (uint32_t m = 0; m < n_roots; m++) {
+    const double* rb = sm.rootbox[m];
+    const uint32_t side = (p.x < rb[0] ? 1u : 0u) | (p.y < rb[1] ? 2u : 0u) | (p.z < rb[2] ? 4u : 0u) |
+                          (p.x > rb[3] ? 8u : 0u) | (p.y > rb[4] ? 16u : 0u) | (p.z > rb[5] ? 32u : 0u);
+    may |= (side & sm.light_side[li][m]) == 0;
+  }
+  if (!may) return false;
+  Ray r;
+  r.o = q.o;
+  r.d = q.ld;
+  if (exact_boxes || needs_exact_walk(r, S.abs_max)) return true;
+  const RayF f = make_rayf(r, S.abs_max);
+  const float ffar = __double2float_ru(q.far);
+  bool need = false;
+  for (uint32_t m = 0; m < n_roots && !need; m++) {
+    const float4* np = (const float4*)&S.wide32[sm.mesh_roots[m]];
+    const float4 b0 = __ldg(np), b1 = __ldg(np + 1);
+    float tm;
+    RH_CNT(nodes, 1);
+    RH_CNT(box, 1);
+    need = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
+  }
+  return need;
+}
+
+constexpr int kClassifyBlock = 256;
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(const __grid_constant__ SceneView S,
+                                                                         const __grid_constant__ ChunkParams P) {
+  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
+  stage_shadow_tables(sm, S, false);
+  const uint32_t n_lights = S.n_lights, n_planes = S.n_occ_planes, n_spheres = S.n_occ_spheres;
+  const uint32_t n_roots = S.n_occ_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
+  const size_t cap = P.q_shadow.capacity;
+  const double2* qp = P.q_shadow.plane;
+  unsigned long long n_culled = 0;
+  const uint32_t stride = gridDim.x * kClassifyBlock;
+  const uint32_t n_rounds = (n_items + stride - 1) / stride;  // every warp runs the same number of rounds (ballots below)
+  for (uint32_t round = 0; round < n_rounds; round++) {
+    const uint32_t item = round * stride + blockIdx.x * kClassifyBlock + threadIdx.x;
+    uint32_t pending = 0, settled = 0;  // per light: queued for a walk / adds nothing
+    if (item < n_items) {
+      const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
+      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
+      V3 acc = mk(0, 0, 0), cd = mk(0, 0, 0);  // foldl ... black lts
+      bool have_cd = false;
+      for (uint32_t li = 0; li < n_lights; li++) {
+        const rh_light& L = sm.lights[li];
+        const LightPair q = make_light_pair(L, p);
+        const double ldn = dot(q.ld, n);
+        if (ldn <= 0) {  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
+          n_culled++;
+          settled |= 1u << li;
+          continue;
+        }
+        if (primitives_occlude<COUNT>(sm, n_planes, n_spheres, q, cnt)) {
+          settled |= 1u << li;  // Just _ -> black
+          continue;
+        }
+        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, n_roots, li, p, q, cnt)) {
+          pending |= 1u << li;
+          continue;
+        }
+        if (pending) continue;  // the fold kernel redoes this hit: no point in the term
+        if (!have_cd) {
+          const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
+          cd = mk(d.x, d.y, e.x);
+          have_cd = true;
+        }
+        V3 lc = ld3(L.color);  // lightAt, Light.hs:14-17
+        if (!q.directional) {
+          const double s = 1.0 + q.dd / L.radius;
+          lc = mul(1.0 / (s * s), lc);
+        }
+        acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+      }
+      if (!pending) {
+        const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
+        const uint32_t sbits = P.q_shadow.sample[item];
+        cd = mk(d.x, d.y, e.x);
+        const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;  // Diffuse adds the ambient term, RayHs.hs:111-114
+        accumulate(P, sbits & 0x7fffffffu, e.y, total);
+      } else {
+        for (uint32_t li = 0; li < n_lights; li++) P.pair_flags[(size_t)item * n_lights + li] = (uint8_t)((settled >> li) & 1u);
+      }
+    }
+    // warp-aggregated append: one 64-bit atomic reserves the deferred slots (low word) and the walk slots (high word).
+    // The warp's pairs go in light-major order — all its pairs for light 0, then light 1, ... — so that consecutive
+    // queue entries are rays from neighbouring hits towards the same light, as coherent as the hits themselves.
+    const unsigned has = __ballot_sync(kFull, pending != 0);
+    if (has) {
+      uint32_t total_walks = 0, my_at = 0;  // my_at: offset of this lane's entry for the light being counted
+      uint32_t offs[kFastLights];
+#pragma unroll
+      for (uint32_t li = 0; li < (uint32_t)kFastLights; li++) {
+        offs[li] = 0;
+        if (li < n_lights) {
+          const unsigned m = __ballot_sync(kFull, (pending >> li) & 1u);
+          offs[li] = total_walks + __popc(m & ((1u << lane) - 1));
+          total_walks += __popc(m);
+        }
+      }
+      (void)my_at;
+      unsigned long long base = 0;
+      if (lane == 0)
+        base = atomicAdd(&ctl->deferred_walk_count[P.pass], ((unsigned long long)total_walks << 32) | (unsigned long long)__popc(has));
+      base = __shfl_sync(kFull, base, 0);
+      if (pending) {
+        const uint32_t dslot = (uint32_t)base + __popc(has & ((1u << lane) - 1));
+        P.deferred_q[dslot] = item;  // deferred hits <= shadow tasks <= capacity
+#pragma unroll
+        for (uint32_t li = 0; li < (uint32_t)kFastLights; li++) {
+          if (li < n_lights && ((pending >> li) & 1u)) {
+            const uint32_t w = (uint32_t)(base >> 32) + offs[li];
+            if (w < P.walk_capacity) P.walk_q[w] = make_uint2(item, li);
+            else ctl->overflow = 1;
+          }
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
+  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
+  flush_counters<COUNT>(cnt, P.counters, 1);
+}
+
+constexpr int kWalkBlock = RH_WALK_BLOCK;
+constexpr uint32_t kWalkChunk = 256;   // walk-queue entries a warp claims per atomic
+constexpr uint32_t kRefillMin = RH_REFILL_MIN;  // idle lanes that trigger a refill while other lanes are still walking
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWalkBlock, 1) shadow_walk_kernel(const __grid_constant__ SceneView S,
+                                                                                     const __grid_constant__ ChunkParams P) {
+  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
+  stage_shadow_tables(sm, S, true);
+  Ctx cx;
+  cx.S = &S;
+  cx.sm_nodes = sm.nodes;
+  cx.objects = S.objects;  // sphere-tree leaves only
+  cx.materials = S.materials;
+  cx.lights = sm.lights;
+  const uint32_t n_lights = S.n_lights, n_roots = S.n_occ_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  const uint32_t n_smem = S.n_smem_nodes;
+  const rh_tri* tris = S.tris;
+  uint4 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_items = min((uint32_t)(ctl->deferred_walk_count[P.pass] >> 32), P.walk_capacity);
+  const size_t cap = P.q_shadow.capacity;
+  const double2* qp = P.q_shadow.plane;
+
+  uint32_t pos = 0, end = 0;  // this warp's claimed range of the walk queue
+  bool exhausted = false;
+  // Lane state: the ray in flight.  What every inner-node step needs stays in registers (the float ray, the node
+  // reference, the stack pointer); what only a leaf needs — the double ray, the light distance, where to report an
+  // occluder — lives in a per-thread column of shared memory, so that the node loop does not spill.
+  double* lane_mem = reinterpret_cast<double*>(rh_smem + sizeof(ShadowTables)) + threadIdx.x;
+  auto lane_slot = [&](int k) -> double& { return lane_mem[k * kWalkBlock]; };  // 0-2 o, 3-5 d, 6 far, 7 dl2, 8 flag index
+  bool active = false, directional = false;
+  RayF f;
+  f.ix = f.iy = f.iz = f.pix = f.piy = f.piz = f.mix = f.miy = f.miz = 0.f;
+  float ffar = 0;
+  uint32_t ref = 0, first = 0;
+  int sp = 0;
+
+  for (;;) {
+    // ---- refill: idle lanes take the next queued pairs
+    const unsigned idle = __ballot_sync(kFull, !active);
+    const uint32_t n_idle = __popc(idle);
+    if (n_idle >= kRefillMin) {
+      if (pos == end && !exhausted) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&ctl->walk_cursor[P.pass], kWalkChunk);
+        b = __shfl_sync(kFull, b, 0);
+        if (b >= n_items) exhausted = true;
+        else {
+          pos = b;
+          end = min(b + kWalkChunk, n_items);
+        }
+      }
+      if (pos < end) {
+        const uint32_t take = min(n_idle, end - pos);
+        const uint32_t rank = __popc(idle & ((1u << lane) - 1));
+        if (!active && rank < take) {
+          const uint2 e = P.walk_q[pos + rank];
+          const uint32_t item = e.x, li = e.y;
+          const double2 a = qp[item], b = qp[cap + item];
+          const LightPair q = make_light_pair(sm.lights[li], mk(a.x, a.y, b.x));
+          Ray r;
+          r.o = q.o;
+          r.d = q.ld;
+          AnyHit sink;
+          sink.directional = q.directional;
+          sink.lpos = q.lp;
+          sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
+          const size_t flag_at = (size_t)item * n_lights + li;
+          if (P.exact_boxes || needs_exact_walk(r, S.abs_max)) {
+            // rare (far origins): the reference's own double boxes, run to the end right here
+            if constexpr (COUNT) atomicAdd(&P.counters->exact_walks, 1ull);
+            bool hit = false;
+            for (uint32_t m = 0; m < n_roots && !hit; m++) {
+              double bound = q.far;
+              if (m < S.n_occ_meshes) hit = traverse_exact<COUNT>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt);
+              else hit = traverse_exact<COUNT, AnyHit, true>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt, true);
+            }
+            if (hit) P.pair_flags[flag_at] = 1;
+          } else {
+            lane_slot(0) = r.o.x; lane_slot(1) = r.o.y; lane_slot(2) = r.o.z;
+            lane_slot(3) = r.d.x; lane_slot(4) = r.d.y; lane_slot(5) = r.d.z;
+            lane_slot(6) = q.far;
+            lane_slot(7) = sink.dl2;
+            lane_slot(8) = __longlong_as_double((long long)flag_at);
+            directional = q.directional;
+            f = make_rayf(r, S.abs_max);
+            ffar = __double2float_ru(q.far);
+            sp = 0;
+            for (uint32_t m = 1; m < n_roots; m++) stack[sp++] = make_uint4(sm.mesh_roots[m], 0, 0, 0);  // entry distance 0
+            ref = sm.mesh_roots[0];
+            first = 0;
+            active = true;
+          }
+        }
+        pos += take;
+      } else if (n_idle == 32) {
+        break;  // nothing in flight, nothing left to claim
+      }
+    }
+    // ---- inner nodes: step until every ray in flight holds a leaf (KDTree.hs:96-107 with the conservative float boxes);
+    // two steps per vote
+    auto node_step = [&]() {
+      const float4* np = ref < n_smem ? (const float4*)&sm.nodes[ref] : (const float4*)&S.wide32[ref];
+      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
+      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
+      RH_CNT(nodes, 1);
+      bool h0 = false, h1 = false;
+      float tm0 = 0, tm1 = 0;
+      if (cw.x != kEmpty) {
+        RH_CNT(box, 1);
+        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > ffar);
+      }
+      if (cw.y != kEmpty) {
+        RH_CNT(box, 1);
+        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > ffar);
+      }
+      if (h0 && h1) {
+        if (tm1 < tm0) {
+          stack[sp++] = make_uint4(cw.x, cw.z, 0, 0);
+          ref = cw.y;
+          first = cw.w;
+        } else {
+          stack[sp++] = make_uint4(cw.y, cw.w, 0, 0);
+          ref = cw.x;
+          first = cw.z;
+        }
+      } else if (h0) {
+        ref = cw.x;
+        first = cw.z;
+      } else if (h1) {
+        ref = cw.y;
+        first = cw.w;
+      } else if (sp == 0) {
+        active = false;  // nothing in front of the light
+      } else {
+        const uint4 e = stack[--sp];
+        ref = e.x;
+        first = e.y;
+      }
+    };
+    for (;;) {
+      bool inner = active && !(ref & kLeafBit);
+      if (!__any_sync(kFull, inner)) break;
+      if (inner) node_step();
+#if RH_WALK_UNROLL > 1
+      inner = active && !(ref & kLeafBit);
+      if (inner) node_step();
+#endif
+    }
+    // ---- leaves: every ray in flight holds one (Mesh.hs:59-82 / Geometry.hs:81-95 per candidate)
+    if (active) {
+      Ray r;
+      r.o = mk(lane_slot(0), lane_slot(1), lane_slot(2));
+      r.d = mk(lane_slot(3), lane_slot(4), lane_slot(5));
+      double bound = lane_slot(6);
+      AnyHit sink;
+      sink.directional = directional;
+      sink.lpos = mk(0, 0, 0);
+      sink.dl2 = lane_slot(7);
+      bool hit;
+      if (ref & kSphereLeafBit) hit = test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, true, cnt);
+      else hit = test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt);
+      if (hit) {
+        P.pair_flags[(size_t)__double_as_longlong(lane_slot(8))] = 1;  // shadowIntersection = Just _
+        active = false;
+      } else if (sp == 0) {
+        active = false;
+      } else {
+        const uint4 e = stack[--sp];
+        ref = e.x;
+        first = e.y;
+      }
+    }
+  }
+  flush_counters<COUNT>(cnt, P.counters, 1);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kClassifyBlock) shadow_fold_kernel(const __grid_constant__ SceneView S,
+                                                                     const __grid_constant__ ChunkParams P) {
+  __shared__ rh_light lights[kFastLights];
+  const uint32_t n_lights = S.n_lights;
+  copy16(lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
+  __syncthreads();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = min((uint32_t)ctl->deferred_walk_count[P.pass], P.q_shadow.capacity);
+  const size_t cap = P.q_shadow.capacity;
+  const double2* qp = P.q_shadow.plane;
+  for (uint32_t i = blockIdx.x * kClassifyBlock + threadIdx.x; i < n_items; i += gridDim.x * kClassifyBlock) {
+    const uint32_t item = P.deferred_q[i];
+    const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
+    const uint32_t sbits = P.q_shadow.sample[item];
+    const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+    const uint8_t* fl = P.pair_flags + (size_t)item * n_lights;
+    V3 acc = mk(0, 0, 0);  // foldl ... black lts
+    for (uint32_t li = 0; li < n_lights; li++) {
+      if (fl[li]) continue;  // Just _ -> black (or l.n <= 0: the term is exactly 0)
+      V3 ld, lc;
+      light_at(lights[li], p, ld, lc);
+      acc = acc + mul(hs_max(dot(ld, n), 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+    }
+    const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
+    accumulate(P, sbits & 0x7fffffffu, e.y, total);
+  }
+}
+
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
 __device__ __forceinline__ int to_int_c(double c, bool& negative) {
   const double v = 255 * hs_min(c, 1);  // hs_min NaN 1 = 1
@@ -1689,6 +2162,11 @@ constexpr size_t kShadowFastSmem =
     sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * 12 * sizeof(double2));
 static_assert(kShadowFastSmem <= 227 * 1024, "fast shadow kernel shared memory");
 
+constexpr size_t kWalkSmem = sizeof(ShadowTables) + 9 * kWalkBlock * sizeof(double);  // tables + per-thread ray columns
+static int g_classify_grid[2] = {148, 148};
+static int g_walk_grid = 148;
+bool shadow_split_possible(const SceneView& S) { return S.shadow_fast && RH_SHADOW_SPLIT && RH_SHADOW_POOL; }
+
 int configure_kernels() {
   cudaError_t e = cudaSuccess;
   auto set = [&](const void* fn, size_t bytes) {
@@ -1700,8 +2178,20 @@ int configure_kernels() {
   set((const void*)shadow_kernel<false>, kShadowSmem);
   set((const void*)shadow_kernel_fast<true>, kShadowFastSmem);
   set((const void*)shadow_kernel_fast<false>, kShadowFastSmem);
+  set((const void*)shadow_walk_kernel<true>, kWalkSmem);
+  set((const void*)shadow_walk_kernel<false>, kWalkSmem);
   set((const void*)shadow_kernel_simple<true>, kShadowSmem);
   set((const void*)shadow_kernel_simple<false>, kShadowSmem);
+  if (e == cudaSuccess) {
+    int dev = 0, sms = 0, nb = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shadow_classify_kernel<false>, kClassifyBlock, sizeof(ShadowTables));
+    g_classify_grid[0] = sms * (nb > 0 ? nb : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shadow_classify_kernel<true>, kClassifyBlock, sizeof(ShadowTables));
+    g_classify_grid[1] = sms * (nb > 0 ? nb : 1);
+    g_walk_grid = sms;  // persistent: one block per SM
+  }
   return (int)e;
 }
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
@@ -1710,9 +2200,20 @@ void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams
   else
     trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, (cudaStream_t)stream>>>(S, cam, P);
 }
-void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, int grid, void* stream) {
+void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream) {
   const bool simple = S.n_lights > 32 || RH_SHADOW_POOL == 0;
-  if (S.shadow_fast && RH_SHADOW_FAST && !simple) {
+  if (split && shadow_split_possible(S)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count) {
+      shadow_classify_kernel<true><<<g_classify_grid[1], kClassifyBlock, sizeof(ShadowTables), st>>>(S, P);
+      shadow_walk_kernel<true><<<g_walk_grid, kWalkBlock, kWalkSmem, st>>>(S, P);
+      shadow_fold_kernel<true><<<g_classify_grid[1], kClassifyBlock, 0, st>>>(S, P);
+    } else {
+      shadow_classify_kernel<false><<<g_classify_grid[0], kClassifyBlock, sizeof(ShadowTables), st>>>(S, P);
+      shadow_walk_kernel<false><<<g_walk_grid, kWalkBlock, kWalkSmem, st>>>(S, P);
+      shadow_fold_kernel<false><<<g_classify_grid[0], kClassifyBlock, 0, st>>>(S, P);
+    }
+  } else if (S.shadow_fast && RH_SHADOW_FAST && !simple) {
     if (count)
       shadow_kernel_fast<true><<<grid, kShadowBlock, kShadowFastSmem, (cudaStream_t)stream>>>(S, P);
     else

@@ -79,7 +79,7 @@ struct Device {
   cudaStream_t copy_stream = nullptr;  // sample-offset uploads
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  DevBuf accum, rayq[2], shq, shq_sample, ctl, counters, offsets[2], rgb, ids;
+  DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, ctl, counters, offsets[2], rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
   size_t pinned_bytes = 0;
   int grid_trace[2] = {0, 0}, grid_shadow[2] = {0, 0};
@@ -113,7 +113,8 @@ struct Device {
   void close() {
     if (dev < 0) return;
     cudaSetDevice(dev);
-    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &ctl, &counters, &offsets[0], &offsets[1], &rgb, &ids})
+    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &walk_q, &deferred_q, &pair_flags, &ctl, &counters, &offsets[0],
+                      &offsets[1], &rgb, &ids})
       b->release();
     if (pinned) cudaFreeHost(pinned);
     pinned = nullptr;
@@ -139,6 +140,10 @@ struct rh_scene {
   DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes;
   SceneView view{};
   uint32_t max_tree_depth = 0;
+  // shadow schedule chosen for this scene: 0 = undecided (frame 1 runs pooled, frame 2 split, both timed), 1 = pooled, 2 = split
+  mutable int shadow_mode = 0;
+  mutable int tune_frames = 0;
+  mutable double tune_ns_per_task[2] = {0, 0};
 };
 
 namespace {
@@ -279,7 +284,7 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
         const rh_node& nd = d.nodes[ni];
         if (nd.is_leaf) {
           if ((uint64_t)nd.left + nd.right > d.n_tris) return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaf range out of bounds");
-          if (nd.right >= kLeafBit) return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaf too large");
+          if (nd.right > kCountMask) return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaf too large");
           if (any_leaf && nd.left < last_first)
             return rh::set_error(RH_ERR_ARG, "rh_scene_create: leaves must store their triangles in left-to-right leaf order");
           last_first = nd.left;
@@ -325,7 +330,7 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
     memcpy(box, nd.lo, 3 * sizeof(double));
     memcpy(box + 3, nd.hi, 3 * sizeof(double));
     if (nd.is_leaf) {
-      w.child[slot] = kLeafBit | nd.right;
+      w.child[slot] = kLeafBit | (ni >= d.n_nodes ? kSphereLeafBit : 0u) | nd.right;
       w.first[slot] = nd.left;
     } else {
       work.push_back({ni, 0, depth + 1});  // wide_index assigned when popped
@@ -714,7 +719,17 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const bool dev_out = (o->flags & RH_FLAG_DEVICE_OUT) != 0;
   const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
   const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
-  const bool profile = (o->flags & RH_FLAG_PROFILE) != 0;
+  // shadow schedule: forced by a flag, else the scene's choice, else this is a timing frame of the choice
+  const bool split_ok = shadow_split_possible(scene->view);
+  bool use_split = false, tuning = false;
+  if (o->flags & RH_FLAG_SHADOW_SPLIT) use_split = split_ok;
+  else if (o->flags & RH_FLAG_SHADOW_POOLED) use_split = false;
+  else if (split_ok && scene->shadow_mode != 0) use_split = scene->shadow_mode == 2;
+  else if (split_ok && !(o->flags & RH_FLAG_COUNT)) {
+    tuning = true;
+    use_split = scene->tune_frames == 1;
+  }
+  const bool profile = (o->flags & RH_FLAG_PROFILE) != 0 || tuning;
   const bool exact_boxes = (o->flags & RH_FLAG_EXACT_BOXES) != 0;
 
   RH_CUDA(cudaSetDevice(D->dev));
@@ -734,7 +749,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   {
     size_t want = (size_t)o->chunk_samples, first = want;
     if (o->chunk_samples <= 0) {
-      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4);
+      const size_t L = std::max<uint32_t>(1, scene->view.n_lights);
+      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4 + 4 + L * (sizeof(uint2) + 1));
       want = std::min<size_t>((size_t)(0.4 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
       if (host_offsets) want = std::min<size_t>(want, (size_t)16 << 20);
       first = host_offsets ? std::min<size_t>(want, (size_t)4 << 20) : want;
@@ -808,6 +824,13 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       if ((rc = D->rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
     if ((rc = D->shq.reserve(cap * 5 * sizeof(double2)))) return rc;
     if ((rc = D->shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
+    const bool split = use_split;
+    const size_t walk_cap = std::min<size_t>(cap * std::max<uint32_t>(1, scene->view.n_lights), 0xfffffff0u);
+    if (split) {
+      if ((rc = D->walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
+      if ((rc = D->deferred_q.reserve(cap * sizeof(uint32_t)))) return rc;
+      if ((rc = D->pair_flags.reserve(cap * scene->view.n_lights))) return rc;
+    }
 
     size_t ev_used = 0;
     auto prof_event = [&]() -> cudaEvent_t {
@@ -862,6 +885,10 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.q_shadow.plane = (double2*)D->shq.p;
       P.q_shadow.sample = (uint32_t*)D->shq_sample.p;
       P.q_shadow.capacity = (uint32_t)cap;
+      P.walk_q = (uint2*)D->walk_q.p;
+      P.deferred_q = (uint32_t*)D->deferred_q.p;
+      P.pair_flags = (uint8_t*)D->pair_flags.p;
+      P.walk_capacity = (uint32_t)walk_cap;
 
       if (stream_offsets) {
         // upload this chunk's rows (runs of image rows that are contiguous inside one band) on the copy stream
@@ -898,9 +925,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         if (profile) a = prof_event();
         launch_trace(scene->view, cam, P, counting, D->grid_trace[counting], D->stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
-        launch_shadow(scene->view, P, counting, D->grid_shadow[counting], D->stream);
+        launch_shadow(scene->view, P, counting, use_split, D->grid_shadow[counting], D->stream);
         if (profile) spans.push_back({a, prof_event(), 1});
-        launches += 2;
+        launches += 1 + (use_split ? 3 : 1);
       }
       cudaEvent_t a = nullptr;
       if (profile) a = prof_event();
@@ -979,6 +1006,26 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->chunks = (uint32_t)n_chunks;
       stats->negative_channels = (uint32_t)std::min<unsigned long long>(fc->negative_channels, 0xffffffffu);
       stats->queue_factor = factor;
+      stats->shadow_split = use_split ? 1 : 0;
+    }
+    if (tuning) {
+      // only frames with enough shadow work to time say anything (1 M shaded hits ~ 0.3 ms)
+      const ChunkCtl* c2 = (const ChunkCtl*)D->pinned;
+      uint64_t tasks = 0;
+      double ms = 0;
+      for (int ck = 0; ck < n_chunks; ck++)
+        for (int p = 0; p < n_passes; p++) tasks += c2[ck].shadow_count[p];
+      for (const Span& sp : spans)
+        if (sp.kind == 1) {
+          float m = 0;
+          cudaEventElapsedTime(&m, sp.a, sp.b);
+          ms += m;
+        }
+      if (tasks >= (1u << 20)) {
+        scene->tune_ns_per_task[scene->tune_frames] = ms * 1e6 / (double)tasks;
+        if (++scene->tune_frames == 2)
+          scene->shadow_mode = scene->tune_ns_per_task[1] < scene->tune_ns_per_task[0] ? 2 : 1;
+      }
     }
     return RH_OK;
   }

@@ -11,13 +11,16 @@ RES = {"cornellBox": (256, 256), "texture": (320, 180), "transform": (320, 180),
        "dragon_low": (320, 180), "dragon_full": (320, 180), "outScene": (320, 180)}
 
 
+@pytest.mark.parametrize("shadow", ["pooled", "split"])
 @pytest.mark.parametrize("name", SCENES)
-def test_one_sample_parity(name):
-    """rayTrace (RayHs.hs:161-166): hit ids bit-exact, image within tolerance, ray counts equal."""
+def test_one_sample_parity(name, shadow):
+    """rayTrace (RayHs.hs:161-166): hit ids bit-exact, image within tolerance, ray counts equal — with either
+    shadow-ray schedule (one pooled kernel per pass, or classify -> walk -> fold)."""
     sc = load_scene(name)
     w, h = RES[name]
     job = rh.renderingFromScene(sc, w, h)
-    img = rh.render(job, want_hit_ids=True)
+    img = rh.render(job, want_hit_ids=True, shadow=shadow)
+    assert img.stats["shadow_split"] == (1 if shadow == "split" else 0)
     ref = oracle_for(sc).render(sc.camera, w, h, sc.max_depth)
     ids_gpu = img.hit_ids.reshape(h, w, 2)
     ids_ref = ref["hit_ids"].reshape(h, w, 2)
@@ -79,3 +82,16 @@ def test_float_cull_equals_exact_boxes(name):
     assert m["maxdiff"] <= 1 and m["exact"] >= 0.99999, m
     for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"):
         assert fast.stats[k] == exact.stats[k], k
+
+
+def test_shadow_schedule_is_chosen_per_scene_and_keeps_the_bytes():
+    """Default flags: the first two large frames of a scene are timed (pooled, then split) and the faster schedule is
+    kept; every frame must carry the same bytes whichever schedule rendered it."""
+    sc = load_scene("dragon_low")
+    w, h = 1600, 900   # > 1 Mi shaded hits: counts as a timing frame
+    job = rh.renderingFromScene(sc, w, h)
+    frames = [rh.render(job) for _ in range(3)]
+    assert [f.stats["shadow_split"] for f in frames[:2]] == [0, 1]
+    assert np.array_equal(frames[0].pixels, frames[1].pixels) and np.array_equal(frames[0].pixels, frames[2].pixels)
+    forced = rh.render(job, shadow="split")
+    assert forced.stats["shadow_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
