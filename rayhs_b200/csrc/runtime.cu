@@ -78,8 +78,8 @@ struct Device {
   cudaStream_t stream = nullptr;       // kernels
   cudaStream_t copy_stream = nullptr;  // sample-offset uploads
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, ctl, counters, offsets[2], rgb, ids;
+  std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
+  DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, ctl, counters, offsets, rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
   size_t pinned_bytes = 0;
   int grid_trace[2] = {0, 0}, grid_shadow[2] = {0, 0};
@@ -98,10 +98,6 @@ struct Device {
     RH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     RH_CUDA(cudaEventCreate(&ev_begin));
     RH_CUDA(cudaEventCreate(&ev_end));
-    for (int k = 0; k < 2; k++) {
-      RH_CUDA(cudaEventCreateWithFlags(&ev_up[k], cudaEventDisableTiming));
-      RH_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
-    }
     RH_CUDA((cudaError_t)configure_kernels());
     for (int c = 0; c < 2; c++) {
       grid_trace[c] = n_sms * std::max(1, trace_blocks_per_sm(c != 0));
@@ -113,16 +109,20 @@ struct Device {
   void close() {
     if (dev < 0) return;
     cudaSetDevice(dev);
-    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &walk_q, &deferred_q, &pair_flags, &ctl, &counters, &offsets[0],
-                      &offsets[1], &rgb, &ids})
+    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &walk_q, &deferred_q, &pair_flags, &ctl, &counters, &offsets,
+                      &rgb, &ids})
       b->release();
     if (pinned) cudaFreeHost(pinned);
     pinned = nullptr;
     pinned_bytes = 0;
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
     prof_events.clear();
-    for (cudaEvent_t e : {ev_begin, ev_end, ev_up[0], ev_up[1], ev_done[0], ev_done[1]})
+    for (cudaEvent_t e : {ev_begin, ev_end})
       if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
+    ev_up.clear();
+    ev_done.clear();
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     stream = copy_stream = nullptr;
@@ -144,6 +144,11 @@ struct rh_scene {
   mutable int shadow_mode = 0;
   mutable int tune_frames = 0;
   mutable double tune_ns_per_task[2] = {0, 0};
+  // Per-chunk kernel time of the last frame that streamed its sample offsets from the host (key: the chunk plan).
+  // The next such frame processes its chunks in descending cost per sample, so that the uploads of the cheap chunks
+  // hide behind the kernels of the expensive ones instead of the other way round.
+  mutable std::vector<int> cost_key;
+  mutable std::vector<float> chunk_ms;
 };
 
 namespace {
@@ -799,12 +804,13 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const void* d_offsets = nullptr;
   int off_index = kOffIndexLocal;
   bool stream_offsets = false;
+  int ring = 2;
   if (mode == RH_OFFSETS_TILED_F64) {
     const size_t bytes = (size_t)o->offset_tile * o->offset_tile * spp * off_elem;
     if (dev_off) d_offsets = o->offsets;
     else {
-      if ((rc = D->offsets[0].reserve(bytes))) return rc;
-      d_offsets = D->offsets[0].p;
+      if ((rc = D->offsets.reserve(bytes))) return rc;
+      d_offsets = D->offsets.p;
     }
   } else if (mode != RH_OFFSETS_NONE) {
     if (dev_off) {
@@ -812,8 +818,18 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       off_index = kOffIndexGlobal;
     } else {
       stream_offsets = true;
-      for (int k = 0; k < 2; k++)
-        if ((rc = D->offsets[k].reserve(chunk_samples * off_elem))) return rc;
+      // Upload ring: as many chunk-sized slots as 10 % of the device memory holds (all chunks, for the frames of
+      // BASELINE.json), so that the copy stream can run ahead of the kernels instead of waiting for a slot.
+      const size_t slot_bytes = chunk_samples * off_elem;
+      ring = (int)std::max<size_t>(2, std::min<size_t>((size_t)n_chunks, (size_t)(0.1 * (double)D->total_mem) / slot_bytes));
+      if ((rc = D->offsets.reserve((size_t)ring * slot_bytes))) return rc;
+      while ((int)D->ev_up.size() < ring) {
+        cudaEvent_t a, b;
+        RH_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        RH_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        D->ev_up.push_back(a);
+        D->ev_done.push_back(b);
+      }
     }
   }
 
@@ -855,11 +871,20 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     uint32_t launches = 0;
     size_t upload_bytes = 0;
 
-    int next_row = 0;
-    for (int ck = 0; ck < n_chunks; ck++) {
-      const int first_row = next_row;
+    // processing order of the chunks (rows are independent, Image.hs:34-36)
+    std::vector<int> first_rows(n_chunks), order(n_chunks);
+    for (int ck = 0, row = 0; ck < n_chunks; row += plan[ck], ck++) { first_rows[ck] = row; order[ck] = ck; }
+    std::vector<int> key = {W, H, spp, G, o->shard_index, bh};
+    key.insert(key.end(), plan.begin(), plan.end());
+    if (stream_offsets && n_chunks > 2 && scene->cost_key == key && (int)scene->chunk_ms.size() == n_chunks)
+      std::stable_sort(order.begin() + 1, order.end(), [&](int x, int y) {  // the small first chunk stays first
+        return scene->chunk_ms[x] / plan[x] > scene->chunk_ms[y] / plan[y];
+      });
+    std::vector<cudaEvent_t> chunk_ev;
+    for (int i = 0; i < n_chunks; i++) {
+      const int ck = order[i];
+      const int first_row = first_rows[ck];
       const int n_rows = plan[ck];
-      next_row += n_rows;
       ChunkParams P{};
       P.first_row = first_row;
       P.n_rows = n_rows;
@@ -892,8 +917,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
 
       if (stream_offsets) {
         // upload this chunk's rows (runs of image rows that are contiguous inside one band) on the copy stream
-        const int b = ck & 1;
-        if (ck >= 2) RH_CUDA(cudaStreamWaitEvent(D->copy_stream, D->ev_done[b], 0));
+        const int b = i % ring;
+        char* slot = (char*)D->offsets.p + (size_t)b * chunk_samples * off_elem;
+        if (i >= ring) RH_CUDA(cudaStreamWaitEvent(D->copy_stream, D->ev_done[b], 0));
         int lr = first_row;
         while (lr < first_row + n_rows) {
           const int lb = lr / bh, rib = lr % bh;
@@ -902,7 +928,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
           const long long rows_ok = std::max<long long>(0, std::min<long long>(run, (long long)H - grow));
           if (rows_ok > 0) {
             const size_t bytes = (size_t)rows_ok * row_samples * off_elem;
-            RH_CUDA(cudaMemcpyAsync((char*)D->offsets[b].p + (size_t)(lr - first_row) * row_samples * off_elem,
+            RH_CUDA(cudaMemcpyAsync(slot + (size_t)(lr - first_row) * row_samples * off_elem,
                                     (const char*)o->offsets + (size_t)grow * row_samples * off_elem, bytes,
                                     cudaMemcpyHostToDevice, D->copy_stream));
             upload_bytes += bytes;
@@ -911,7 +937,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         }
         RH_CUDA(cudaEventRecord(D->ev_up[b], D->copy_stream));
         RH_CUDA(cudaStreamWaitEvent(D->stream, D->ev_up[b], 0));
-        P.offsets = D->offsets[b].p;
+        P.offsets = slot;
+        chunk_ev.push_back(prof_event());  // after the wait: the span holds kernel time only
       }
 
       RH_CUDA(cudaMemset2DAsync(D->accum.p, chunk_samples * sizeof(double), 0, (size_t)P.n_samples * sizeof(double), 3, D->stream));
@@ -934,7 +961,10 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       launch_resolve(P, D->stream);
       if (profile) spans.push_back({a, prof_event(), 2});
       launches += 1;
-      if (stream_offsets) RH_CUDA(cudaEventRecord(D->ev_done[ck & 1], D->stream));
+      if (stream_offsets) {
+        RH_CUDA(cudaEventRecord(D->ev_done[i % ring], D->stream));
+        chunk_ev.push_back(prof_event());
+      }
     }
     RH_CUDA(cudaGetLastError());
     RH_CUDA(cudaMemcpyAsync(D->pinned, D->ctl.p, (size_t)n_chunks * sizeof(ChunkCtl), cudaMemcpyDeviceToHost, D->stream));
@@ -1007,6 +1037,11 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->negative_channels = (uint32_t)std::min<unsigned long long>(fc->negative_channels, 0xffffffffu);
       stats->queue_factor = factor;
       stats->shadow_split = use_split ? 1 : 0;
+    }
+    if (stream_offsets && (int)chunk_ev.size() == 2 * n_chunks) {
+      scene->chunk_ms.assign(n_chunks, 0.f);
+      for (int i = 0; i < n_chunks; i++) cudaEventElapsedTime(&scene->chunk_ms[order[i]], chunk_ev[2 * i], chunk_ev[2 * i + 1]);
+      scene->cost_key = key;
     }
     if (tuning) {
       // only frames with enough shadow work to time say anything (1 M shaded hits ~ 0.3 ms)
