@@ -284,15 +284,28 @@ def main():
     ab = algorithmic_bytes(cnt, 16)
     peaks, peak_kind = load_peaks()
     if prof["ms_shadow"] >= prof["ms_trace"]:
-        dom, dom_ms, dom_n, dom_bytes = "shadow_kernel", prof["ms_shadow"], prof["shadow_launches"], ab["shadow"]
+        dom = "shadow_classify_kernel+shadow_walk_kernel+shadow_fold_kernel" if prof.get("shadow_split") else "shadow_kernel_fast"
+        dom_ms, dom_n, dom_bytes = prof["ms_shadow"], prof["shadow_launches"], ab["shadow"]
     else:
         dom, dom_ms, dom_n, dom_bytes = "trace_kernel", prof["ms_trace"], prof["trace_launches"], ab["trace"]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     gather_l2, gather_hbm = capi.C.c_double(), capi.C.c_double()
     capi.check(L.rh_bench_gather(4 << 20, 20, capi.C.byref(gather_l2)))
     capi.check(L.rh_bench_gather(4 << 30, 5, capi.C.byref(gather_hbm)))
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu launch list of this workload
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        name = dom
+        if name in tj["kernels"] and G == 1:
+            traffic = tj["kernels"][name]["dram_bytes_per_launch"]
+            traffic_src = "profiles/" + tj["source"] + " (dram__bytes_read.sum + dram__bytes_write.sum per launch of " + name + ")"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
                 "algorithmic_bytes_per_frame": dom_bytes, "kernel_ms_per_frame": dom_ms, "launches_per_frame": dom_n,
                 "avg_launch_ms": dom_ms / max(1, dom_n),
                 "kernel_share_of_frame": dom_ms / max(prof["ms_total"], 1e-9),
