@@ -223,18 +223,41 @@ def main():
             torch.cuda.current_stream().synchronize()
             capi.check(L.rh_deinterleave_bands(gathered.data_ptr(), full_dev.data_ptr(), W, H, G, bh))
 
-    def step_device(**kw):
+    # N > 1, fused exchange: every rank's resolve kernel stores its rows straight into all ranks' full frames (CUDA IPC
+    # mappings, NVLink peer stores); one barrier after the render call completes the frame everywhere.
+    peers = rh.PeerFrames(H, W) if G > 1 else None
+
+    def step_device_nccl(**kw):
         st = rh.render_device(job, rgb_dev, spp=spp, offsets_dev=off_dev, shard_index=rank, shard_count=G, band_height=bh, **kw)
         assemble()
         return st
 
+    def step_device_fused(**kw):
+        st = rh.render_device(job, None, spp=spp, offsets_dev=off_dev, shard_index=rank, shard_count=G, band_height=bh,
+                              peer_frames=peers.pointers, **kw)
+        dist.barrier()
+        return st
+
+    def step_device(**kw):
+        if G == 1:
+            return rh.render_device(job, rgb_dev, spp=spp, offsets_dev=off_dev, **kw)
+        return step_device_fused(**kw) if use_fused[0] else step_device_nccl(**kw)
+
     def step_e2e():
         if G == 1:
             return rh.render(job, spp=spp, offsets=off_host, out=rgb_host.numpy()).stats
+        if use_fused[0]:
+            st = rh.render_device(job, None, spp=spp, offsets_dev=off_host, shard_index=rank, shard_count=G, band_height=bh,
+                                  peer_frames=peers.pointers)
+            dist.barrier()
+            full_host.copy_(peers.frame)
+            return st
         st = rh.render_device(job, rgb_dev, spp=spp, offsets_dev=off_host, shard_index=rank, shard_count=G, band_height=bh)
         assemble()
         full_host.copy_(full_dev)
         return st
+
+    use_fused = [G > 1]
 
     def barrier():
         if G > 1:
@@ -265,6 +288,19 @@ def main():
         step_device()
     step_e2e()
 
+    # N > 1: time both exchanges, report the frame with the faster one (both are in the JSON line)
+    exchange = None
+    if G > 1:
+        for _ in range(2):
+            step_device_nccl()
+        ms_nccl, _ = timed(step_device_nccl, args.steps)
+        ms_fused, _ = timed(step_device_fused, args.steps)
+        use_fused[0] = ms_fused <= ms_nccl
+        exchange = {"used": "peer_stores" if use_fused[0] else "nccl_allgather", "ms_per_step_peer_stores": ms_fused,
+                    "ms_per_step_nccl_allgather": ms_nccl,
+                    "note": "peer_stores: resolve kernel writes finished rows into every rank's frame over NVLink (CUDA IPC), "
+                            "then one barrier; nccl_allgather: compact bands -> all_gather_into_tensor -> rh_deinterleave_bands"}
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -272,6 +308,11 @@ def main():
     ms_dev, stats = timed(step_device, args.steps)
     launches = (L.rh_launch_count() - launches0) // args.steps
     ms_e2e, stats_e2e = timed(step_e2e, args.steps)
+    ms_seeded = None
+    if G == 1:  # beside e2e: the same call with the offset stream regenerated on the device from its seed (no upload)
+        seeded = lambda: rh.render(job, spp=spp, seed=WORKLOAD["seed"], out=rgb_host.numpy()).stats
+        seeded()
+        ms_seeded, _ = timed(seeded, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     rays = total_rays(stats[-1])
     value = rays / (ms_dev * 1e-3) / 1e6
@@ -321,13 +362,13 @@ def main():
     # outside the timed region.  The bench scene has no Transparent forks, so the sums are order-independent.
     assembled_ok = None
     if G > 1:
-        step_device()
-        full_host.copy_(full_dev)
+        step_device_nccl()
+        step_device_fused()
         torch.cuda.synchronize()
         if rank == 0:
             solo = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
             rh.render_device(job, solo, spp=spp, offsets_dev=off_dev)
-            assembled_ok = bool(torch.equal(solo.cpu(), full_host))
+            assembled_ok = bool(torch.equal(solo, full_dev)) and bool(torch.equal(solo, peers.frame))
 
     cpu = None
     if rank == 0 and G == 1 and not args.no_cpu_baseline:
@@ -347,10 +388,17 @@ def main():
                 "rays_by_class_rank0": {k: int(st[k]) for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow",
                                                                 "rays_shadow_culled")},
                 "roofline": roofline, "cpu_baseline": cpu}
+        if ms_seeded is not None:
+            line["e2e_device_generated_offsets"] = {"value": rays / (ms_seeded * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_seeded,
+                                                    "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(rows * W * 3),
+                                                    "note": "RH_OFFSETS_SPLITMIX64: same stream, same image, regenerated in the kernel; "
+                                                            "informational — `e2e` above uploads the stream as north_star asks"}
         if assembled_ok is not None:
             line["assembled_frame_equals_single_gpu_frame"] = assembled_ok
+            line["exchange"] = exchange
         print(json.dumps(line), flush=True)
     if G > 1:
+        peers.close()
         dist.destroy_process_group()
     rh.shutdown()
 

@@ -60,7 +60,11 @@ enum {
   RH_OFFSETS_NONE = 0,     /* 1 sample at the integer pixel coordinate (generatePixels, Image.hs:34-36) */
   RH_OFFSETS_F64 = 1,      /* double[w*h][spp][2], pixel-major, values already (x-0.5, y-0.5)          */
   RH_OFFSETS_F32 = 2,      /* float [w*h][spp][2], same order                                          */
-  RH_OFFSETS_TILED_F64 = 3 /* double[tile*tile][spp][2], tile period given in rh_render_opts (declared deviation) */
+  RH_OFFSETS_TILED_F64 = 3, /* double[tile*tile][spp][2], tile period given in rh_render_opts (declared deviation) */
+  RH_OFFSETS_SPLITMIX64 = 4 /* `offsets` points at ONE uint64 seed (host memory): the kernel regenerates the stream of
+                               rh_sample_offsets_f64(seed, ...) in place — SplitMix64 is counter-based, so value k of
+                               the stream needs no predecessor — instead of reading 16 bytes per sample.  Same values,
+                               same image; for hosts whose stream is this generator. */
 };
 
 #define RH_NO_NODE 0xFFFFFFFFu /* KDTree.hs:61 `Empty` */
@@ -216,7 +220,13 @@ typedef struct rh_render_opts {
   int32_t band_height;    /* rows per band; 0 = library default */
   int32_t chunk_samples;  /* wavefront chunk size in pixel samples; 0 = default */
   int32_t flags;          /* RH_FLAG_* */
-  int32_t pad_;
+  int32_t n_peer_frames;  /* RH_FLAG_PEER_FRAMES: entries of peer_frames (= shard_count) */
+  /* RH_FLAG_PEER_FRAMES (fused exchange): host array of n_peer_frames DEVICE pointers, one full
+   * [height][width][3] frame per shard of the job (this shard's own included), all addressable from this device
+   * (rh_peer_alloc / rh_peer_open).  The resolve kernel stores every finished row straight into all of them, so after
+   * all shards have returned (and one barrier) every GPU holds the complete frame: no all-gather, no de-interleave.
+   * rgb_out may then be NULL. */
+  void* const* peer_frames;
 } rh_render_opts;
 
 enum {
@@ -230,7 +240,8 @@ enum {
   /* Shadow-ray schedule (same image either way; DESIGN.md "Kernels").  Default: the library times both on the
    * first two large frames of a scene and keeps the faster one for that scene. */
   RH_FLAG_SHADOW_POOLED = 64, /* one kernel per pass, tree walks in warp-local rounds of 32 (coherent rays)   */
-  RH_FLAG_SHADOW_SPLIT = 128  /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
+  RH_FLAG_SHADOW_SPLIT = 128, /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
+  RH_FLAG_PEER_FRAMES = 256   /* store the finished rows into rh_render_opts.peer_frames (see there) */
 };
 
 /* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
@@ -304,6 +315,15 @@ int rh_default_band_height(int height, int shard_count);
  * (device), out = [h][w][3] (device).  Runs on the library stream and synchronises. */
 int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int width, int height,
                           int shard_count, int band_height);
+
+/* Frames shared between the processes of one job (one process per GPU): rh_peer_alloc allocates device memory on this
+ * process's device and returns its CUDA IPC handle (64 bytes, to be sent to the other processes by any means);
+ * rh_peer_open maps another process's allocation into this one (peer access over NVLink).  Close before the owner frees. */
+#define RH_PEER_HANDLE_BYTES 64
+int rh_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[RH_PEER_HANDLE_BYTES]);
+int rh_peer_open(const unsigned char handle[RH_PEER_HANDLE_BYTES], void** dev_ptr_out);
+int rh_peer_close(void* dev_ptr);
+int rh_peer_free(void* dev_ptr);
 
 /* Micro-benchmarks used by bench.py for the roofline denominators:
  * random 32-byte-aligned 64-byte gathers over `bytes` of device memory; returns GB/s. */

@@ -4,9 +4,9 @@ See DESIGN.md.  The Python layer mirrors the reference's interface for this path
 (`Rendering`, `rayTrace`, `distributedRayTrace`, `writePPM`); the kernels live in
 csrc/kernels.cu and are reached through librayhs_b200.so (include/rayhs_b200.h).
 """
-from .host import (Image, Rendering, Scene, assemble_bands, buildRendering, distributedRayTrace, init, main, rayTrace,
+from .host import (Image, PeerFrames, Rendering, Scene, assemble_bands, buildRendering, distributedRayTrace, init, main, rayTrace,
                    render, render_device, renderingFromScene, sample_offsets, shard_global_rows, shutdown, writePPM)
 
-__all__ = ["Image", "Rendering", "Scene", "assemble_bands", "buildRendering", "distributedRayTrace", "init", "main",
+__all__ = ["Image", "PeerFrames", "Rendering", "Scene", "assemble_bands", "buildRendering", "distributedRayTrace", "init", "main",
            "rayTrace", "render", "render_device", "renderingFromScene", "sample_offsets", "shard_global_rows", "shutdown",
            "writePPM"]

@@ -20,9 +20,9 @@ RH_MAT_MIRROR, RH_MAT_DIFFUSE, RH_MAT_PLASTIC, RH_MAT_EMMIT, RH_MAT_TRANSPARENT,
 RH_CMAP_FLAT, RH_CMAP_CHECKER, RH_CMAP_TEXTURE = 0, 1, 2
 RH_LIGHT_DIRECTIONAL, RH_LIGHT_POINT = 0, 1
 RH_PROJ_ORTHOGRAPHIC, RH_PROJ_PERSPECTIVE = 0, 1
-RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64 = 0, 1, 2, 3
+RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64, RH_OFFSETS_SPLITMIX64 = 0, 1, 2, 3, 4
 RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE, RH_FLAG_EXACT_BOXES = 1, 2, 4, 8, 16, 32
-RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT = 64, 128
+RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES = 64, 128, 256
 RH_NO_NODE = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -89,7 +89,7 @@ class rh_render_opts(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32), ("spp", C.c_int32),
                 ("offset_mode", C.c_int32), ("offset_tile", C.c_int32), ("offsets", C.c_void_p), ("shard_index", C.c_int32),
                 ("shard_count", C.c_int32), ("band_height", C.c_int32), ("chunk_samples", C.c_int32), ("flags", C.c_int32),
-                ("pad_", C.c_int32)]
+                ("n_peer_frames", C.c_int32), ("peer_frames", C.POINTER(C.c_void_p))]
 
 
 class rh_stats(C.Structure):
@@ -130,6 +130,10 @@ SIGNATURES = {
     "rh_shard_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rh_default_band_height": (C.c_int, [C.c_int, C.c_int]),
     "rh_deinterleave_bands": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "rh_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "rh_peer_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "rh_peer_close": (C.c_int, [vp]),
+    "rh_peer_free": (C.c_int, [vp]),
     "rh_bench_gather": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "rh_bench_dfma": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "rh_flatten": (C.c_int, [C.POINTER(rh_raw_scene), C.POINTER(vp)]),

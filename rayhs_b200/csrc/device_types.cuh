@@ -21,6 +21,7 @@ constexpr int kSmemNodes = RH_SMEM_NODES;   // top wide (fp32) nodes staged in s
 constexpr int kSmemObjects = 64;            // object / material tables staged when the scene has at most this many
 constexpr int kSmemLights = 16;
 constexpr int kBlock = 128;                // resolve kernel
+constexpr int kMaxPeers = 16;
 #ifndef RH_TRACE_BLOCK
 #define RH_TRACE_BLOCK 768
 #define RH_TRACE_MINB 1
@@ -190,11 +191,15 @@ struct ChunkParams {
   int32_t exact_boxes;    // RH_FLAG_EXACT_BOXES: double slab test for every ray (validation)
   int32_t pad2_;
   const void* offsets;    // device
+  unsigned long long offset_seed;  // RH_OFFSETS_SPLITMIX64
   double* accum;          // 3 planes of accum_stride (r,g,b), chunk-local sample order
   uint32_t accum_stride;
   uint32_t pad_;
   int2* hit_ids;          // shard-compact [pixel][spp] (object, tri) or null
-  uint8_t* rgb;           // shard-compact framebuffer
+  uint8_t* rgb;           // shard-compact framebuffer (or null with peer frames)
+  uint8_t* peer[kMaxPeers];  // RH_FLAG_PEER_FRAMES: full frames of all shards
+  uint32_t n_peers;
+  uint32_t pad4_;
   ChunkCtl* ctl;
   FrameCounters* counters;
   RayQueue q_in, q_out;

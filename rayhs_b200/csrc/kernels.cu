@@ -856,6 +856,16 @@ __device__ __forceinline__ Ray camera_ray(const CameraParams& cam, double px, do
   return r;
 }
 
+// Value k (0-based) of the SplitMix64 stream seeded with `seed`, as a double in [0, 1): the generator's state after
+// k + 1 steps is seed + (k + 1) * gamma, so any value can be produced on its own (csrc/frontend.cpp SplitMix64).
+__device__ __forceinline__ double splitmix01(unsigned long long seed, unsigned long long k) {
+  unsigned long long z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
 // ------------------------------------------------------------------ K1/K2/K4/K5
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(const __grid_constant__ SceneView S,
@@ -894,7 +904,12 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(con
           valid = false;  // padding row of the last band
         } else {
           double ox = 0, oy = 0;
-          if (P.offset_mode != RH_OFFSETS_NONE) {
+          if (P.offset_mode == RH_OFFSETS_SPLITMIX64) {
+            // values 2g and 2g+1 of the stream rh_sample_offsets_f64(seed, ...) writes (x before y, RayHs.hs:185-188)
+            const unsigned long long g = ((unsigned long long)grow * P.width + col) * P.spp + s;
+            ox = splitmix01(P.offset_seed, 2 * g) - 0.5;
+            oy = splitmix01(P.offset_seed, 2 * g + 1) - 0.5;
+          } else if (P.offset_mode != RH_OFFSETS_NONE) {
             size_t idx;
             if (P.offset_mode == RH_OFFSETS_TILED_F64)
               idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
@@ -2085,9 +2100,33 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(const __grid_constant__
   const unsigned neg = __ballot_sync(kFull, negative);
   if ((threadIdx.x & 31) == 0 && neg) atomicAdd(&P.counters->negative_channels, (unsigned long long)__popc(neg));
   __syncthreads();
+  const uint32_t n_here = min((uint32_t)kBlock, n_pixels - blockIdx.x * kBlock) * 3;
+  if (P.n_peers) {
+    // Fused exchange: the block's bytes go straight into every shard's full frame (peer stores over NVLink), at the
+    // image row of each byte.  Rows are whole multiples of 4 bytes and the block starts on a word when width % 4 == 0,
+    // so a 32-bit word never straddles two rows; otherwise byte stores.
+    const uint32_t row_bytes = P.width * 3;
+    const size_t local0 = (size_t)blockIdx.x * kBlock * 3;  // byte offset inside the chunk's compact rows
+    const bool words = (row_bytes & 3u) == 0 && (local0 & 3u) == 0;
+    const uint32_t step = words ? 4u : 1u;
+    for (uint32_t i = threadIdx.x * step; i < n_here; i += kBlock * step) {
+      const size_t lb = local0 + i;
+      const uint32_t lrow = (uint32_t)(lb / row_bytes), inrow = (uint32_t)(lb - (size_t)lrow * row_bytes);
+      const uint32_t grow = global_row(P, P.first_row + lrow);
+      if (grow >= P.height) continue;  // padding row of the last band
+      const size_t at = (size_t)grow * row_bytes + inrow;
+      if (words && i + 4 <= n_here) {
+        const uint32_t v = *(const uint32_t*)(bytes + i);
+        for (uint32_t g = 0; g < P.n_peers; g++) *(uint32_t*)(P.peer[g] + at) = v;
+      } else {
+        for (uint32_t k = 0; k < step && i + k < n_here; k++)
+          for (uint32_t g = 0; g < P.n_peers; g++) P.peer[g][at + k] = bytes[i + k];
+      }
+    }
+    return;
+  }
   // coalesced store: the block's 384 bytes leave as 32-bit words when the destination allows it
   uint8_t* dst = P.rgb + ((size_t)P.first_row * P.width + (size_t)blockIdx.x * kBlock) * 3;
-  const uint32_t n_here = min((uint32_t)kBlock, n_pixels - blockIdx.x * kBlock) * 3;
   if ((((uintptr_t)dst) & 3) == 0) {
     const uint32_t words = n_here / 4;
     if (threadIdx.x < words) ((uint32_t*)dst)[threadIdx.x] = ((const uint32_t*)bytes)[threadIdx.x];

@@ -703,7 +703,12 @@ struct Launch {
 
 int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const rh_render_opts* o, uint8_t* rgb_out,
               int32_t* hit_ids_out, rh_stats* stats) {
-  if (!scene || !camera || !o || !rgb_out) return rh::set_error(RH_ERR_ARG, "rh_render: null argument");
+  const bool peer_frames = o && (o->flags & RH_FLAG_PEER_FRAMES) != 0;
+  if (!scene || !camera || !o || (!rgb_out && !peer_frames)) return rh::set_error(RH_ERR_ARG, "rh_render: null argument");
+  if (peer_frames && (!o->peer_frames || o->n_peer_frames <= 0 || o->n_peer_frames > kMaxPeers))
+    return rh::set_error(RH_ERR_ARG, "rh_render: RH_FLAG_PEER_FRAMES needs 1..16 peer frame pointers");
+  if (peer_frames && (o->flags & RH_FLAG_HIT_IDS))
+    return rh::set_error(RH_ERR_ARG, "rh_render: hit ids are not exchanged; render them without RH_FLAG_PEER_FRAMES");
   if (scene->device != D) return rh::set_error(RH_ERR_ARG, "rh_render: scene lives on another device context");
   const int W = o->width, H = o->height, spp = o->spp;
   if (W <= 0 || H <= 0 || spp <= 0 || o->max_depth < 0 || o->max_depth > kMaxDepth)
@@ -715,7 +720,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const int bh = o->band_height > 0 ? o->band_height : rh_default_band_height(H, G);
   const int rows_local = rh_shard_rows(H, G, bh);
   const int mode = o->offset_mode;
-  if (mode < RH_OFFSETS_NONE || mode > RH_OFFSETS_TILED_F64) return rh::set_error(RH_ERR_ARG, "rh_render: bad offset_mode");
+  if (mode < RH_OFFSETS_NONE || mode > RH_OFFSETS_SPLITMIX64) return rh::set_error(RH_ERR_ARG, "rh_render: bad offset_mode");
   if (mode != RH_OFFSETS_NONE && !o->offsets) return rh::set_error(RH_ERR_ARG, "rh_render: offsets is null");
   if (mode == RH_OFFSETS_TILED_F64 && o->offset_tile <= 0) return rh::set_error(RH_ERR_ARG, "rh_render: offset_tile must be > 0");
   if ((uint64_t)W * spp > 0x7fffffffu) return rh::set_error(RH_ERR_ARG, "rh_render: row too large");
@@ -775,7 +780,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   int rc;
   uint8_t* d_rgb;
   const size_t rgb_bytes = (size_t)rows_local * W * 3;
-  if (dev_out) d_rgb = rgb_out;
+  if (peer_frames) d_rgb = nullptr;
+  else if (dev_out) d_rgb = rgb_out;
   else {
     if ((rc = D->rgb.reserve(rgb_bytes))) return rc;
     d_rgb = (uint8_t*)D->rgb.p;
@@ -804,6 +810,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const void* d_offsets = nullptr;
   int off_index = kOffIndexLocal;
   bool stream_offsets = false;
+  unsigned long long offset_seed = 0;
   int ring = 2;
   if (mode == RH_OFFSETS_TILED_F64) {
     const size_t bytes = (size_t)o->offset_tile * o->offset_tile * spp * off_elem;
@@ -812,6 +819,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       if ((rc = D->offsets.reserve(bytes))) return rc;
       d_offsets = D->offsets.p;
     }
+  } else if (mode == RH_OFFSETS_SPLITMIX64) {
+    if (dev_off) return rh::set_error(RH_ERR_ARG, "rh_render: RH_OFFSETS_SPLITMIX64 takes a host pointer to the seed");
+    memcpy(&offset_seed, o->offsets, sizeof offset_seed);
   } else if (mode != RH_OFFSETS_NONE) {
     if (dev_off) {
       d_offsets = o->offsets;
@@ -901,10 +911,15 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.offset_index = off_index;
       P.offset_tile = o->offset_tile;
       P.offsets = d_offsets;
+      P.offset_seed = offset_seed;
       P.accum = (double*)D->accum.p;
       P.accum_stride = (uint32_t)chunk_samples;
       P.hit_ids = d_ids;
       P.rgb = d_rgb;
+      if (peer_frames) {
+        P.n_peers = (uint32_t)o->n_peer_frames;
+        for (int g = 0; g < o->n_peer_frames; g++) P.peer[g] = (uint8_t*)o->peer_frames[g];
+      }
       P.ctl = (ChunkCtl*)D->ctl.p + ck;
       P.counters = (FrameCounters*)D->counters.p;
       P.q_shadow.plane = (double2*)D->shq.p;
@@ -970,7 +985,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     RH_CUDA(cudaMemcpyAsync(D->pinned, D->ctl.p, (size_t)n_chunks * sizeof(ChunkCtl), cudaMemcpyDeviceToHost, D->stream));
     RH_CUDA(cudaMemcpyAsync((char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl), D->counters.p, sizeof(FrameCounters),
                             cudaMemcpyDeviceToHost, D->stream));
-    if (!dev_out) {
+    if (!dev_out && !peer_frames) {
       RH_CUDA(cudaMemcpyAsync(rgb_out, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, D->stream));
       if (want_ids) RH_CUDA(cudaMemcpyAsync(hit_ids_out, d_ids, ids_bytes, cudaMemcpyDeviceToHost, D->stream));
     }
@@ -1132,6 +1147,43 @@ int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int wid
   g_launches.fetch_add(1);
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(g_dev->stream));
+  return RH_OK;
+}
+
+int rh_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[RH_PEER_HANDLE_BYTES]) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_peer_alloc: call rh_init first");
+  if (!bytes || !dev_ptr_out || !handle_out) return rh::set_error(RH_ERR_ARG, "rh_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RH_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  RH_CUDA(cudaSetDevice(g_dev->dev));
+  void* p = nullptr;
+  RH_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return rh::set_error(RH_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &h, sizeof h);
+  *dev_ptr_out = p;
+  return RH_OK;
+}
+int rh_peer_open(const unsigned char handle[RH_PEER_HANDLE_BYTES], void** dev_ptr_out) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_peer_open: call rh_init first");
+  if (!handle || !dev_ptr_out) return rh::set_error(RH_ERR_ARG, "rh_peer_open: bad argument");
+  RH_CUDA(cudaSetDevice(g_dev->dev));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  RH_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return RH_OK;
+}
+int rh_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return RH_OK;
+  RH_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return RH_OK;
+}
+int rh_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return RH_OK;
+  RH_CUDA(cudaFree(dev_ptr));
   return RH_OK;
 }
 

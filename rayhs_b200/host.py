@@ -174,12 +174,19 @@ def _offset_mode(offsets, tile: int):
 def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, want_hit_ids: bool = False,
            shard_index: int = 0, shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0,
            count: bool = False, profile: bool = False, exact_boxes: bool = False, out: np.ndarray | None = None,
-           shadow: str | None = None) -> Image:
+           shadow: str | None = None, seed: int | None = None) -> Image:
     """One rh_render call with HOST buffers (numpy or pinned torch CPU tensors for `offsets`).
+    `seed` (instead of `offsets`): the kernel regenerates sample_offsets(width*height, spp, seed) on the device.
     Returns the shard-compact RGB8 rows when shard_count > 1."""
     L = lib()
     mode, off = _offset_mode(offsets, offset_tile)
     off_ptr = None
+    seed_box = None
+    if seed is not None:
+        if offsets is not None:
+            raise ValueError("pass either offsets or seed")
+        seed_box = C.c_uint64(seed)
+        mode, off, off_ptr = capi.RH_OFFSETS_SPLITMIX64, None, C.addressof(seed_box)
     if off is not None:
         off_ptr = off.data_ptr() if hasattr(off, "data_ptr") else off.ctypes.data
         need = (offset_tile * offset_tile if offset_tile else job.width * job.height) * spp * 2
@@ -208,7 +215,7 @@ def _shadow_flag(shadow: str | None) -> int:
 
 def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offset_tile: int = 0, shard_index: int = 0,
                   shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0, count: bool = False,
-                  profile: bool = False, shadow: str | None = None) -> dict:
+                  profile: bool = False, shadow: str | None = None, seed: int | None = None, peer_frames=None) -> dict:
     """rh_render into a DEVICE framebuffer (torch CUDA uint8 tensor [rows, width, 3]).  `offsets_dev` is the
     full-frame [height*width, spp, 2] float64/float32 stream (or the [tile*tile, spp, 2] tile), either a CUDA
     tensor (already uploaded) or a pinned CPU tensor (uploaded chunk by chunk inside the call).  The call
@@ -219,18 +226,77 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     mode, off = _offset_mode(offsets_dev, offset_tile)
     bh = band_height or L.rh_default_band_height(job.height, shard_count)
     rows = L.rh_shard_rows(job.height, shard_count, bh)
-    if tuple(rgb_dev.shape) != (rows, job.width, 3) or rgb_dev.dtype != torch.uint8 or not rgb_dev.is_cuda:
+    if peer_frames is None and (tuple(rgb_dev.shape) != (rows, job.width, 3) or rgb_dev.dtype != torch.uint8 or not rgb_dev.is_cuda):
         raise ValueError("rgb_dev must be a CUDA uint8 tensor of shape [rows, width, 3]")
     flags = (capi.RH_FLAG_DEVICE_OUT | (capi.RH_FLAG_COUNT if count else 0) | (capi.RH_FLAG_PROFILE if profile else 0)
              | _shadow_flag(shadow))
     if off is not None and off.is_cuda:
         flags |= capi.RH_FLAG_DEVICE_OFFSETS
         torch.cuda.current_stream().synchronize()
-    o = _opts(job, spp, mode, off.data_ptr() if off is not None else None, offset_tile, shard_index, shard_count, bh,
-              chunk_samples, flags)
+    off_ptr = off.data_ptr() if off is not None else None
+    seed_box = None
+    if seed is not None:  # the kernel regenerates sample_offsets(width*height, spp, seed) on the device
+        seed_box = C.c_uint64(seed)
+        mode, off_ptr = capi.RH_OFFSETS_SPLITMIX64, C.addressof(seed_box)
+    ptrs = None
+    if peer_frames is not None:  # fused exchange: rows go straight into every shard's full frame (PeerFrames.pointers)
+        flags |= capi.RH_FLAG_PEER_FRAMES
+        ptrs = (C.c_void_p * len(peer_frames))(*peer_frames)
+    o = _opts(job, spp, mode, off_ptr, offset_tile, shard_index, shard_count, bh, chunk_samples, flags)
+    if ptrs is not None:
+        o.n_peer_frames, o.peer_frames = len(peer_frames), ptrs
     st = capi.rh_stats()
-    check(L.rh_render(job.scene.device, C.byref(job.camera), C.byref(o), rgb_dev.data_ptr(), None, C.byref(st)))
+    check(L.rh_render(job.scene.device, C.byref(job.camera), C.byref(o), rgb_dev.data_ptr() if rgb_dev is not None else None,
+                      None, C.byref(st)))
     return st.as_dict()
+
+
+class PeerFrames:
+    """One full [height, width, 3] RGB8 frame per process of a torch.distributed job (one process per GPU), each mapped
+    into every other process through CUDA IPC (rh_peer_alloc / rh_peer_open), so that rh_render's resolve kernel can
+    store finished rows straight into all of them over NVLink (RH_FLAG_PEER_FRAMES) — the fused form of the
+    all-gather + de-interleave exchange of SURVEY 8e.  `pointers` is ordered by rank; `frame` is this rank's own frame
+    as a torch tensor.  After every rank's render call has returned, one barrier makes all frames complete."""
+
+    def __init__(self, height: int, width: int):
+        import torch
+        import torch.distributed as dist
+
+        L = lib()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(L.rh_peer_alloc(height * width * 3, C.byref(self._own), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw)
+        self._opened = {}
+        self.pointers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.pointers.append(self._own.value)
+            else:
+                p = C.c_void_p()
+                check(L.rh_peer_open(h, C.byref(p)))
+                self._opened[r] = p
+                self.pointers.append(p.value)
+
+        class _Cai:
+            __cuda_array_interface__ = {"shape": (height, width, 3), "typestr": "|u1", "data": (self._own.value, False), "version": 3}
+
+        self.frame = torch.as_tensor(_Cai(), device="cuda")
+
+    def close(self):
+        import torch.distributed as dist
+
+        L = lib()
+        self.frame = None
+        for p in self._opened.values():
+            L.rh_peer_close(p)
+        self._opened = {}
+        dist.barrier()  # nobody frees while a peer still has the allocation mapped
+        if self._own:
+            L.rh_peer_free(self._own)
+            self._own = C.c_void_p()
 
 
 def shard_global_rows(height: int, shard_index: int, shard_count: int, band_height: int) -> list[int]:

@@ -95,3 +95,38 @@ def test_shadow_schedule_is_chosen_per_scene_and_keeps_the_bytes():
     assert np.array_equal(frames[0].pixels, frames[1].pixels) and np.array_equal(frames[0].pixels, frames[2].pixels)
     forced = rh.render(job, shadow="split")
     assert forced.stats["shadow_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
+
+
+def test_offsets_regenerated_on_the_device_equal_the_uploaded_stream():
+    """RH_OFFSETS_SPLITMIX64: the kernel regenerates the SplitMix64 stream from its seed (counter-based: value k needs no
+    predecessor).  Same hit ids and bytes as uploading rh_sample_offsets_f64's output, also for a row shard."""
+    sc = load_scene("dragon_low")
+    w, h, spp = 200, 120, 5
+    job = rh.renderingFromScene(sc, w, h)
+    off = rh.sample_offsets(w * h, spp, seed=24)
+    up = rh.render(job, spp=spp, offsets=off, want_hit_ids=True)
+    gen = rh.render(job, spp=spp, seed=24, want_hit_ids=True)
+    assert gen.stats["upload_bytes"] == 0 and up.stats["upload_bytes"] == off.nbytes
+    assert np.array_equal(up.hit_ids, gen.hit_ids) and np.array_equal(up.pixels, gen.pixels)
+    other = rh.render(job, spp=spp, seed=25)
+    assert not np.array_equal(other.pixels, gen.pixels)
+    a = rh.render(job, spp=spp, offsets=off, shard_index=1, shard_count=4, band_height=8).pixels
+    b = rh.render(job, spp=spp, seed=24, shard_index=1, shard_count=4, band_height=8).pixels
+    assert np.array_equal(a, b)
+
+
+def test_peer_frame_stores_assemble_the_frame_without_a_gather():
+    """RH_FLAG_PEER_FRAMES: the resolve kernel stores finished rows at their image position in every given full frame.
+    On one GPU: four shards rendered one after the other into the same frame must rebuild the single-shard image —
+    also for a width that is not a multiple of 4 (byte-store path) and a height the bands do not divide."""
+    import torch
+
+    sc = load_scene("cornellBox")
+    for (w, h, bh) in ((200, 150, 4), (203, 149, 8)):
+        job = rh.renderingFromScene(sc, w, h)
+        base = rh.render(job, shadow="pooled").pixels
+        full = torch.full((h, w, 3), 7, dtype=torch.uint8, device="cuda")
+        for g in range(4):
+            rh.render_device(job, None, shard_index=g, shard_count=4, band_height=bh, peer_frames=[full.data_ptr()], shadow="pooled")
+        d = np.abs(full.cpu().numpy().astype(np.int32) - base.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4, (w, h, int(d.max()))   # Transparent forks: atomic order
