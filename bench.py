@@ -194,9 +194,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: anything a library prints to fd 1 in between (NCCL's version banner under
+    # NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE) goes to stderr; fd 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rh.init(local_rank)
     L = capi.lib()
@@ -396,7 +400,10 @@ def main():
         if assembled_ok is not None:
             line["assembled_frame_equals_single_gpu_frame"] = assembled_ok
             line["exchange"] = exchange
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if G > 1:
         peers.close()
         dist.destroy_process_group()

@@ -316,6 +316,23 @@ int rh_default_band_height(int height, int shard_count);
 int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int width, int height,
                           int shard_count, int band_height);
 
+/* ---- several GPUs from ONE process (the Haskell host is one OS process) ----
+ * rh_multi_init opens devices 0 .. n_gpus-1 and enables peer access to device 0; rh_multi_scene_create replicates the
+ * scene on all of them; rh_multi_render renders shard g of the interleaved row bands on GPU g (one host thread per GPU),
+ * every resolve kernel storing its rows straight into ONE full frame on device 0 (peer stores over NVLink,
+ * RH_FLAG_PEER_FRAMES), and copies that frame to rgb_out (host, width*height*3).  opts: shard_index / shard_count /
+ * peer_frames are ignored (set by the library), RH_FLAG_HIT_IDS and the DEVICE flags are refused; host sample offsets
+ * are uploaded per shard.  stats: ray counts summed over the shards, ms_total = the slowest shard.  Independent of
+ * rh_init / rh_render (both contexts may exist). */
+typedef struct rh_multi_scene rh_multi_scene;
+int rh_multi_init(int n_gpus);
+void rh_multi_shutdown(void);
+int rh_multi_gpu_count(void);
+int rh_multi_scene_create(const rh_scene_desc* desc, rh_multi_scene** out);
+void rh_multi_scene_destroy(rh_multi_scene* scene);
+int rh_multi_render(const rh_multi_scene* scene, const rh_camera* camera, const rh_render_opts* opts, uint8_t* rgb_out,
+                    rh_stats* stats);
+
 /* Frames shared between the processes of one job (one process per GPU): rh_peer_alloc allocates device memory on this
  * process's device and returns its CUDA IPC handle (64 bytes, to be sent to the other processes by any means);
  * rh_peer_open maps another process's allocation into this one (peer access over NVLink).  Close before the owner frees. */

@@ -130,6 +130,12 @@ SIGNATURES = {
     "rh_shard_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rh_default_band_height": (C.c_int, [C.c_int, C.c_int]),
     "rh_deinterleave_bands": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "rh_multi_init": (C.c_int, [C.c_int]),
+    "rh_multi_shutdown": (None, []),
+    "rh_multi_gpu_count": (C.c_int, []),
+    "rh_multi_scene_create": (C.c_int, [C.POINTER(rh_scene_desc), C.POINTER(vp)]),
+    "rh_multi_scene_destroy": (None, [vp]),
+    "rh_multi_render": (C.c_int, [vp, C.POINTER(rh_camera), C.POINTER(rh_render_opts), vp, C.POINTER(rh_stats)]),
     "rh_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.c_char_p]),
     "rh_peer_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "rh_peer_close": (C.c_int, [vp]),

@@ -3,7 +3,8 @@
 // (INTEGRATION.md).  Same option semantics as GetOpt RequireOrder with an optional-argument
 // `-o` (the file name must be glued: -ocornell.ppm), same default (out.ppm), same progress lines.
 // Extra environment knobs (not in the reference): RAYHS_SPP (samples per pixel, default 1 =
-// rayTrace; >1 = distributedRayTrace with the RayHs.hs:239 seed 24), RAYHS_WIDTH / RAYHS_HEIGHT.
+// rayTrace; >1 = distributedRayTrace with the RayHs.hs:239 seed 24), RAYHS_WIDTH / RAYHS_HEIGHT,
+// RAYHS_GPUS (render on that many GPUs of this box through rh_multi_render).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,9 +42,16 @@ int main(int argc, char** argv) {
   printf("Rendering...\n");  // RayHs.hs:228
   rh_flat_scene* flat = nullptr;
   if (rh_flatten(rh_loaded_raw(loaded), &flat)) return fail("flatten");
-  if (rh_init(-1)) return fail("rh_init");
+  const int n_gpus = getenv("RAYHS_GPUS") ? atoi(getenv("RAYHS_GPUS")) : 1;
   rh_scene* scene = nullptr;
-  if (rh_scene_create(rh_flat_desc(flat), &scene)) return fail("rh_scene_create");
+  rh_multi_scene* mscene = nullptr;
+  if (n_gpus > 1) {
+    if (rh_multi_init(n_gpus)) return fail("rh_multi_init");
+    if (rh_multi_scene_create(rh_flat_desc(flat), &mscene)) return fail("rh_multi_scene_create");
+  } else {
+    if (rh_init(-1)) return fail("rh_init");
+    if (rh_scene_create(rh_flat_desc(flat), &scene)) return fail("rh_scene_create");
+  }
   rh_render_opts o;
   memset(&o, 0, sizeof o);
   rh_loaded_size(loaded, &o.width, &o.height, &o.max_depth);
@@ -61,7 +69,11 @@ int main(int argc, char** argv) {
   }
   std::vector<uint8_t> rgb((size_t)o.width * o.height * 3);
   rh_stats st;
-  if (rh_render(scene, rh_loaded_camera(loaded), &o, rgb.data(), nullptr, &st)) return fail("rh_render");
+  if (n_gpus > 1) {
+    if (rh_multi_render(mscene, rh_loaded_camera(loaded), &o, rgb.data(), &st)) return fail("rh_multi_render");
+  } else if (rh_render(scene, rh_loaded_camera(loaded), &o, rgb.data(), nullptr, &st)) {
+    return fail("rh_render");
+  }
   if (rh_write_ppm(out_file.c_str(), rgb.data(), o.width, o.height)) return fail("writePPM");
   printf("Done! Output written to %s\n", out_file.c_str());  // RayHs.hs:232
   if (getenv("RAYHS_STATS")) {
@@ -69,8 +81,13 @@ int main(int argc, char** argv) {
     fprintf(stderr, "%.3f ms on the GPU, %llu rays (%.1f Mrays/s), %u launches\n", st.ms_total, rays, rays / st.ms_total / 1e3,
             st.kernel_launches);
   }
-  rh_scene_destroy(scene);
-  rh_shutdown();
+  if (n_gpus > 1) {
+    rh_multi_scene_destroy(mscene);
+    rh_multi_shutdown();
+  } else {
+    rh_scene_destroy(scene);
+    rh_shutdown();
+  }
   rh_flat_destroy(flat);
   rh_loaded_destroy(loaded);
   return 0;

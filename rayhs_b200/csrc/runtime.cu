@@ -22,6 +22,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -1147,6 +1148,149 @@ int rh_deinterleave_bands(const uint8_t* gathered_dev, uint8_t* out_dev, int wid
   g_launches.fetch_add(1);
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(g_dev->stream));
+  return RH_OK;
+}
+
+// ------------------------------------------------------------------ several GPUs from one process
+}  // extern "C"
+
+struct rh_multi_scene {
+  std::vector<rh_scene*> replica;  // one per GPU of the multi context
+};
+
+namespace {
+std::vector<std::unique_ptr<Device>> g_multi;  // rh_multi_init
+DevBuf g_multi_frame;                            // the full frame on device 0
+}  // namespace
+
+extern "C" {
+
+int rh_multi_init(int n_gpus) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_multi.empty()) return rh::set_error(RH_ERR_STATE, "rh_multi_init: already initialised");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return rh::set_error(RH_ERR_CUDA, std::string("rh_multi_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (n_gpus <= 0 || n_gpus > n || n_gpus > kMaxPeers) return rh::set_error(RH_ERR_ARG, "rh_multi_init: n_gpus out of range");
+  std::vector<std::unique_ptr<Device>> devs;
+  for (int g = 0; g < n_gpus; g++) {
+    auto d = std::make_unique<Device>();
+    int rc = d->open(g);
+    if (rc) {
+      d->close();
+      for (auto& x : devs) x->close();
+      return rc;
+    }
+    if (g > 0) {  // stores into device 0's frame
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, g, 0);
+      cudaError_t pe = can ? cudaDeviceEnablePeerAccess(0, 0) : cudaErrorPeerAccessUnsupported;
+      if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
+      if (pe != cudaSuccess) {
+        d->close();
+        for (auto& x : devs) x->close();
+        return rh::set_error(RH_ERR_CUDA, std::string("rh_multi_init: no peer access from a device to device 0: ") + cudaGetErrorString(pe));
+      }
+    }
+    devs.push_back(std::move(d));
+  }
+  g_multi = std::move(devs);
+  return RH_OK;
+}
+
+void rh_multi_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_multi.empty()) {
+    cudaSetDevice(g_multi[0]->dev);
+    g_multi_frame.release();
+  }
+  for (auto& d : g_multi) d->close();
+  g_multi.clear();
+}
+
+int rh_multi_gpu_count(void) { return (int)g_multi.size(); }
+
+int rh_multi_scene_create(const rh_scene_desc* desc, rh_multi_scene** out) {
+  if (g_multi.empty()) return rh::set_error(RH_ERR_STATE, "rh_multi_scene_create: call rh_multi_init first");
+  if (!out) return rh::set_error(RH_ERR_ARG, "rh_multi_scene_create: null argument");
+  auto ms = std::make_unique<rh_multi_scene>();
+  for (auto& d : g_multi) {
+    rh_scene* s = nullptr;
+    int rc = scene_create_on(d.get(), desc, &s);
+    if (rc) {
+      for (rh_scene* r : ms->replica) scene_destroy(r);
+      return rc;
+    }
+    ms->replica.push_back(s);
+  }
+  *out = ms.release();
+  return RH_OK;
+}
+
+void rh_multi_scene_destroy(rh_multi_scene* scene) {
+  if (!scene) return;
+  for (rh_scene* r : scene->replica) scene_destroy(r);
+  delete scene;
+}
+
+int rh_multi_render(const rh_multi_scene* scene, const rh_camera* camera, const rh_render_opts* opts, uint8_t* rgb_out,
+                    rh_stats* stats) {
+  if (g_multi.empty()) return rh::set_error(RH_ERR_STATE, "rh_multi_render: call rh_multi_init first");
+  if (!scene || !camera || !opts || !rgb_out) return rh::set_error(RH_ERR_ARG, "rh_multi_render: null argument");
+  const int G = (int)g_multi.size();
+  if ((int)scene->replica.size() != G) return rh::set_error(RH_ERR_ARG, "rh_multi_render: scene belongs to another multi context");
+  if (opts->flags & (RH_FLAG_HIT_IDS | RH_FLAG_DEVICE_OUT | RH_FLAG_DEVICE_OFFSETS))
+    return rh::set_error(RH_ERR_ARG, "rh_multi_render: hit ids and device pointers are not supported here");
+  if (opts->width <= 0 || opts->height <= 0) return rh::set_error(RH_ERR_ARG, "rh_multi_render: bad width/height");
+  const size_t bytes = (size_t)opts->width * opts->height * 3;
+  RH_CUDA(cudaSetDevice(g_multi[0]->dev));
+  int rc = g_multi_frame.reserve(bytes);
+  if (rc) return rc;
+  void* frame = g_multi_frame.p;
+  std::vector<int> rcs(G, RH_OK);
+  std::vector<std::string> errs(G);
+  std::vector<rh_stats> st(G);
+  std::vector<std::thread> threads;
+  for (int g = 0; g < G; g++)
+    threads.emplace_back([&, g]() {
+      rh_render_opts o = *opts;
+      o.shard_index = g;
+      o.shard_count = G;
+      o.flags |= RH_FLAG_PEER_FRAMES;
+      o.n_peer_frames = 1;
+      void* frames[1] = {frame};
+      o.peer_frames = frames;
+      rcs[g] = render_on(g_multi[g].get(), scene->replica[g], camera, &o, nullptr, nullptr, &st[g]);
+      if (rcs[g]) errs[g] = rh_last_error();  // thread-local: carry it to the caller's thread
+    });
+  for (auto& t : threads) t.join();
+  for (int g = 0; g < G; g++)
+    if (rcs[g]) return rh::set_error(rcs[g], "rh_multi_render (GPU " + std::to_string(g) + "): " + errs[g]);
+  RH_CUDA(cudaSetDevice(g_multi[0]->dev));
+  RH_CUDA(cudaMemcpy(rgb_out, frame, bytes, cudaMemcpyDeviceToHost));  // every shard has synchronised its stream
+  if (stats) {
+    *stats = st[0];
+    for (int g = 1; g < G; g++) {
+      const rh_stats& s = st[g];
+      stats->rays_primary += s.rays_primary; stats->rays_reflect += s.rays_reflect; stats->rays_probe += s.rays_probe;
+      stats->rays_exit += s.rays_exit; stats->rays_shadow += s.rays_shadow; stats->rays_shadow_culled += s.rays_shadow_culled;
+      stats->shadow_tasks += s.shadow_tasks; stats->queued_rays += s.queued_rays;
+      stats->box_tests += s.box_tests; stats->tri_tests += s.tri_tests; stats->prim_tests += s.prim_tests;
+      stats->shade_fetches += s.shade_fetches; stats->texel_fetches += s.texel_fetches; stats->node_visits += s.node_visits;
+      stats->shadow_box_tests += s.shadow_box_tests; stats->shadow_tri_tests += s.shadow_tri_tests;
+      stats->shadow_prim_tests += s.shadow_prim_tests; stats->shadow_node_visits += s.shadow_node_visits;
+      stats->upload_bytes += s.upload_bytes;
+      stats->ms_total = std::max(stats->ms_total, s.ms_total);
+      stats->ms_trace = std::max(stats->ms_trace, s.ms_trace);
+      stats->ms_shadow = std::max(stats->ms_shadow, s.ms_shadow);
+      stats->ms_resolve = std::max(stats->ms_resolve, s.ms_resolve);
+      stats->kernel_launches += s.kernel_launches;
+      stats->chunks += s.chunks;
+      stats->negative_channels += s.negative_channels;
+      stats->queue_factor = std::max(stats->queue_factor, s.queue_factor);
+    }
+  }
   return RH_OK;
 }
 

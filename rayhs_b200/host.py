@@ -251,6 +251,44 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     return st.as_dict()
 
 
+def render_multi(job: Rendering, n_gpus: int, spp: int = 1, offsets=None, seed: int | None = None, band_height: int = 0,
+                 shadow: str | None = None) -> Image:
+    """rh_multi_render: the whole frame on `n_gpus` GPUs of this process (one host thread per GPU, row bands interleaved,
+    finished rows stored into one frame on GPU 0 over NVLink) — what a single-process host such as the Haskell
+    front end calls.  The multi context and the replicated scene are created on first use."""
+    L = lib()
+    if L.rh_multi_gpu_count() == 0:
+        check(L.rh_multi_init(int(n_gpus)))
+    elif L.rh_multi_gpu_count() != n_gpus:
+        raise ValueError(f"multi context already open on {L.rh_multi_gpu_count()} GPUs")
+    sc = job.scene
+    if getattr(sc, "_multi", None) is None:
+        sc._multi = C.c_void_p()
+        check(L.rh_multi_scene_create(sc.flat, C.byref(sc._multi)))
+    mode, off = _offset_mode(offsets, 0)
+    off_ptr = None
+    seed_box = None
+    if seed is not None:
+        seed_box = C.c_uint64(seed)
+        mode, off_ptr = capi.RH_OFFSETS_SPLITMIX64, C.addressof(seed_box)
+    elif off is not None:
+        off_ptr = off.data_ptr() if hasattr(off, "data_ptr") else off.ctypes.data
+    o = _opts(job, spp, mode, off_ptr, 0, 0, 1, band_height, 0, _shadow_flag(shadow))
+    rgb = np.empty((job.height, job.width, 3), dtype=np.uint8)
+    st = capi.rh_stats()
+    check(L.rh_multi_render(sc._multi, C.byref(job.camera), C.byref(o), rgb.ctypes.data, C.byref(st)))
+    return Image(job.width, job.height, rgb, st.as_dict(), None)
+
+
+def multi_shutdown(scenes=()) -> None:
+    L = lib()
+    for sc in scenes:
+        if getattr(sc, "_multi", None):
+            L.rh_multi_scene_destroy(sc._multi)
+            sc._multi = None
+    L.rh_multi_shutdown()
+
+
 class PeerFrames:
     """One full [height, width, 3] RGB8 frame per process of a torch.distributed job (one process per GPU), each mapped
     into every other process through CUDA IPC (rh_peer_alloc / rh_peer_open), so that rh_render's resolve kernel can

@@ -130,3 +130,55 @@ def test_peer_frame_stores_assemble_the_frame_without_a_gather():
             rh.render_device(job, None, shard_index=g, shard_count=4, band_height=bh, peer_frames=[full.data_ptr()], shadow="pooled")
         d = np.abs(full.cpu().numpy().astype(np.int32) - base.astype(np.int32))
         assert d.max() <= 1 and (d > 0).mean() < 1e-4, (w, h, int(d.max()))   # Transparent forks: atomic order
+
+
+def test_multi_gpu_entry_from_one_process():
+    """rh_multi_render (what a single-process host calls): on however many GPUs this box has (1 on the test box; the
+    2- and 8-GPU runs are scripts/gpu_multi_check.py), the frame must equal rh_render's."""
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    sc = load_scene("cornellBox")
+    w, h, spp = 203, 149, 3
+    job = rh.renderingFromScene(sc, w, h)
+    off = rh.sample_offsets(w * h, spp, seed=24)
+    base = rh.render(job, spp=spp, offsets=off)
+    try:
+        multi = rh.render_multi(job, n, spp=spp, offsets=off)
+        seeded = rh.render_multi(job, n, spp=spp, seed=24)
+    finally:
+        rh.multi_shutdown([sc])
+    for img in (multi, seeded):
+        d = np.abs(img.pixels.astype(np.int32) - base.pixels.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4   # Transparent forks: atomic order
+    for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"):
+        assert multi.stats[k] == base.stats[k], k
+
+
+def test_cpp_cli_writes_the_oracles_ppm(tmp_path):
+    """`rayhs -oFILE scene.json` (csrc/rayhs_main.cpp, the C++ stand-in for RayHs.hs:204-234) on a self-contained scene in
+    the reference's JSON schema: the P3 file must carry the oracle's bytes in writePPM's format (Image.hs:60-75);
+    RAYHS_GPUS routes the same run through rh_multi_render."""
+    import os
+    import subprocess
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scene = os.path.join(root, "tests", "golden", "cli_scene.json")
+    job = rh.buildRendering(scene)
+    ref = oracle_for(job.scene).render(job.scene.camera, job.width, job.height, job.maxDepth)["rgb_u8"]
+    for gpus in (1, min(torch.cuda.device_count(), 8)):
+        out = tmp_path / f"out{gpus}.ppm"
+        env = dict(os.environ, RAYHS_GPUS=str(gpus))
+        r = subprocess.run([os.path.join(root, "rayhs_b200", "rayhs"), f"-o{out}", scene], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.splitlines() == [f"Loading scene from {scene}...", "Rendering...", f"Done! Output written to {out}"]
+        text = out.read_text()
+        head, body = text.split("\n255\n", 1)
+        assert head == f"P3\n{job.width} {job.height}" and not text.endswith("\n")
+        rows = body.split("\n")
+        assert len(rows) == job.height and all(row.endswith("  ") for row in rows)
+        got = np.array([[int(x) for x in row.split()] for row in rows], dtype=np.int32).reshape(job.height, job.width, 3)
+        d = np.abs(got - ref.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4, (gpus, int(d.max()))   # Transparent sphere: atomic order
