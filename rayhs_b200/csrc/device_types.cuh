@@ -64,6 +64,9 @@ struct __align__(16) WideNode {
   uint32_t refine;    // bit c: child c's box is a culling refinement inside a reference leaf (not a reference box)
   uint32_t pad_[3];
 };
+#ifndef RH_CULL_SAH
+#define RH_CULL_SAH 1  // 1: the float path culls with its own SAH tree; 0: the reference tree refined below its leaves
+#endif
 #ifndef RH_SUBLEAF
 #define RH_SUBLEAF 4  // reference leaves (< 20 triangles) are refined down to at most this many triangles per cull leaf
 #endif
@@ -109,6 +112,7 @@ struct SceneView {
   const double* texels;
   const uint32_t* lin_objs;     // objects scanned linearly in scene order (RayHs.hs:64-71): all of them, or all but the spheres
   const uint32_t* sphere_refs;  // sphere tree leaves: object indices
+  const uint32_t* exact_index;  // exact walk: slot of the reference tree's leaves -> slot in tris / shade (null: identical)
   uint32_t n_lin;
   uint32_t sphere_root;         // super-root of the sphere tree or kEmpty (spheres are in lin_objs then)
   const OccPlane* occ_planes;
@@ -155,7 +159,8 @@ struct FrameCounters {
   unsigned long long shadow_culled;  // (hit, light) pairs with l.n <= 0: Lambert term is exactly 0, query skipped
   unsigned long long exact_walks;    // RH_FLAG_COUNT: shadow rays that took the exact (double box) walk
   unsigned long long max_walk_nodes; // RH_FLAG_COUNT: most node records one shadow ray visited
-  unsigned long long pad_;
+  unsigned long long exact_closest;  // RH_FLAG_COUNT: closest-hit rays that took the exact walk
+  unsigned long long max_closest_nodes;
   KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow_kernel
 };
 

@@ -275,9 +275,9 @@ struct AnyHit {
 // (the 1e-100 guard keeps idet*un away from underflow to -0, which `u < 0` would not reject).
 template <bool COUNT, class Sink>
 __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint32_t first, uint32_t count, const Ray& r,
-                                          Sink& sink, double& bound, Cnt<COUNT>& cnt) {
+                                          Sink& sink, double& bound, Cnt<COUNT>& cnt, const uint32_t* __restrict__ index = nullptr) {
   for (uint32_t k = 0; k < count; k++) {
-    const uint32_t slot = first + k;
+    const uint32_t slot = index ? __ldg(index + first + k) : first + k;  // (exact walk over the reference tree's leaves)
     const double2* tp = (const double2*)(tris + slot);
     const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
     const double e2z = __ldg((const double*)(tp + 4));
@@ -454,7 +454,7 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
     } else if constexpr (SPHERES) {
       if (test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, skip_emitters, cnt)) return true;
     } else {
-      if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt)) return true;
+      if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt, cx.S->exact_index)) return true;
     }
     if (sp == 0) return false;
     const uint4 e = stack[--sp];
@@ -947,7 +947,16 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(con
 
     Closest best;
     best.obj = -1;
-    if (valid) closest_hit<COUNT>(cx, r, P.exact_boxes || needs_exact_walk(r, S.abs_max), best, stack, cnt);
+    if (valid) {
+      const bool exact = P.exact_boxes || needs_exact_walk(r, S.abs_max);
+      unsigned long long nodes_before = 0;
+      if constexpr (COUNT) nodes_before = cnt.nodes;
+      closest_hit<COUNT>(cx, r, exact, best, stack, cnt);
+      if constexpr (COUNT) {
+        if (exact) atomicAdd(&P.counters->exact_closest, 1ull);
+        atomicMax(&P.counters->max_closest_nodes, cnt.nodes - nodes_before);
+      }
+    }
 
     if (primary && valid && P.hit_ids) {
       int tri = -1;

@@ -138,7 +138,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index;
   SceneView view{};
   uint32_t max_tree_depth = 0;
   // shadow schedule chosen for this scene: 0 = undecided (frame 1 runs pooled, frame 2 split, both timed), 1 = pooled, 2 = split
@@ -504,6 +504,162 @@ struct Refiner {
   }
 };
 
+// Cull tree of the float path.  The reference's tree (midpoint of the box on a cycling axis, KDTree.hs:79-90) decides
+// nothing but which triangles a ray gets to test, and every triangle a ray can hit lies inside its reference leaf's box
+// and all of that leaf's ancestors (the boxes are built from the triangles' own vertices).  So the float path may cull
+// with ANY bounding hierarchy over the same triangles: the accepted hits are the same set, the winner is picked by the
+// same key (t, reference leaf order, list position — carried in the triangle records), and the caveat is the one the
+// conservative float boxes already have (a hit within an ulp of a reference box face).  This builds a
+// binned surface-area-heuristic tree with at most kSubLeaf triangles per leaf; the exact walk keeps the reference's
+// own tree and boxes and reaches the permuted triangle records through an index.
+struct SahTree {
+  struct Ref { uint32_t slot; float lo[3], hi[3], c[3]; };
+  const std::vector<rh_tri>& tris;  // reference (leaf) order
+  std::vector<rh_node> nodes;       // leaves: left = first NEW slot, right = count
+  std::vector<uint32_t> order;      // new slot -> reference slot
+  uint32_t max_depth = 0;
+  std::vector<Ref> refs;
+
+  explicit SahTree(const std::vector<rh_tri>& t) : tris(t) {}
+
+  static float area(const float* lo, const float* hi) {
+    const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+    return x * y + y * z + z * x;
+  }
+
+  uint32_t build(size_t b, size_t e, uint32_t depth) {
+    max_depth = std::max(max_depth, depth);
+    const float inf = std::numeric_limits<float>::infinity();
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf}, clo[3] = {inf, inf, inf}, chi[3] = {-inf, -inf, -inf};
+    for (size_t i = b; i < e; i++)
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], refs[i].lo[k]);
+        hi[k] = std::max(hi[k], refs[i].hi[k]);
+        clo[k] = std::min(clo[k], refs[i].c[k]);
+        chi[k] = std::max(chi[k], refs[i].c[k]);
+      }
+    rh_node nd{};
+    for (int k = 0; k < 3; k++) { nd.lo[k] = lo[k]; nd.hi[k] = hi[k]; }
+    const uint32_t self = (uint32_t)nodes.size();
+    nodes.push_back(nd);
+    const size_t n = e - b;
+    if (n <= kSubLeaf) {
+      nodes[self].is_leaf = 1;
+      nodes[self].left = (uint32_t)order.size();
+      nodes[self].right = (uint32_t)n;
+      for (size_t i = b; i < e; i++) order.push_back(refs[i].slot);
+      return self;
+    }
+    // binned SAH over the three axes; deep or degenerate ranges fall back to the object median of the widest axis
+    constexpr int kBins = 16;
+    int best_axis = -1, best_bin = 0;
+    float best_cost = inf;
+    if (depth < 48) {
+      for (int axis = 0; axis < 3; axis++) {
+        const float ext = chi[axis] - clo[axis];
+        if (!(ext > 0)) continue;
+        const float scale = (float)kBins / ext;
+        float blo[kBins][3], bhi[kBins][3];
+        uint32_t cnt[kBins];
+        for (int i = 0; i < kBins; i++) {
+          cnt[i] = 0;
+          for (int k = 0; k < 3; k++) { blo[i][k] = inf; bhi[i][k] = -inf; }
+        }
+        for (size_t i = b; i < e; i++) {
+          int bi = (int)((refs[i].c[axis] - clo[axis]) * scale);
+          bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
+          cnt[bi]++;
+          for (int k = 0; k < 3; k++) {
+            blo[bi][k] = std::min(blo[bi][k], refs[i].lo[k]);
+            bhi[bi][k] = std::max(bhi[bi][k], refs[i].hi[k]);
+          }
+        }
+        float rarea[kBins];
+        uint32_t rcnt[kBins];
+        float alo[3] = {inf, inf, inf}, ahi[3] = {-inf, -inf, -inf};
+        uint32_t c = 0;
+        for (int i = kBins - 1; i > 0; i--) {
+          for (int k = 0; k < 3; k++) { alo[k] = std::min(alo[k], blo[i][k]); ahi[k] = std::max(ahi[k], bhi[i][k]); }
+          c += cnt[i];
+          rarea[i] = c ? area(alo, ahi) : 0.f;
+          rcnt[i] = c;
+        }
+        for (int k = 0; k < 3; k++) { alo[k] = inf; ahi[k] = -inf; }
+        c = 0;
+        for (int i = 1; i < kBins; i++) {
+          for (int k = 0; k < 3; k++) { alo[k] = std::min(alo[k], blo[i - 1][k]); ahi[k] = std::max(ahi[k], bhi[i - 1][k]); }
+          c += cnt[i - 1];
+          if (!c || !rcnt[i]) continue;
+          const float cost = area(alo, ahi) * (float)c + rarea[i] * (float)rcnt[i];
+          if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = i; }
+        }
+      }
+    }
+    size_t mid;
+    if (best_axis >= 0) {
+      const int axis = best_axis;
+      const float ext = chi[axis] - clo[axis], scale = (float)kBins / ext, c0 = clo[axis];
+      const int bb = best_bin;
+      mid = std::partition(refs.begin() + b, refs.begin() + e, [=](const Ref& r) {
+              int bi = (int)((r.c[axis] - c0) * scale);
+              bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
+              return bi < bb;
+            }) - refs.begin();
+    } else {
+      int axis = 0;
+      for (int k = 1; k < 3; k++)
+        if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+      mid = b + n / 2;
+      std::nth_element(refs.begin() + b, refs.begin() + mid, refs.begin() + e,
+                       [axis](const Ref& x, const Ref& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.slot < y.slot); });
+    }
+    if (mid == b || mid == e) mid = b + n / 2;
+    const uint32_t l = build(b, mid, depth + 1);
+    const uint32_t r = build(mid, e, depth + 1);
+    nodes[self].left = l;
+    nodes[self].right = r;
+    return self;
+  }
+
+  // Builds the tree of the triangles in the given reference slots; returns the root node index (RH_NO_NODE if none).
+  uint32_t run(const std::vector<uint32_t>& slots) {
+    if (slots.empty()) return RH_NO_NODE;
+    const uint32_t count = (uint32_t)slots.size();
+    refs.resize(count);
+    for (uint32_t k = 0; k < count; k++) {
+      Ref& r = refs[k];
+      r.slot = slots[k];
+      double lo[3], hi[3];
+      Refiner::tri_box(tris[slots[k]], lo, hi);
+      for (int a = 0; a < 3; a++) {  // float is enough to choose splits; the stored boxes are recomputed in double
+        r.lo[a] = (float)lo[a];
+        r.hi[a] = (float)hi[a];
+        r.c[a] = 0.5f * (r.lo[a] + r.hi[a]);
+      }
+    }
+    return build(0, count, 0);
+  }
+
+  // Exact (double, padded) boxes of all nodes from the permuted triangles, bottom-up.
+  void refit(const std::vector<rh_tri>& new_tris) {
+    const double inf = std::numeric_limits<double>::infinity();
+    for (size_t i = nodes.size(); i-- > 0;) {  // children always follow their parent in `nodes`
+      rh_node& nd = nodes[i];
+      for (int k = 0; k < 3; k++) { nd.lo[k] = inf; nd.hi[k] = -inf; }
+      if (nd.is_leaf) {
+        for (uint32_t t = 0; t < nd.right; t++) {
+          double lo[3], hi[3];
+          Refiner::tri_box(new_tris[nd.left + t], lo, hi);
+          for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], lo[k]); nd.hi[k] = std::max(nd.hi[k], hi[k]); }
+        }
+      } else {
+        for (uint32_t c : {nd.left, nd.right})
+          for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], nodes[c].lo[k]); nd.hi[k] = std::max(nd.hi[k], nodes[c].hi[k]); }
+      }
+    }
+  }
+};
+
 template <class T>
 int upload(DevBuf& b, const T* src, size_t n) {
   int rc = b.reserve(std::max<size_t>(n * sizeof(T), 256));
@@ -543,28 +699,83 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   std::vector<rh_tri_shade> dshade;
   std::vector<uint32_t> lin_objs, sphere_refs;
   uint32_t sphere_root = kEmpty;
+  std::vector<WideNode> wide_cull;      // RH_CULL_SAH: the float path's own tree (same super-root indices as `wide`)
+  std::vector<uint32_t> exact_index;    // RH_CULL_SAH: reference slot -> slot in the permuted triangle arrays
   try {
     int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
     if (rc) return rc;
     dtris.assign(d->tris, d->tris + d->n_tris);
     dshade.assign(d->tri_shade, d->tri_shade + d->n_tris);
+    // order key of the tie rule: the first slot of a triangle's reference leaf (leaves are numbered left to right by it)
+    for (uint32_t ni = 0; ni < d->n_nodes; ni++)
+      if (d->nodes[ni].is_leaf)
+        for (uint32_t k = 0; k < d->nodes[ni].right; k++) dtris[d->nodes[ni].left + k].pad_ = d->nodes[ni].left;
+#if RH_CULL_SAH
+    {
+      SahTree sah(dtris);
+      std::vector<rh_object> objects2(d->objects, d->objects + d->n_objects);
+      for (uint32_t i = 0; i < d->n_objects; i++) {
+        if (objects2[i].kind != RH_OBJ_MESH || objects2[i].root == RH_NO_NODE) continue;
+        std::vector<uint32_t> slots, dfs{objects2[i].root};
+        while (!dfs.empty()) {  // the mesh's triangles, in reference order
+          const rh_node& nd = d->nodes[dfs.back()];
+          dfs.pop_back();
+          if (nd.is_leaf) {
+            for (uint32_t k = 0; k < nd.right; k++) slots.push_back(nd.left + k);
+          } else {
+            if (nd.right != RH_NO_NODE) dfs.push_back(nd.right);
+            if (nd.left != RH_NO_NODE) dfs.push_back(nd.left);
+          }
+        }
+        objects2[i].root = sah.run(slots);
+      }
+      // permute the records into the cull tree's leaf order
+      std::vector<rh_tri> ptris(sah.order.size());
+      std::vector<rh_tri_shade> pshade(sah.order.size());
+      exact_index.assign(d->n_tris, 0);
+      for (size_t k = 0; k < sah.order.size(); k++) {
+        ptris[k] = dtris[sah.order[k]];
+        pshade[k] = dshade[sah.order[k]];
+        exact_index[sah.order[k]] = (uint32_t)k;
+      }
+      sah.refit(ptris);
+      dtris.swap(ptris);
+      dshade.swap(pshade);
+      rh_scene_desc d2 = *d;
+      d2.objects = objects2.data();
+      d2.nodes = sah.nodes.data();
+      d2.n_nodes = (uint32_t)sah.nodes.size();
+      d2.n_tris = (uint32_t)dtris.size();
+      std::vector<DObject> objs2;
+      std::vector<uint32_t> lin2, refs2;
+      uint32_t depth2 = 0, sroot2 = kEmpty;
+      rc = build_wide(d2, wide_cull, objs2, &depth2, lin2, refs2, &sroot2);
+      if (rc) return rc;
+      for (size_t i = 0; i < objs.size(); i++)
+        if (objs[i].root != objs2[i].root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: cull tree roots out of step");
+      if (sroot2 != sphere_root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: sphere tree roots out of step");
+      depth = std::max(depth, depth2);
+    }
+#else
     Refiner refiner{wide, dtris, dshade};
     refiner.run();
     depth += refiner.max_sub_depth + 1;  // refinement levels below the reference leaves
+#endif
     if (depth + 4 > (uint32_t)kStack) return rh::set_error(RH_ERR_ARG, "rh_scene_create: tree too deep for the traversal stack");
   } catch (const std::bad_alloc&) {
     return rh::set_error(RH_ERR_OOM, "rh_scene_create: out of host memory");
   }
+  const std::vector<WideNode>& cull = wide_cull.empty() ? wide : wide_cull;
   RH_CUDA(cudaSetDevice(D->dev));
   auto S = std::make_unique<rh_scene>();
   S->device = D;
   S->max_tree_depth = depth;
   int rc;
   // conservative float copy of the boxes: lower bounds rounded down, upper bounds rounded up
-  std::vector<WideNode32> wide32(wide.size());
+  std::vector<WideNode32> wide32(cull.size());
   float abs_max = 0.f;
-  for (size_t i = 0; i < wide.size(); i++) {
-    const WideNode& w = wide[i];
+  for (size_t i = 0; i < cull.size(); i++) {
+    const WideNode& w = cull[i];
     WideNode32& n = wide32[i];
     for (int c = 0; c < 2; c++) {
       for (int k = 0; k < 3; k++) {
@@ -595,6 +806,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   if ((rc = upload(S->texels, d->texels, (size_t)d->n_texels * 3))) return rc;
   if ((rc = upload(S->lin_objs, lin_objs.data(), lin_objs.size()))) return rc;
   if ((rc = upload(S->sphere_refs, sphere_refs.data(), sphere_refs.size()))) return rc;
+  if ((rc = upload(S->exact_index, exact_index.data(), exact_index.size()))) return rc;
   // occluder tables (isOccluder, RayHs.hs:81-82: everything but Emmit objects)
   std::vector<OccPlane> occ_planes;
   std::vector<OccSphere> occ_spheres;
@@ -638,7 +850,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.lights = (const rh_light*)S->lights.p;
   v.textures = (const rh_texture*)S->textures.p;
   v.texels = (const double*)S->texels.p;
-  v.n_wide = (uint32_t)wide.size();
+  v.n_wide = (uint32_t)cull.size();
   v.n_tris = d->n_tris;
   v.n_objects = d->n_objects;
   v.n_materials = d->n_materials;
@@ -646,6 +858,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.n_textures = d->n_textures;
   v.lin_objs = (const uint32_t*)S->lin_objs.p;
   v.sphere_refs = (const uint32_t*)S->sphere_refs.p;
+  v.exact_index = exact_index.empty() ? nullptr : (const uint32_t*)S->exact_index.p;
   v.n_lin = (uint32_t)lin_objs.size();
   v.sphere_root = sphere_root;
   v.n_smem_nodes = std::min<uint32_t>(v.n_wide, kSmemNodes);
@@ -659,7 +872,7 @@ void scene_destroy(rh_scene* s) {
   if (!s) return;
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
   for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels,
-                    &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes})
+                    &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes, &s->exact_index})
     b->release();
   delete s;
 }
@@ -1035,8 +1248,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->shadow_tasks = shadow_tasks;
       stats->rays_shadow_culled = fc->shadow_culled;
       if (counting && getenv("RAYHS_B200_DEBUG"))
-        fprintf(stderr, "rayhs_b200: exact shadow walks %llu, most nodes visited by one shadow ray %llu\n", fc->exact_walks,
-                fc->max_walk_nodes);
+        fprintf(stderr, "rayhs_b200: exact shadow walks %llu, most nodes visited by one shadow ray %llu; exact closest-hit walks %llu, "
+                "most nodes visited by one closest-hit ray %llu\n", fc->exact_walks, fc->max_walk_nodes, fc->exact_closest,
+                fc->max_closest_nodes);
       stats->upload_bytes = upload_bytes;
       float ms = 0;
       cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
