@@ -123,8 +123,9 @@ struct SceneView {
   uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables
-  float abs_max;            // largest |coordinate| of any mesh box (pads the fp32 slab test)
+  float abs_max;            // largest |coordinate - center| of any tree box (pads the fp32 slab test)
   uint32_t pad_;
+  double center[3];         // the float boxes of wide32 are stored relative to this point
 };
 
 // Camera with everything `rayFromPixel` recomputes per pixel hoisted to the host

@@ -173,19 +173,25 @@ struct RayF {
 //    test would pass every box and the ray would visit the whole tree (measured: 331 k nodes for one shadow ray of the
 //    1 M-triangle synthetic scene, a one-second tail) — while the double test culls as usual.
 // Decided on the exponent bits with integer compares.
-__device__ __forceinline__ bool needs_exact_walk(const Ray& r, float abs_max) {
+__device__ __forceinline__ bool needs_exact_walk(const Ray& r, const SceneView& S) {
   const uint32_t lo = 0x39B00000u, span = 0x46300000u - 0x39B00000u;  // biased exponents 923 (2^-100) and 1123 (2^100)
   const uint32_t hx = (uint32_t)__double2hiint(r.d.x) & 0x7fffffffu, hy = (uint32_t)__double2hiint(r.d.y) & 0x7fffffffu,
                  hz = (uint32_t)__double2hiint(r.d.z) & 0x7fffffffu;
-  const uint32_t lim = (uint32_t)__double2hiint(4096.0 * (double)abs_max);
-  const uint32_t ox = (uint32_t)__double2hiint(r.o.x) & 0x7fffffffu, oy = (uint32_t)__double2hiint(r.o.y) & 0x7fffffffu,
-                 oz = (uint32_t)__double2hiint(r.o.z) & 0x7fffffffu;
+  const uint32_t lim = (uint32_t)__double2hiint(4096.0 * (double)S.abs_max);
+  // distances are taken from the centre of the scene's boxes, like the float boxes themselves
+  const uint32_t ox = (uint32_t)__double2hiint(r.o.x - S.center[0]) & 0x7fffffffu,
+                 oy = (uint32_t)__double2hiint(r.o.y - S.center[1]) & 0x7fffffffu,
+                 oz = (uint32_t)__double2hiint(r.o.z - S.center[2]) & 0x7fffffffu;
   return !((hx - lo < span) & (hy - lo < span) & (hz - lo < span) & (ox < lim) & (oy < lim) & (oz < lim));
 }
 
-__device__ __forceinline__ RayF make_rayf(const Ray& r, float abs_max) {
+// The float boxes are stored relative to S.center (the middle of all tree boxes), so that a scene far from the
+// coordinate origin keeps float's full resolution; the ray origin is moved the same way (one correctly rounded double
+// subtraction: relative error 2^-53 of the result, far inside e's budget).
+__device__ __forceinline__ RayF make_rayf(const Ray& r, const SceneView& S) {
   RayF f;
-  const float ox = (float)r.o.x, oy = (float)r.o.y, oz = (float)r.o.z;
+  const float abs_max = S.abs_max;
+  const float ox = (float)(r.o.x - S.center[0]), oy = (float)(r.o.y - S.center[1]), oz = (float)(r.o.z - S.center[2]);
   // (float)max|o_k| == max|(float)o_k|: rounding is monotonic
   const float e = 4.76837158203125e-07f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) * 1.0000002f + abs_max);
   f.ix = __frcp_rn((float)r.d.x);  // two roundings (d -> float, reciprocal): still inside e's budget of eight
@@ -502,7 +508,7 @@ __device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, dou
 template <bool COUNT>
 __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, uint4* stack,
                                             Cnt<COUNT>& cnt) {
-  const RayF f = make_rayf(r, cx.S->abs_max);
+  const RayF f = make_rayf(r, *cx.S);
   best.t = __longlong_as_double(0x7ff0000000000000LL);
   best.u = best.v = 0;
   best.slot = 0;
@@ -546,7 +552,7 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
 template <bool COUNT>
 __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, uint4* stack,
                                          Cnt<COUNT>& cnt) {
-  const RayF f = make_rayf(r, cx.S->abs_max);
+  const RayF f = make_rayf(r, *cx.S);
   AnyHit sink;
   sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
   sink.lpos = ld3(L.vec);
@@ -948,7 +954,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(con
     Closest best;
     best.obj = -1;
     if (valid) {
-      const bool exact = P.exact_boxes || needs_exact_walk(r, S.abs_max);
+      const bool exact = P.exact_boxes || needs_exact_walk(r, S);
       unsigned long long nodes_before = 0;
       if constexpr (COUNT) nodes_before = cnt.nodes;
       closest_hit<COUNT>(cx, r, exact, best, stack, cnt);
@@ -1073,7 +1079,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
         continue;
       }
       const Ray sr = rayEps(p, ld);
-      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || needs_exact_walk(sr, S.abs_max), L, stack, cnt);
+      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || needs_exact_walk(sr, S), L, stack, cnt);
       if (!shadowed) acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));
     }
     const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
@@ -1131,8 +1137,8 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
     const V3 p = mk(a.x, a.y, b.x);
     const rh_light& L = cx.lights[li];
     const ShadowRay sr = make_shadow_ray(L, p, light_dir(L, p));
-    const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S.abs_max);
-    const RayF f = make_rayf(sr.r, S.abs_max);
+    const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S);
+    const RayF f = make_rayf(sr.r, S);
     bool hit = false;
     for (uint32_t k = 0; k < n_lin && !hit; k++) {
       const uint32_t oi = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
@@ -1184,8 +1190,8 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(
             n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
           } else {
             const ShadowRay sr = make_shadow_ray(L, p, ld);
-            const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S.abs_max);
-            const RayF f = make_rayf(sr.r, S.abs_max);
+            const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S);
+            const RayF f = make_rayf(sr.r, S);
             const float ffar = __double2float_ru(sr.far);
             bool shadowed = false;
             for (uint32_t k = 0; k < n_lin && !shadowed; k++) {
@@ -1333,7 +1339,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
     sm.mesh_roots[threadIdx.x] = root;
     const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
     for (int a = 0; a < 3; a++) {
-      const double lo = (double)fb[a], hi = (double)fb[3 + a];
+      const double lo = (double)fb[a] + S.center[a], hi = (double)fb[3 + a] + S.center[a];  // world coordinates
       sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
       sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
     }
@@ -1407,8 +1413,8 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
     sink.directional = q.directional;
     sink.lpos = q.lp;
     sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
-    const bool exact = P.exact_boxes || needs_exact_walk(r, S.abs_max);
-    const RayF f = make_rayf(r, S.abs_max);
+    const bool exact = P.exact_boxes || needs_exact_walk(r, S);
+    const RayF f = make_rayf(r, S);
     bool hit = false;
     unsigned long long nodes_before = 0;
     if constexpr (COUNT) {
@@ -1535,10 +1541,10 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
               }
               // the root boxes themselves (slot 0 of each super-root)
               if (!may) {
-              } else if (P.exact_boxes || needs_exact_walk(r, S.abs_max)) {
+              } else if (P.exact_boxes || needs_exact_walk(r, S)) {
                 need_walk = true;
               } else {
-                const RayF f = make_rayf(r, S.abs_max);
+                const RayF f = make_rayf(r, S);
                 const float ffar = __double2float_ru(q.far);
                 for (uint32_t m = 0; m < n_roots && !need_walk; m++) {
                   const uint32_t root = sm.mesh_roots[m];
@@ -1622,7 +1628,7 @@ __device__ __forceinline__ void stage_shadow_tables(ShadowTables& sm, const Scen
     sm.mesh_roots[threadIdx.x] = root;
     const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
     for (int a = 0; a < 3; a++) {
-      const double lo = (double)fb[a], hi = (double)fb[3 + a];
+      const double lo = (double)fb[a] + S.center[a], hi = (double)fb[3 + a] + S.center[a];  // world coordinates
       sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
       sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
     }
@@ -1739,8 +1745,8 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
   Ray r;
   r.o = q.o;
   r.d = q.ld;
-  if (exact_boxes || needs_exact_walk(r, S.abs_max)) return true;
-  const RayF f = make_rayf(r, S.abs_max);
+  if (exact_boxes || needs_exact_walk(r, S)) return true;
+  const RayF f = make_rayf(r, S);
   const float ffar = __double2float_ru(q.far);
   bool need = false;
   for (uint32_t m = 0; m < n_roots && !need; m++) {
@@ -1933,7 +1939,7 @@ __global__ void __launch_bounds__(kWalkBlock, 1) shadow_walk_kernel(const __grid
           sink.lpos = q.lp;
           sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
           const size_t flag_at = (size_t)item * n_lights + li;
-          if (P.exact_boxes || needs_exact_walk(r, S.abs_max)) {
+          if (P.exact_boxes || needs_exact_walk(r, S)) {
             // rare (far origins): the reference's own double boxes, run to the end right here
             if constexpr (COUNT) atomicAdd(&P.counters->exact_walks, 1ull);
             bool hit = false;
@@ -1950,7 +1956,7 @@ __global__ void __launch_bounds__(kWalkBlock, 1) shadow_walk_kernel(const __grid
             lane_slot(7) = sink.dl2;
             lane_slot(8) = __longlong_as_double((long long)flag_at);
             directional = q.directional;
-            f = make_rayf(r, S.abs_max);
+            f = make_rayf(r, S);
             ffar = __double2float_ru(q.far);
             sp = 0;
             for (uint32_t m = 1; m < n_roots; m++) stack[sp++] = make_uint4(sm.mesh_roots[m], 0, 0, 0);  // entry distance 0

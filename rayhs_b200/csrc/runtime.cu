@@ -772,24 +772,42 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   S->max_tree_depth = depth;
   int rc;
   // conservative float copy of the boxes: lower bounds rounded down, upper bounds rounded up
+  // ... stored relative to the middle of all boxes, so that a scene far from the coordinate origin keeps float's full
+  // resolution (one correctly rounded double subtraction per coordinate, then one extra float ulp outward for it)
   std::vector<WideNode32> wide32(cull.size());
   float abs_max = 0.f;
+  double center[3] = {0, 0, 0};
+  {
+    const double inf = std::numeric_limits<double>::infinity();
+    double blo[3] = {inf, inf, inf}, bhi[3] = {-inf, -inf, -inf};
+    for (const WideNode& w : cull)
+      for (int c = 0; c < 2; c++)
+        if (w.child[c] != kEmpty)
+          for (int k = 0; k < 3; k++) {
+            const double lo = w.box[6 * c + k], hi = w.box[6 * c + 3 + k];
+            if (!(std::fabs(lo) < 1e30) || !(std::fabs(hi) < 1e30))
+              return rh::set_error(RH_ERR_ARG, "rh_scene_create: box coordinate is not finite or exceeds 1e30");
+            blo[k] = std::min(blo[k], lo);
+            bhi[k] = std::max(bhi[k], hi);
+          }
+    for (int k = 0; k < 3; k++)
+      if (blo[k] <= bhi[k]) center[k] = 0.5 * (blo[k] + bhi[k]);
+  }
+  const float finf = std::numeric_limits<float>::infinity();
   for (size_t i = 0; i < cull.size(); i++) {
     const WideNode& w = cull[i];
     WideNode32& n = wide32[i];
     for (int c = 0; c < 2; c++) {
       for (int k = 0; k < 3; k++) {
-        const double lo = w.box[6 * c + k], hi = w.box[6 * c + 3 + k];
+        const double lo = w.box[6 * c + k] - center[k], hi = w.box[6 * c + 3 + k] - center[k];
         float flo = (float)lo, fhi = (float)hi;
-        if ((double)flo > lo) flo = std::nextafterf(flo, -std::numeric_limits<float>::infinity());
-        if ((double)fhi < hi) fhi = std::nextafterf(fhi, std::numeric_limits<float>::infinity());
+        if ((double)flo > lo) flo = std::nextafterf(flo, -finf);
+        if ((double)fhi < hi) fhi = std::nextafterf(fhi, finf);
+        if (std::isfinite(flo)) flo = std::nextafterf(flo, -finf);
+        if (std::isfinite(fhi)) fhi = std::nextafterf(fhi, finf);
         n.box[6 * c + k] = flo;
         n.box[6 * c + 3 + k] = fhi;
-        if (w.child[c] != kEmpty) {
-          if (!(std::fabs(lo) < 1e30) || !(std::fabs(hi) < 1e30))
-            return rh::set_error(RH_ERR_ARG, "rh_scene_create: box coordinate is not finite or exceeds 1e30");
-          abs_max = std::max(abs_max, std::max(std::fabs(flo), std::fabs(fhi)));
-        }
+        if (w.child[c] != kEmpty) abs_max = std::max(abs_max, std::max(std::fabs(flo), std::fabs(fhi)));
       }
       n.child[c] = w.child[c];
       n.first[c] = w.first[c];
@@ -843,6 +861,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
   v.abs_max = abs_max;
+  for (int k = 0; k < 3; k++) v.center[k] = center[k];
   v.tris = (const rh_tri*)S->tris.p;
   v.shade = (const rh_tri_shade*)S->shade.p;
   v.objects = (const DObject*)S->objects.p;

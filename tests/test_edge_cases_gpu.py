@@ -190,3 +190,27 @@ def test_centre_row_and_column_rays_take_the_exact_path():
                   [{"kind": "point", "vec": (0, 0, -1), "color": (3, 3, 3), "radius": 1.0}])
     both(rs, 64, 64)
     both(rs, 65, 63)
+
+
+def test_scene_far_from_the_coordinate_origin_keeps_parity_and_the_float_cull():
+    """The float cull boxes are stored relative to the middle of the scene: a scene translated by (1e6, -2e6, 3e6) must
+    still match its oracle bit for bit AND still cull (node visits within 2x of the untranslated scene; absolute float
+    coordinates would resolve nothing at 1e6 and every ray would visit the whole tree)."""
+    def scene(shift):
+        sx, sy, sz = shift
+        g = grid_mesh(24, z=1.0, wobble=0.15)
+        g["positions"] = np.asarray(g["positions"]) + np.array(shift)
+        objs = [dict(kind="mesh", material=1, **g),
+                {"kind": "sphere", "center": (sx + 0.4, sy - 0.2, sz + 0.3), "radius": 0.3, "material": 0},
+                {"kind": "plane", "point": (sx, sy - 0.8, sz), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 0}]
+        mats = [{"kind": "diffuse", "color1": (0.8, 0.7, 0.6)}, {"kind": "plastic", "ior": 1.6, "color1": (0.3, 0.6, 0.9)}]
+        lights = [{"kind": "point", "vec": (sx + 0.5, sy + 1.5, sz - 1.0), "color": (30, 30, 30), "radius": 0.5}]
+        return RawScene(objs, mats, lights, camera={"position": (sx, sy + 0.3, sz - 2.5), "target": (sx, sy, sz + 0.5)})
+
+    near, far = scene((0.0, 0.0, 0.0)), scene((1e6, -2e6, 3e6))
+    both(near, 160, 120)
+    both(far, 160, 120)
+    job_n, job_f = rh.Rendering(near, near.camera, 160, 120, 3), rh.Rendering(far, far.camera, 160, 120, 3)
+    n = rh.render(job_n, count=True, shadow="pooled").stats
+    f = rh.render(job_f, count=True, shadow="pooled").stats
+    assert f["node_visits"] + f["shadow_node_visits"] < 2 * (n["node_visits"] + n["shadow_node_visits"]), (n, f)
