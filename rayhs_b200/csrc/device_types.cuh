@@ -64,6 +64,9 @@ struct __align__(16) WideNode {
   uint32_t refine;    // bit c: child c's box is a culling refinement inside a reference leaf (not a reference box)
   uint32_t pad_[3];
 };
+#ifndef RH_LANES
+#define RH_LANES 2  // chunks in flight (streams with their own queues); 1 = strictly one chunk after the other
+#endif
 #ifndef RH_CULL_SAH
 #define RH_CULL_SAH 1  // 1: the float path culls with its own SAH tree; 0: the reference tree refined below its leaves
 #endif

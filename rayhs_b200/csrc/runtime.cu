@@ -76,11 +76,17 @@ struct Device {
   int dev = -1;
   int n_sms = 0;
   size_t total_mem = 0;
-  cudaStream_t stream = nullptr;       // kernels
+  cudaStream_t stream = nullptr;       // kernels (lane 0)
+  cudaStream_t stream2 = nullptr;      // kernels of every second chunk when two chunks are in flight (lane 1)
   cudaStream_t copy_stream = nullptr;  // sample-offset uploads
+  cudaEvent_t ev_lane = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
-  DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, ctl, counters, offsets, rgb, ids;
+  // per-lane scratch: a chunk's accumulators and queues
+  struct Scratch {
+    DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags;
+  } lane[2];
+  DevBuf ctl, counters, offsets, rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
   size_t pinned_bytes = 0;
   int grid_trace[2] = {0, 0}, grid_shadow[2] = {0, 0};
@@ -96,7 +102,9 @@ struct Device {
     n_sms = prop.multiProcessorCount;
     total_mem = prop.totalGlobalMem;
     RH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    RH_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     RH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    RH_CUDA(cudaEventCreateWithFlags(&ev_lane, cudaEventDisableTiming));
     RH_CUDA(cudaEventCreate(&ev_begin));
     RH_CUDA(cudaEventCreate(&ev_end));
     RH_CUDA((cudaError_t)configure_kernels());
@@ -110,16 +118,20 @@ struct Device {
   void close() {
     if (dev < 0) return;
     cudaSetDevice(dev);
-    for (DevBuf* b : {&accum, &rayq[0], &rayq[1], &shq, &shq_sample, &walk_q, &deferred_q, &pair_flags, &ctl, &counters, &offsets,
-                      &rgb, &ids})
+    for (Scratch& sc : lane)
+      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.shq, &sc.shq_sample, &sc.walk_q, &sc.deferred_q, &sc.pair_flags})
+        b->release();
+    for (DevBuf* b : {&ctl, &counters, &offsets, &rgb, &ids})
       b->release();
     if (pinned) cudaFreeHost(pinned);
     pinned = nullptr;
     pinned_bytes = 0;
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
     prof_events.clear();
-    for (cudaEvent_t e : {ev_begin, ev_end})
+    for (cudaEvent_t e : {ev_begin, ev_end, ev_lane})
       if (e) cudaEventDestroy(e);
+    if (stream2) cudaStreamDestroy(stream2);
+    stream2 = nullptr;
     for (cudaEvent_t e : ev_up) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_done) cudaEventDestroy(e);
     ev_up.clear();
@@ -1028,7 +1040,12 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       d_ids = (int2*)D->ids.p;
     }
   }
-  if ((rc = D->accum.reserve(chunk_samples * 3 * sizeof(double)))) return rc;
+  // Two chunks in flight (two streams, two sets of queues) when the frame has several: the kernels are persistent and
+  // fill the GPU, so a chunk's next kernel starts on the SMs the other chunk's kernel frees as its warps run out of
+  // work — the tail of every launch is filled instead of idle.  One lane when every launch is timed on its own.
+  const int n_lanes = (RH_LANES > 1 && n_chunks >= 2 && !profile && !counting) ? 2 : 1;
+  for (int l = 0; l < n_lanes; l++)
+    if ((rc = D->lane[l].accum.reserve(chunk_samples * 3 * sizeof(double)))) return rc;
   if ((rc = D->ctl.reserve((size_t)n_chunks * sizeof(ChunkCtl)))) return rc;
   if ((rc = D->counters.reserve(sizeof(FrameCounters)))) return rc;
   const size_t pinned_need = (size_t)n_chunks * sizeof(ChunkCtl) + sizeof(FrameCounters);
@@ -1079,19 +1096,23 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   uint32_t factor = 2;  // queue capacity = factor * chunk samples; doubled when a chunk overflows
   for (;;) {
     const size_t cap = std::min<size_t>((size_t)factor * chunk_samples, 0x7ffffff0u);
-    for (int k = 0; k < 2; k++)
-      if ((rc = D->rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
-    if ((rc = D->shq.reserve(cap * 5 * sizeof(double2)))) return rc;
-    if ((rc = D->shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
     const bool split = use_split;
     const size_t walk_cap = std::min<size_t>(cap * std::max<uint32_t>(1, scene->view.n_lights), 0xfffffff0u);
-    if (split) {
-      if ((rc = D->walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
-      if ((rc = D->deferred_q.reserve(cap * sizeof(uint32_t)))) return rc;
-      if ((rc = D->pair_flags.reserve(cap * scene->view.n_lights))) return rc;
+    for (int l = 0; l < n_lanes; l++) {
+      Device::Scratch& sc = D->lane[l];
+      for (int k = 0; k < 2; k++)
+        if ((rc = sc.rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
+      if ((rc = sc.shq.reserve(cap * 5 * sizeof(double2)))) return rc;
+      if ((rc = sc.shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
+      if (split) {
+        if ((rc = sc.walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
+        if ((rc = sc.deferred_q.reserve(cap * sizeof(uint32_t)))) return rc;
+        if ((rc = sc.pair_flags.reserve(cap * scene->view.n_lights))) return rc;
+      }
     }
 
     size_t ev_used = 0;
+    cudaStream_t lane_stream = D->stream;  // the stream of the chunk being enqueued
     auto prof_event = [&]() -> cudaEvent_t {
       if (ev_used == D->prof_events.size()) {
         cudaEvent_t e;
@@ -1099,7 +1120,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         D->prof_events.push_back(e);
       }
       cudaEvent_t e = D->prof_events[ev_used++];
-      cudaEventRecord(e, D->stream);
+      cudaEventRecord(e, lane_stream);
       return e;
     };
     struct Span { cudaEvent_t a, b; int kind; };
@@ -1111,6 +1132,10 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     if (mode == RH_OFFSETS_TILED_F64 && !dev_off)
       RH_CUDA(cudaMemcpyAsync((void*)d_offsets, o->offsets, (size_t)o->offset_tile * o->offset_tile * spp * off_elem,
                               cudaMemcpyHostToDevice, D->stream));
+    if (n_lanes > 1) {  // lane 1 starts after the control blocks are zeroed
+      RH_CUDA(cudaEventRecord(D->ev_lane, D->stream));
+      RH_CUDA(cudaStreamWaitEvent(D->stream2, D->ev_lane, 0));
+    }
     uint32_t launches = 0;
     size_t upload_bytes = 0;
 
@@ -1128,6 +1153,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       const int ck = order[i];
       const int first_row = first_rows[ck];
       const int n_rows = plan[ck];
+      Device::Scratch& sc = D->lane[i % n_lanes];
+      lane_stream = (i % n_lanes) ? D->stream2 : D->stream;
       ChunkParams P{};
       P.first_row = first_row;
       P.n_rows = n_rows;
@@ -1145,7 +1172,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.offset_tile = o->offset_tile;
       P.offsets = d_offsets;
       P.offset_seed = offset_seed;
-      P.accum = (double*)D->accum.p;
+      P.accum = (double*)sc.accum.p;
       P.accum_stride = (uint32_t)chunk_samples;
       P.hit_ids = d_ids;
       P.rgb = d_rgb;
@@ -1155,12 +1182,12 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       }
       P.ctl = (ChunkCtl*)D->ctl.p + ck;
       P.counters = (FrameCounters*)D->counters.p;
-      P.q_shadow.plane = (double2*)D->shq.p;
-      P.q_shadow.sample = (uint32_t*)D->shq_sample.p;
+      P.q_shadow.plane = (double2*)sc.shq.p;
+      P.q_shadow.sample = (uint32_t*)sc.shq_sample.p;
       P.q_shadow.capacity = (uint32_t)cap;
-      P.walk_q = (uint2*)D->walk_q.p;
-      P.deferred_q = (uint32_t*)D->deferred_q.p;
-      P.pair_flags = (uint8_t*)D->pair_flags.p;
+      P.walk_q = (uint2*)sc.walk_q.p;
+      P.deferred_q = (uint32_t*)sc.deferred_q.p;
+      P.pair_flags = (uint8_t*)sc.pair_flags.p;
       P.walk_capacity = (uint32_t)walk_cap;
 
       if (stream_offsets) {
@@ -1184,37 +1211,42 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
           lr += run;
         }
         RH_CUDA(cudaEventRecord(D->ev_up[b], D->copy_stream));
-        RH_CUDA(cudaStreamWaitEvent(D->stream, D->ev_up[b], 0));
+        RH_CUDA(cudaStreamWaitEvent(lane_stream, D->ev_up[b], 0));
         P.offsets = slot;
         chunk_ev.push_back(prof_event());  // after the wait: the span holds kernel time only
       }
 
-      RH_CUDA(cudaMemset2DAsync(D->accum.p, chunk_samples * sizeof(double), 0, (size_t)P.n_samples * sizeof(double), 3, D->stream));
+      RH_CUDA(cudaMemset2DAsync(sc.accum.p, chunk_samples * sizeof(double), 0, (size_t)P.n_samples * sizeof(double), 3, lane_stream));
       for (int pass = 0; pass < n_passes; pass++) {
         P.pass = pass;
-        P.q_in.plane = (double2*)D->rayq[(pass + 1) & 1].p;
+        P.q_in.plane = (double2*)sc.rayq[(pass + 1) & 1].p;
         P.q_in.capacity = (uint32_t)cap;
-        P.q_out.plane = (double2*)D->rayq[pass & 1].p;
+        P.q_out.plane = (double2*)sc.rayq[pass & 1].p;
         P.q_out.capacity = (uint32_t)cap;  // (the last pass cannot emit: every ray in it has depth == maxDepth)
         cudaEvent_t a = nullptr;
         if (profile) a = prof_event();
-        launch_trace(scene->view, cam, P, counting, D->grid_trace[counting], D->stream);
+        launch_trace(scene->view, cam, P, counting, D->grid_trace[counting], lane_stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
-        launch_shadow(scene->view, P, counting, use_split, D->grid_shadow[counting], D->stream);
+        launch_shadow(scene->view, P, counting, use_split, D->grid_shadow[counting], lane_stream);
         if (profile) spans.push_back({a, prof_event(), 1});
         launches += 1 + (use_split ? 3 : 1);
       }
       cudaEvent_t a = nullptr;
       if (profile) a = prof_event();
-      launch_resolve(P, D->stream);
+      launch_resolve(P, lane_stream);
       if (profile) spans.push_back({a, prof_event(), 2});
       launches += 1;
       if (stream_offsets) {
-        RH_CUDA(cudaEventRecord(D->ev_done[i % ring], D->stream));
+        RH_CUDA(cudaEventRecord(D->ev_done[i % ring], lane_stream));
         chunk_ev.push_back(prof_event());
       }
     }
     RH_CUDA(cudaGetLastError());
+    lane_stream = D->stream;
+    if (n_lanes > 1) {  // join: everything below waits for lane 1 too
+      RH_CUDA(cudaEventRecord(D->ev_lane, D->stream2));
+      RH_CUDA(cudaStreamWaitEvent(D->stream, D->ev_lane, 0));
+    }
     RH_CUDA(cudaMemcpyAsync(D->pinned, D->ctl.p, (size_t)n_chunks * sizeof(ChunkCtl), cudaMemcpyDeviceToHost, D->stream));
     RH_CUDA(cudaMemcpyAsync((char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl), D->counters.p, sizeof(FrameCounters),
                             cudaMemcpyDeviceToHost, D->stream));

@@ -21,6 +21,7 @@ ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--pack", default="dragon_full")
 ap.add_argument("--count", action="store_true")
 ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--no-profile", action="store_true", help="no per-launch events: lets two chunks be in flight")
 ap.add_argument("--shadow", default="pooled", choices=["auto", "pooled", "split"],
                 help="shadow-ray schedule; forced by default so that every frame launches the same kernels")
 a = ap.parse_args()
@@ -33,6 +34,6 @@ L.rh_sample_offsets_f64(24, a.width * a.height, a.spp, off.data_ptr())
 off_dev = off.cuda()
 rgb = torch.empty((a.height, a.width, 3), dtype=torch.uint8, device="cuda")
 for i in range(a.frames):
-    st = rh.render_device(job, rgb, spp=a.spp, offsets_dev=off_dev, profile=True, count=a.count, chunk_samples=a.chunk,
+    st = rh.render_device(job, rgb, spp=a.spp, offsets_dev=off_dev, profile=not a.no_profile, count=a.count, chunk_samples=a.chunk,
                           shadow=None if a.shadow == "auto" else a.shadow)
 print(json.dumps(st))
