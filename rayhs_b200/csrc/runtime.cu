@@ -1007,8 +1007,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       const size_t L = std::max<uint32_t>(1, scene->view.n_lights);
       const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4 + 4 + L * (sizeof(uint2) + 1));
       want = std::min<size_t>((size_t)(0.4 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
-      if (host_offsets) want = std::min<size_t>(want, (size_t)16 << 20);
-      first = host_offsets ? std::min<size_t>(want, (size_t)4 << 20) : want;
+      if (host_offsets) want = std::min<size_t>(want, (size_t)RH_STREAM_CHUNK_MI << 20);
+      first = host_offsets ? std::min<size_t>(want, (size_t)RH_STREAM_FIRST_MI << 20) : want;
     }
     int row = 0;
     while (row < rows_local) {
