@@ -387,132 +387,15 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
   return RH_OK;
 }
 
-// Culling refinement below the reference's leaves.  A reference leaf holds up to 19 triangles
-// (KDTree.hs:82), all of which the reference tests once the leaf's box passes.  Here each such leaf
-// becomes a small SAH-split subtree whose leaves hold <= kSubLeaf triangles, so a ray only tests the
-// triangles near it.  The reference's result does not change: a triangle it would have accepted is
-// inside its own sub-box, and the conservative float test never rejects a box the ray enters.
-// The exact (double) walk treats these boxes as always-hit (WideNode::refine), i.e. it still tests
-// every triangle of a reference leaf whose box passes.  Triangles are permuted inside their leaf's
-// slot range; the tie rule's keys travel with them (rh_tri::pad_ = reference leaf, tri_id = list order).
-struct Refiner {
-  std::vector<WideNode>& wide;
-  std::vector<rh_tri>& tris;
-  std::vector<rh_tri_shade>& shade;
-  struct Item { uint32_t slot; double lo[3], hi[3], c[3]; };
-  uint32_t max_sub_depth = 0;
-
+// Bounding box of one triangle record, padded for p0 + e != p exactly.
+struct TriBox {
   static void tri_box(const rh_tri& t, double* lo, double* hi) {
     for (int k = 0; k < 3; k++) {
       const double a = t.p0[k], b = t.p0[k] + t.e1[k], c = t.p0[k] + t.e2[k];
-      const double pad = 4e-16 * (std::fabs(a) + std::fabs(t.e1[k]) + std::fabs(t.e2[k]));  // p0 + e != p exactly
+      const double pad = 4e-16 * (std::fabs(a) + std::fabs(t.e1[k]) + std::fabs(t.e2[k]));
       lo[k] = std::min(a, std::min(b, c)) - pad;
       hi[k] = std::max(a, std::max(b, c)) + pad;
     }
-  }
-  static double area(const double* lo, const double* hi) {
-    const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
-    return x * y + y * z + z * x;
-  }
-  static void grow(double* lo, double* hi, const Item& it) {
-    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], it.lo[k]); hi[k] = std::max(hi[k], it.hi[k]); }
-  }
-
-  // Fills slot `c` of wide[w] for items[b, e) which occupy triangle slots first + [b, e).
-  void build(uint32_t w, int c, std::vector<Item>& items, size_t b, size_t e, uint32_t first, uint32_t sub_depth) {
-    max_sub_depth = std::max(max_sub_depth, sub_depth);
-    const double inf = std::numeric_limits<double>::infinity();
-    double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-    for (size_t i = b; i < e; i++) grow(lo, hi, items[i]);
-    memcpy(wide[w].box + 6 * c, lo, sizeof lo);
-    memcpy(wide[w].box + 6 * c + 3, hi, sizeof hi);
-    wide[w].refine |= 1u << c;
-    const size_t n = e - b;
-    if (n <= kSubLeaf) {
-      wide[w].child[c] = kLeafBit | (uint32_t)n;
-      wide[w].first[c] = first + (uint32_t)b;
-      return;
-    }
-    // SAH sweep over the three axes (n <= 19: exhaustive)
-    double best_cost = inf;
-    int best_axis = 0;
-    size_t best_k = b + n / 2;
-    std::vector<Item> tmp(items.begin() + b, items.begin() + e), best_order;
-    std::vector<double> right(n);
-    for (int axis = 0; axis < 3; axis++) {
-      std::stable_sort(tmp.begin(), tmp.end(), [axis](const Item& x, const Item& y) { return x.c[axis] < y.c[axis]; });
-      double rlo[3] = {inf, inf, inf}, rhi[3] = {-inf, -inf, -inf};
-      for (size_t i = n; i-- > 1;) { grow(rlo, rhi, tmp[i]); right[i] = area(rlo, rhi); }
-      double llo[3] = {inf, inf, inf}, lhi[3] = {-inf, -inf, -inf};
-      for (size_t i = 1; i < n; i++) {
-        grow(llo, lhi, tmp[i - 1]);
-        const double cost = area(llo, lhi) * (double)i + right[i] * (double)(n - i);
-        if (cost < best_cost) { best_cost = cost; best_axis = axis; best_k = b + i; best_order = tmp; }
-      }
-    }
-    (void)best_axis;
-    if (!best_order.empty()) std::copy(best_order.begin(), best_order.end(), items.begin() + b);
-    const uint32_t wi = (uint32_t)wide.size();
-    wide[w].child[c] = wi;
-    WideNode nn{};
-    nn.child[0] = nn.child[1] = kEmpty;
-    wide.push_back(nn);
-    build(wi, 0, items, b, best_k, first, sub_depth + 1);
-    build(wi, 1, items, best_k, e, first, sub_depth + 1);
-  }
-
-  void run() {
-    const size_t n_ref = wide.size();
-    std::vector<rh_tri> tsrc;
-    std::vector<rh_tri_shade> ssrc;
-    for (size_t w = 0; w < n_ref; w++)
-      for (int c = 0; c < 2; c++) {
-        const uint32_t ch = wide[w].child[c];
-        if (ch == kEmpty || !(ch & kLeafBit) || (wide[w].refine & kSphereTreeFlag)) continue;
-        const uint32_t count = ch & ~kLeafBit, first = wide[w].first[c];
-        for (uint32_t k = 0; k < count; k++) tris[first + k].pad_ = first;  // reference-leaf order key
-        if (count <= kSubLeaf) continue;
-        std::vector<Item> items(count);
-        for (uint32_t k = 0; k < count; k++) {
-          items[k].slot = first + k;
-          tri_box(tris[first + k], items[k].lo, items[k].hi);
-          for (int a = 0; a < 3; a++) items[k].c[a] = 0.5 * (items[k].lo[a] + items[k].hi[a]);
-        }
-        // the reference leaf keeps its own (reference) box in the parent slot; the subtree hangs below a new node
-        const uint32_t wi = (uint32_t)wide.size();
-        WideNode nn{};
-        nn.child[0] = nn.child[1] = kEmpty;
-        const double inf = std::numeric_limits<double>::infinity();
-        for (int k = 0; k < 3; k++) { nn.box[k] = nn.box[6 + k] = inf; nn.box[3 + k] = nn.box[9 + k] = -inf; }
-        wide.push_back(nn);
-        wide[w].child[c] = wi;
-        // split once at the top so that both slots of the new node are used
-        double best_cost = inf;
-        size_t best_k = count / 2;
-        std::vector<Item> tmp = items, best_order;
-        std::vector<double> right(count);
-        for (int axis = 0; axis < 3; axis++) {
-          std::stable_sort(tmp.begin(), tmp.end(), [axis](const Item& x, const Item& y) { return x.c[axis] < y.c[axis]; });
-          double rlo[3] = {inf, inf, inf}, rhi[3] = {-inf, -inf, -inf};
-          for (size_t i = count; i-- > 1;) { grow(rlo, rhi, tmp[i]); right[i] = area(rlo, rhi); }
-          double llo[3] = {inf, inf, inf}, lhi[3] = {-inf, -inf, -inf};
-          for (size_t i = 1; i < count; i++) {
-            grow(llo, lhi, tmp[i - 1]);
-            const double cost = area(llo, lhi) * (double)i + right[i] * (double)(count - i);
-            if (cost < best_cost) { best_cost = cost; best_k = i; best_order = tmp; }
-          }
-        }
-        if (!best_order.empty()) items = best_order;
-        build(wi, 0, items, 0, best_k, first, 1);
-        build(wi, 1, items, best_k, count, first, 1);
-        // permute the triangle and shading records of this leaf
-        tsrc.assign(tris.begin() + first, tris.begin() + first + count);
-        ssrc.assign(shade.begin() + first, shade.begin() + first + count);
-        for (uint32_t k = 0; k < count; k++) {
-          tris[first + k] = tsrc[items[k].slot - first];
-          shade[first + k] = ssrc[items[k].slot - first];
-        }
-      }
   }
 };
 
@@ -642,7 +525,7 @@ struct SahTree {
       Ref& r = refs[k];
       r.slot = slots[k];
       double lo[3], hi[3];
-      Refiner::tri_box(tris[slots[k]], lo, hi);
+      TriBox::tri_box(tris[slots[k]], lo, hi);
       for (int a = 0; a < 3; a++) {  // float is enough to choose splits; the stored boxes are recomputed in double
         r.lo[a] = (float)lo[a];
         r.hi[a] = (float)hi[a];
@@ -661,7 +544,7 @@ struct SahTree {
       if (nd.is_leaf) {
         for (uint32_t t = 0; t < nd.right; t++) {
           double lo[3], hi[3];
-          Refiner::tri_box(new_tris[nd.left + t], lo, hi);
+          TriBox::tri_box(new_tris[nd.left + t], lo, hi);
           for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], lo[k]); nd.hi[k] = std::max(nd.hi[k], hi[k]); }
         }
       } else {
@@ -711,8 +594,8 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   std::vector<rh_tri_shade> dshade;
   std::vector<uint32_t> lin_objs, sphere_refs;
   uint32_t sphere_root = kEmpty;
-  std::vector<WideNode> wide_cull;      // RH_CULL_SAH: the float path's own tree (same super-root indices as `wide`)
-  std::vector<uint32_t> exact_index;    // RH_CULL_SAH: reference slot -> slot in the permuted triangle arrays
+  std::vector<WideNode> wide_cull;      // the float path's own tree (same super-root indices as `wide`)
+  std::vector<uint32_t> exact_index;    // reference slot -> slot in the permuted triangle arrays
   try {
     int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
     if (rc) return rc;
@@ -722,7 +605,6 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
     for (uint32_t ni = 0; ni < d->n_nodes; ni++)
       if (d->nodes[ni].is_leaf)
         for (uint32_t k = 0; k < d->nodes[ni].right; k++) dtris[d->nodes[ni].left + k].pad_ = d->nodes[ni].left;
-#if RH_CULL_SAH
     {
       SahTree sah(dtris);
       std::vector<rh_object> objects2(d->objects, d->objects + d->n_objects);
@@ -768,11 +650,6 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       if (sroot2 != sphere_root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: sphere tree roots out of step");
       depth = std::max(depth, depth2);
     }
-#else
-    Refiner refiner{wide, dtris, dshade};
-    refiner.run();
-    depth += refiner.max_sub_depth + 1;  // refinement levels below the reference leaves
-#endif
     if (depth + 4 > (uint32_t)kStack) return rh::set_error(RH_ERR_ARG, "rh_scene_create: tree too deep for the traversal stack");
   } catch (const std::bad_alloc&) {
     return rh::set_error(RH_ERR_OOM, "rh_scene_create: out of host memory");

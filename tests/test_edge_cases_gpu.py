@@ -214,3 +214,24 @@ def test_scene_far_from_the_coordinate_origin_keeps_parity_and_the_float_cull():
     n = rh.render(job_n, count=True, shadow="pooled").stats
     f = rh.render(job_f, count=True, shadow="pooled").stats
     assert f["node_visits"] + f["shadow_node_visits"] < 2 * (n["node_visits"] + n["shadow_node_visits"]), (n, f)
+
+
+def test_scene_beyond_the_fast_shadow_tables_uses_the_general_pooled_kernel():
+    """14 lights, 18 occluding planes and 9 meshes exceed the shared-memory occluder tables of the fast shadow kernels
+    (12 / 16 / 8): the general pooled kernel (object table walked with kind dispatch) must give the same image."""
+    rng = np.random.RandomState(21)
+    lights = [{"kind": "point", "vec": tuple(rng.uniform(-1, 1, 3) * (1.2, 0.3, 1.2) + (0, 1.6, 0.3)), "color": (1.5, 1.5, 1.5),
+               "radius": 0.5} for _ in range(13)] + [{"kind": "directional", "vec": (0.2, 1.0, -0.3), "color": (0.2, 0.2, 0.2)}]
+    objs = [{"kind": "plane", "point": (0, -0.6, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 0}]
+    for k in range(17):   # slanted planes behind and beside the scene
+        a = 0.37 * k
+        objs.append({"kind": "plane", "point": (3 * np.cos(a), 0, 2.5 + 3 * abs(np.sin(a))), "normal": (-np.cos(a), 0.1, -abs(np.sin(a)) - 0.2),
+                     "tangent": (0, 1, 0), "material": k % 2})
+    for k in range(9):
+        g = grid_mesh(5, z=0.6 + 0.15 * k, wobble=0.05, seed=k)
+        g["positions"] = np.asarray(g["positions"]) * 0.25 + np.array([-1 + 0.25 * k, -0.2 + 0.05 * k, 0])
+        objs.append(dict(kind="mesh", material=k % 2, **g))
+    mats = [{"kind": "diffuse", "color1": (0.7, 0.7, 0.6)}, {"kind": "plastic", "ior": 1.5, "color1": (0.4, 0.6, 0.8)}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0, 0.5, -3), "target": (0, 0, 1)})
+    img, _ = both(rs, 120, 90)
+    assert img.stats["shadow_split"] == 0
