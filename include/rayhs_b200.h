@@ -241,7 +241,10 @@ enum {
    * first two large frames of a scene and keeps the faster one for that scene. */
   RH_FLAG_SHADOW_POOLED = 64, /* one kernel per pass, tree walks in warp-local rounds of 32 (coherent rays)   */
   RH_FLAG_SHADOW_SPLIT = 128, /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
-  RH_FLAG_PEER_FRAMES = 256   /* store the finished rows into rh_render_opts.peer_frames (see there) */
+  RH_FLAG_PEER_FRAMES = 256,  /* store the finished rows into rh_render_opts.peer_frames (see there) */
+  /* Closest-hit schedule, chosen and timed per scene like the shadow schedule (same image either way). */
+  RH_FLAG_TRACE_FUSED = 512,  /* one kernel per pass: closest hit + shade, 32 items per warp in lock step (coherent rays) */
+  RH_FLAG_TRACE_SPLIT = 1024  /* intersect (per-lane refill) -> shade from hit records (incoherent rays)           */
 };
 
 /* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
@@ -279,7 +282,7 @@ typedef struct rh_stats {
   uint32_t negative_channels; /* pixels with a channel whose toIntC is < 0 before the RGB8 clamp (App. A-Q2) */
   uint32_t queue_factor;      /* ray-queue capacity / chunk samples that was needed */
   uint32_t shadow_split;      /* 1: this frame used the split shadow schedule (RH_FLAG_SHADOW_SPLIT or auto)  */
-  uint32_t pad_;
+  uint32_t trace_split;       /* 1: ... the split closest-hit schedule (RH_FLAG_TRACE_SPLIT or auto)          */
 } rh_stats;
 
 typedef struct rh_scene rh_scene; /* opaque; owns device copies */

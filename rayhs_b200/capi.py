@@ -22,7 +22,7 @@ RH_LIGHT_DIRECTIONAL, RH_LIGHT_POINT = 0, 1
 RH_PROJ_ORTHOGRAPHIC, RH_PROJ_PERSPECTIVE = 0, 1
 RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64, RH_OFFSETS_SPLITMIX64 = 0, 1, 2, 3, 4
 RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE, RH_FLAG_EXACT_BOXES = 1, 2, 4, 8, 16, 32
-RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES = 64, 128, 256
+RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES, RH_FLAG_TRACE_FUSED, RH_FLAG_TRACE_SPLIT = 64, 128, 256, 512, 1024
 RH_NO_NODE = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -102,7 +102,7 @@ class rh_stats(C.Structure):
                 ("upload_bytes", C.c_uint64), ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_resolve", C.c_double), ("trace_launches", C.c_uint32), ("shadow_launches", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("negative_channels", C.c_uint32),
-                ("queue_factor", C.c_uint32), ("shadow_split", C.c_uint32), ("pad_", C.c_uint32)]
+                ("queue_factor", C.c_uint32), ("shadow_split", C.c_uint32), ("trace_split", C.c_uint32)]
 
     def rays_total(self) -> int:
         return self.rays_primary + self.rays_reflect + self.rays_probe + self.rays_exit + self.rays_shadow

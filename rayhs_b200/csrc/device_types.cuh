@@ -151,6 +151,7 @@ struct ChunkCtl {
   // split shadow pipeline: low word = deferred hits, high word = (hit, light) pairs queued for a tree walk
   unsigned long long deferred_walk_count[kMaxPasses + 2];
   uint32_t walk_cursor[kMaxPasses + 2];
+  uint32_t isect_cursor[kMaxPasses + 2];  // split trace schedule: intersect_kernel's work cursor
   uint32_t overflow;
   uint32_t pad_[3];
 };
@@ -220,10 +221,12 @@ struct ChunkParams {
   uint8_t* pair_flags;    // [item * n_lights + light]: 1 = the pair adds nothing (l.n <= 0 or occluded)
   uint32_t walk_capacity;
   uint32_t pad3_;
+  double4* hits;          // split trace schedule: (t, u, v, slot | obj << 32) per work item of the pass
 };
 
 // Launchers (kernels.cu).  `count` selects the instrumented instantiation (box/tri counters).
-void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
+// split: intersect_kernel (closest hits with per-lane refill -> P.hits) then trace_kernel<.., true> (shade from the records)
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, bool split, int grid, void* stream);
 // split: classify -> walk -> fold (3 launches) instead of one pooled kernel; only when shadow_split_possible(S)
 void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream);
 bool shadow_split_possible(const SceneView& S);

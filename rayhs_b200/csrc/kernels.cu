@@ -234,7 +234,9 @@ struct Closest {
     return mine.y > held.y || (mine.y == held.y && mine.x < held.x);
   }
   __device__ __forceinline__ bool offer(const Ray&, double tt, double uu, double vv, uint32_t s, double& bound) {
-    if (tt < t || (tt == t && obj == cur_obj && wins_tie(s))) {
+    // (cur_obj < obj only happens when objects are not visited in scene order — intersect_kernel tests the planes and
+    // spheres before the meshes: the first object of the scene list wins a tie, RayHs.hs:67-71)
+    if (tt < t || (tt == t && (cur_obj < obj || (obj == cur_obj && wins_tie(s))))) {
       t = tt;
       u = uu;
       v = vv;
@@ -872,8 +874,59 @@ __device__ __forceinline__ double splitmix01(unsigned long long seed, unsigned l
   return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// Work item -> ray: the camera ray of a pixel sample (pass 0: pixelCoord, Image.hs:31-32, + sample offset,
+// RayHs.hs:178-181) or a queued secondary ray with its weight and tags.  False for a padding row of the last band.
+__device__ __forceinline__ bool load_item(const ChunkParams& P, const CameraParams& cam, uint32_t item, bool primary, Ray& r,
+                                          double& w, uint32_t& sample, int& depth, int& kind, uint32_t& probe_mat) {
+  r.o = r.d = mk(0, 0, 1);
+  if (primary) {
+    const uint32_t lp = item / P.spp, s = item - lp * P.spp;
+    const uint32_t lrow = lp / P.width, col = lp - lrow * P.width;
+    const uint32_t grow = global_row(P, P.first_row + lrow);
+    if (grow >= P.height) return false;
+    double ox = 0, oy = 0;
+    if (P.offset_mode == RH_OFFSETS_SPLITMIX64) {
+      // values 2g and 2g+1 of the stream rh_sample_offsets_f64(seed, ...) writes (x before y, RayHs.hs:185-188)
+      const unsigned long long g = ((unsigned long long)grow * P.width + col) * P.spp + s;
+      ox = splitmix01(P.offset_seed, 2 * g) - 0.5;
+      oy = splitmix01(P.offset_seed, 2 * g + 1) - 0.5;
+    } else if (P.offset_mode != RH_OFFSETS_NONE) {
+      size_t idx;
+      if (P.offset_mode == RH_OFFSETS_TILED_F64)
+        idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
+      else if (P.offset_index == kOffIndexGlobal)
+        idx = ((size_t)grow * P.width + col) * P.spp + s;
+      else
+        idx = item;
+      if (P.offset_mode == RH_OFFSETS_F32) {
+        const float2 o2 = __ldg((const float2*)P.offsets + idx);
+        ox = (double)o2.x;
+        oy = (double)o2.y;
+      } else {
+        const double2 o2 = __ldg((const double2*)P.offsets + idx);
+        ox = o2.x;
+        oy = o2.y;
+      }
+    }
+    r = camera_ray(cam, (double)col + ox, (double)grow + oy);
+    return true;
+  }
+  const size_t cap = P.q_in.capacity;
+  const double2 a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item], d = P.q_in.plane[3 * cap + item];
+  r.o = mk(a.x, a.y, b.x);
+  r.d = mk(b.y, c.x, c.y);
+  w = d.x;
+  const uint64_t bits = (uint64_t)__double_as_longlong(d.y);
+  sample = (uint32_t)bits;
+  depth = (int)((bits >> 32) & 0xff);
+  kind = (int)((bits >> 40) & 0xff);
+  probe_mat = (uint32_t)((bits >> 48) & 0x7fff);
+  return true;
+}
+
 // ------------------------------------------------------------------ K1/K2/K4/K5
-template <bool COUNT>
+// HITS: the closest hits were found by intersect_kernel (split schedule) and are read from P.hits.
+template <bool COUNT, bool HITS = false>
 __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(const __grid_constant__ SceneView S,
                                                        const __grid_constant__ CameraParams cam,
                                                        const __grid_constant__ ChunkParams P) {
@@ -897,63 +950,26 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(con
     const uint32_t item = base + lane;
     bool valid = item < n_items;
     Ray r;
-    r.o = r.d = mk(0, 0, 1);
     double w = 1;
     uint32_t sample = item, probe_mat = 0;
     int depth = 0, kind = kRayNormal;
-    if (valid) {
-      if (primary) {
-        const uint32_t lp = item / P.spp, s = item - lp * P.spp;
-        const uint32_t lrow = lp / P.width, col = lp - lrow * P.width;
-        const uint32_t grow = global_row(P, P.first_row + lrow);
-        if (grow >= P.height) {
-          valid = false;  // padding row of the last band
-        } else {
-          double ox = 0, oy = 0;
-          if (P.offset_mode == RH_OFFSETS_SPLITMIX64) {
-            // values 2g and 2g+1 of the stream rh_sample_offsets_f64(seed, ...) writes (x before y, RayHs.hs:185-188)
-            const unsigned long long g = ((unsigned long long)grow * P.width + col) * P.spp + s;
-            ox = splitmix01(P.offset_seed, 2 * g) - 0.5;
-            oy = splitmix01(P.offset_seed, 2 * g + 1) - 0.5;
-          } else if (P.offset_mode != RH_OFFSETS_NONE) {
-            size_t idx;
-            if (P.offset_mode == RH_OFFSETS_TILED_F64)
-              idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
-            else if (P.offset_index == kOffIndexGlobal)
-              idx = ((size_t)grow * P.width + col) * P.spp + s;
-            else
-              idx = item;
-            if (P.offset_mode == RH_OFFSETS_F32) {
-              const float2 o2 = __ldg((const float2*)P.offsets + idx);
-              ox = (double)o2.x;
-              oy = (double)o2.y;
-            } else {
-              const double2 o2 = __ldg((const double2*)P.offsets + idx);
-              ox = o2.x;
-              oy = o2.y;
-            }
-          }
-          // pixelCoord (Image.hs:31-32) + sample offset (RayHs.hs:178-181)
-          r = camera_ray(cam, (double)col + ox, (double)grow + oy);
-        }
-      } else {
-        const size_t cap = P.q_in.capacity;
-        const double2 a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item],
-                      d = P.q_in.plane[3 * cap + item];
-        r.o = mk(a.x, a.y, b.x);
-        r.d = mk(b.y, c.x, c.y);
-        w = d.x;
-        const uint64_t bits = (uint64_t)__double_as_longlong(d.y);
-        sample = (uint32_t)bits;
-        depth = (int)((bits >> 32) & 0xff);
-        kind = (int)((bits >> 40) & 0xff);
-        probe_mat = (uint32_t)((bits >> 48) & 0x7fff);
-      }
-    }
+    if (valid) valid = load_item(P, cam, item, primary, r, w, sample, depth, kind, probe_mat);
+    else r.o = r.d = mk(0, 0, 1);
 
     Closest best;
     best.obj = -1;
-    if (valid) {
+    if constexpr (HITS) {
+      if (valid) {
+        const double4 h = P.hits[item];  // (t, u, v, slot | obj)
+        const unsigned long long so = (unsigned long long)__double_as_longlong(h.w);
+        best.t = h.x;
+        best.u = h.y;
+        best.v = h.z;
+        best.slot = (uint32_t)so;
+        best.obj = (int)(uint32_t)(so >> 32);
+        best.tris = S.tris;
+      }
+    } else if (valid) {
       const bool exact = P.exact_boxes || needs_exact_walk(r, S);
       unsigned long long nodes_before = 0;
       if constexpr (COUNT) nodes_before = cnt.nodes;
@@ -2077,6 +2093,219 @@ __global__ void __launch_bounds__(kClassifyBlock) shadow_fold_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------ K1/K4 split: intersect -> shade
+// The closest-hit search of trace_kernel with the walk kernel's per-lane refill: a lane whose ray has finished writes
+// its hit record and takes the next work item while its neighbours keep walking.  Incoherent rays (reflections, the
+// synthetic triangle soup: 5-9 active threads per instruction in trace_kernel's walks) keep the warp busy this way;
+// trace_kernel<COUNT, true> then shades from the records with no tree code in it.  Meshes are walked in scene order
+// (their roots are stacked in reverse), planes and linear spheres are tested when the item is taken; ties between
+// objects go to the lower object index (Closest::offer), within a mesh to the reference's key.
+constexpr int kIsectBlock = RH_WALK_BLOCK;
+constexpr size_t kIsectSmem = sizeof(SmemTables) + 10 * kIsectBlock * sizeof(double);
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kIsectBlock, 1) intersect_kernel(const __grid_constant__ SceneView S,
+                                                                   const __grid_constant__ CameraParams cam,
+                                                                   const __grid_constant__ ChunkParams P) {
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  // per-thread columns: 0-2 origin, 3-5 direction, 6 best t, 7 u, 8 v, 9 slot | obj << 32
+  double* lane_mem = reinterpret_cast<double*>(rh_smem + sizeof(SmemTables)) + threadIdx.x;
+  auto lane_slot = [&](int k) -> double& { return lane_mem[k * kIsectBlock]; };
+  uint4 stack[kStack];
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  const uint32_t lane = threadIdx.x & 31;
+  const bool primary = (P.pass == 0);
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_items = primary ? P.n_samples : min(ctl->ray_count[P.pass], P.q_in.capacity);
+  const uint32_t n_smem = S.n_smem_nodes, n_lin = S.n_lin, sphere_root = S.sphere_root;
+  const rh_tri* tris = S.tris;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+
+  uint32_t pos = 0, end = 0;
+  bool exhausted = false;
+  bool active = false;
+  RayF f;
+  f.ix = f.iy = f.iz = f.pix = f.piy = f.piz = f.mix = f.miy = f.miz = 0.f;
+  float fb = 0;  // float upper bound of best t * slack
+  uint32_t ref = 0, first = 0, item = 0;
+  int sp = 0, cur_obj = -1;
+
+  auto write_record = [&](uint32_t it, double t, double u, double v, uint32_t slot, int obj) {
+    P.hits[it] = make_double4(t, u, v, __longlong_as_double((long long)(((unsigned long long)(uint32_t)obj << 32) | slot)));
+  };
+  auto finish = [&]() {
+    const unsigned long long so = (unsigned long long)__double_as_longlong(lane_slot(9));
+    write_record(item, lane_slot(6), lane_slot(7), lane_slot(8), (uint32_t)so, (int)(uint32_t)(so >> 32));
+    active = false;
+  };
+  auto pop_next = [&]() {  // next stacked subtree the bound does not prune, or the ray is done
+    for (;;) {
+      if (sp == 0) {
+        finish();
+        return;
+      }
+      const uint4 e = stack[--sp];
+      if (__uint_as_float(e.z) > fb) continue;
+      ref = e.x;
+      first = e.y;
+      if (e.w) cur_obj = (int)e.w - 1;  // a mesh's super-root: hits below it belong to this object
+      return;
+    }
+  };
+
+  for (;;) {
+    // ---- refill
+    const unsigned idle = __ballot_sync(kFull, !active);
+    const uint32_t n_idle = __popc(idle);
+    if (n_idle >= kRefillMin) {
+      if (pos == end && !exhausted) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&ctl->isect_cursor[P.pass], kWalkChunk);
+        b = __shfl_sync(kFull, b, 0);
+        if (b >= n_items) exhausted = true;
+        else {
+          pos = b;
+          end = min(b + kWalkChunk, n_items);
+        }
+      }
+      if (pos < end) {
+        const uint32_t take = min(n_idle, end - pos);
+        const uint32_t rank = __popc(idle & ((1u << lane) - 1));
+        if (!active && rank < take) {
+          item = pos + rank;
+          Ray r;
+          double w = 1;
+          uint32_t sample = 0, probe_mat = 0;
+          int depth = 0, kind = 0;
+          if (!load_item(P, cam, item, primary, r, w, sample, depth, kind, probe_mat)) {
+            write_record(item, kInf, 0, 0, 0, -1);  // padding row
+          } else if (P.exact_boxes || needs_exact_walk(r, S)) {
+            // rare (far origins): the whole search with the reference's double boxes, right here
+            Closest best;
+            if constexpr (COUNT) atomicAdd(&P.counters->exact_closest, 1ull);
+            closest_hit<COUNT>(cx, r, true, best, stack, cnt);
+            write_record(item, best.t, best.u, best.v, best.slot, best.obj);
+          } else {
+            // planes and linear spheres (Geometry.hs:68-96) now; mesh roots on the stack, first mesh on top
+            double bt = kInf;
+            int bobj = -1;
+            sp = 0;
+            if (sphere_root != kEmpty) stack[sp++] = make_uint4(sphere_root, 0, 0, 0);
+            for (uint32_t k = n_lin; k-- > 0;) {
+              const uint32_t i = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
+              const DObject& ob = cx.objects[i];
+              if (ob.kind == RH_OBJ_MESH && ob.root != kEmpty) stack[sp++] = make_uint4(ob.root, 0, 0, i + 1);
+            }
+            for (uint32_t k = 0; k < n_lin; k++) {
+              const uint32_t i = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
+              const DObject& ob = cx.objects[i];
+              const int okind = ob.kind;
+              if (okind == RH_OBJ_MESH) continue;
+              double time;
+              RH_CNT(prim, 1);
+              const bool hit = (okind == RH_OBJ_PLANE) ? plane_time(r, ob, bt, time) : sphere_time(r, ob, time);
+              if (hit && time < bt) {
+                bt = time;
+                bobj = (int)i;
+              }
+            }
+            lane_slot(0) = r.o.x; lane_slot(1) = r.o.y; lane_slot(2) = r.o.z;
+            lane_slot(3) = r.d.x; lane_slot(4) = r.d.y; lane_slot(5) = r.d.z;
+            lane_slot(6) = bt;
+            lane_slot(7) = 0;
+            lane_slot(8) = 0;
+            lane_slot(9) = __longlong_as_double((long long)((unsigned long long)(uint32_t)bobj << 32));
+            f = make_rayf(r, S);
+            fb = __double2float_ru(bt * kPruneSlack);
+            cur_obj = -1;
+            active = true;
+            pop_next();  // (no tree at all: writes the record)
+          }
+        }
+        pos += take;
+      } else if (n_idle == 32) {
+        break;
+      }
+    }
+    // ---- inner nodes (KDTree.hs:96-107, ordered and pruned, conservative float boxes); two steps per vote
+    auto node_step = [&]() {
+      const float4* np = ref < n_smem ? (const float4*)&sm.nodes[ref] : (const float4*)&S.wide32[ref];
+      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
+      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
+      RH_CNT(nodes, 1);
+      bool h0 = false, h1 = false;
+      float tm0 = 0, tm1 = 0;
+      if (cw.x != kEmpty) {
+        RH_CNT(box, 1);
+        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > fb);
+      }
+      if (cw.y != kEmpty) {
+        RH_CNT(box, 1);
+        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > fb);
+      }
+      if (h0 && h1) {
+        if (tm1 < tm0) {
+          stack[sp++] = make_uint4(cw.x, cw.z, __float_as_uint(tm0), 0);
+          ref = cw.y;
+          first = cw.w;
+        } else {
+          stack[sp++] = make_uint4(cw.y, cw.w, __float_as_uint(tm1), 0);
+          ref = cw.x;
+          first = cw.z;
+        }
+      } else if (h0) {
+        ref = cw.x;
+        first = cw.z;
+      } else if (h1) {
+        ref = cw.y;
+        first = cw.w;
+      } else {
+        pop_next();
+      }
+    };
+    for (;;) {
+      bool inner = active && !(ref & kLeafBit);
+      if (!__any_sync(kFull, inner)) break;
+      if (inner) node_step();
+      inner = active && !(ref & kLeafBit);
+      if (inner) node_step();
+    }
+    // ---- leaves
+    if (active) {
+      Ray r;
+      r.o = mk(lane_slot(0), lane_slot(1), lane_slot(2));
+      r.d = mk(lane_slot(3), lane_slot(4), lane_slot(5));
+      Closest best;
+      const unsigned long long so = (unsigned long long)__double_as_longlong(lane_slot(9));
+      best.t = lane_slot(6);
+      best.u = lane_slot(7);
+      best.v = lane_slot(8);
+      best.slot = (uint32_t)so;
+      best.obj = (int)(uint32_t)(so >> 32);
+      best.cur_obj = cur_obj;
+      best.tris = tris;
+      const double t_before = best.t;
+      const uint32_t slot_before = best.slot;
+      const int obj_before = best.obj;
+      double bound = best.t * kPruneSlack;
+      if (ref & kSphereLeafBit) test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, best, bound, false, cnt);
+      else test_leaf<COUNT>(tris, first, ref & kCountMask, r, best, bound, cnt);
+      if (best.t != t_before || best.slot != slot_before || best.obj != obj_before) {
+        lane_slot(6) = best.t;
+        lane_slot(7) = best.u;
+        lane_slot(8) = best.v;
+        lane_slot(9) = __longlong_as_double((long long)(((unsigned long long)(uint32_t)best.obj << 32) | best.slot));
+        fb = __double2float_ru(best.t * kPruneSlack);
+      }
+      pop_next();
+    }
+  }
+  flush_counters<COUNT>(cnt, P.counters, 0);
+}
+
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
 __device__ __forceinline__ int to_int_c(double c, bool& negative) {
   const double v = 255 * hs_min(c, 1);  // hs_min NaN 1 = 1
@@ -2228,6 +2457,10 @@ int configure_kernels() {
   };
   set((const void*)trace_kernel<true>, kTraceSmem);
   set((const void*)trace_kernel<false>, kTraceSmem);
+  set((const void*)trace_kernel<true, true>, kTraceSmem);
+  set((const void*)trace_kernel<false, true>, kTraceSmem);
+  set((const void*)intersect_kernel<true>, kIsectSmem);
+  set((const void*)intersect_kernel<false>, kIsectSmem);
   set((const void*)shadow_kernel<true>, kShadowSmem);
   set((const void*)shadow_kernel<false>, kShadowSmem);
   set((const void*)shadow_kernel_fast<true>, kShadowFastSmem);
@@ -2248,11 +2481,21 @@ int configure_kernels() {
   }
   return (int)e;
 }
-void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
-  if (count)
-    trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, (cudaStream_t)stream>>>(S, cam, P);
-  else
-    trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, (cudaStream_t)stream>>>(S, cam, P);
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, bool split, int grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (split) {  // intersect (per-lane refill) -> shade from the hit records
+    if (count) {
+      intersect_kernel<true><<<g_walk_grid, kIsectBlock, kIsectSmem, st>>>(S, cam, P);
+      trace_kernel<true, true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+    } else {
+      intersect_kernel<false><<<g_walk_grid, kIsectBlock, kIsectSmem, st>>>(S, cam, P);
+      trace_kernel<false, true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+    }
+  } else if (count) {
+    trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  } else {
+    trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  }
 }
 void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream) {
   const bool simple = S.n_lights > 32 || RH_SHADOW_POOL == 0;

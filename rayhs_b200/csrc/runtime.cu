@@ -84,7 +84,7 @@ struct Device {
   std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
   // per-lane scratch: a chunk's accumulators and queues
   struct Scratch {
-    DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags;
+    DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, hits;
   } lane[2];
   DevBuf ctl, counters, offsets, rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
@@ -119,7 +119,7 @@ struct Device {
     if (dev < 0) return;
     cudaSetDevice(dev);
     for (Scratch& sc : lane)
-      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.shq, &sc.shq_sample, &sc.walk_q, &sc.deferred_q, &sc.pair_flags})
+      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.shq, &sc.shq_sample, &sc.walk_q, &sc.deferred_q, &sc.pair_flags, &sc.hits})
         b->release();
     for (DevBuf* b : {&ctl, &counters, &offsets, &rgb, &ids})
       b->release();
@@ -155,8 +155,10 @@ struct rh_scene {
   uint32_t max_tree_depth = 0;
   // shadow schedule chosen for this scene: 0 = undecided (frame 1 runs pooled, frame 2 split, both timed), 1 = pooled, 2 = split
   mutable int shadow_mode = 0;
+  mutable int trace_mode = 0;  // closest-hit schedule, same convention: 1 = fused, 2 = split
   mutable int tune_frames = 0;
   mutable double tune_ns_per_task[2] = {0, 0};
+  mutable double tune_ns_per_ray[2] = {0, 0};
   // Per-chunk kernel time of the last frame that streamed its sample offsets from the host (key: the chunk plan).
   // The next such frame processes its chunks in descending cost per sample, so that the uploads of the cheap chunks
   // hide behind the kernels of the expensive ones instead of the other way round.
@@ -851,16 +853,21 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const bool dev_out = (o->flags & RH_FLAG_DEVICE_OUT) != 0;
   const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
   const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
-  // shadow schedule: forced by a flag, else the scene's choice, else this is a timing frame of the choice
+  // Shadow and closest-hit schedules: forced by flags, else the scene's measured choice, else this is one of the two
+  // timing frames of a scene (frame 1: pooled + fused, frame 2: split + split; both kernels' times compared per unit).
   const bool split_ok = shadow_split_possible(scene->view);
-  bool use_split = false, tuning = false;
+  const bool forced = (o->flags & (RH_FLAG_SHADOW_POOLED | RH_FLAG_SHADOW_SPLIT | RH_FLAG_TRACE_FUSED | RH_FLAG_TRACE_SPLIT)) != 0;
+  const bool decided = scene->tune_frames >= 2;
+  const bool tuning = !forced && !decided && !(o->flags & RH_FLAG_COUNT);
+  bool use_split = false, use_split_trace = false;
   if (o->flags & RH_FLAG_SHADOW_SPLIT) use_split = split_ok;
   else if (o->flags & RH_FLAG_SHADOW_POOLED) use_split = false;
-  else if (split_ok && scene->shadow_mode != 0) use_split = scene->shadow_mode == 2;
-  else if (split_ok && !(o->flags & RH_FLAG_COUNT)) {
-    tuning = true;
-    use_split = scene->tune_frames == 1;
-  }
+  else if (decided) use_split = split_ok && scene->shadow_mode == 2;
+  else if (tuning) use_split = split_ok && scene->tune_frames == 1;
+  if (o->flags & RH_FLAG_TRACE_SPLIT) use_split_trace = true;
+  else if (o->flags & RH_FLAG_TRACE_FUSED) use_split_trace = false;
+  else if (decided) use_split_trace = scene->trace_mode == 2;
+  else if (tuning) use_split_trace = scene->tune_frames == 1;
   const bool profile = (o->flags & RH_FLAG_PROFILE) != 0 || tuning;
   const bool exact_boxes = (o->flags & RH_FLAG_EXACT_BOXES) != 0;
 
@@ -882,7 +889,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     size_t want = (size_t)o->chunk_samples, first = want;
     if (o->chunk_samples <= 0) {
       const size_t L = std::max<uint32_t>(1, scene->view.n_lights);
-      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4 + 4 + L * (sizeof(uint2) + 1));
+      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4 + 4 + sizeof(double4) + L * (sizeof(uint2) + 1));
       want = std::min<size_t>((size_t)(0.4 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
       if (host_offsets) want = std::min<size_t>(want, (size_t)RH_STREAM_CHUNK_MI << 20);
       first = host_offsets ? std::min<size_t>(want, (size_t)RH_STREAM_FIRST_MI << 20) : want;
@@ -981,6 +988,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         if ((rc = sc.rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
       if ((rc = sc.shq.reserve(cap * 5 * sizeof(double2)))) return rc;
       if ((rc = sc.shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
+      if (use_split_trace && (rc = sc.hits.reserve(cap * sizeof(double4)))) return rc;
       if (split) {
         if ((rc = sc.walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
         if ((rc = sc.deferred_q.reserve(cap * sizeof(uint32_t)))) return rc;
@@ -1065,6 +1073,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.walk_q = (uint2*)sc.walk_q.p;
       P.deferred_q = (uint32_t*)sc.deferred_q.p;
       P.pair_flags = (uint8_t*)sc.pair_flags.p;
+      P.hits = (double4*)sc.hits.p;
       P.walk_capacity = (uint32_t)walk_cap;
 
       if (stream_offsets) {
@@ -1102,11 +1111,11 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         P.q_out.capacity = (uint32_t)cap;  // (the last pass cannot emit: every ray in it has depth == maxDepth)
         cudaEvent_t a = nullptr;
         if (profile) a = prof_event();
-        launch_trace(scene->view, cam, P, counting, D->grid_trace[counting], lane_stream);
+        launch_trace(scene->view, cam, P, counting, use_split_trace, D->grid_trace[counting], lane_stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
         launch_shadow(scene->view, P, counting, use_split, D->grid_shadow[counting], lane_stream);
         if (profile) spans.push_back({a, prof_event(), 1});
-        launches += 1 + (use_split ? 3 : 1);
+        launches += (use_split_trace ? 2 : 1) + (use_split ? 3 : 1);
       }
       cudaEvent_t a = nullptr;
       if (profile) a = prof_event();
@@ -1195,6 +1204,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->negative_channels = (uint32_t)std::min<unsigned long long>(fc->negative_channels, 0xffffffffu);
       stats->queue_factor = factor;
       stats->shadow_split = use_split ? 1 : 0;
+      stats->trace_split = use_split_trace ? 1 : 0;
     }
     if (stream_offsets && (int)chunk_ev.size() == 2 * n_chunks) {
       scene->chunk_ms.assign(n_chunks, 0.f);
@@ -1204,20 +1214,26 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     if (tuning) {
       // only frames with enough shadow work to time say anything (1 M shaded hits ~ 0.3 ms)
       const ChunkCtl* c2 = (const ChunkCtl*)D->pinned;
-      uint64_t tasks = 0;
-      double ms = 0;
+      uint64_t tasks = 0, rays = (uint64_t)rows_local * row_samples;
+      double ms = 0, ms_trace = 0;
       for (int ck = 0; ck < n_chunks; ck++)
-        for (int p = 0; p < n_passes; p++) tasks += c2[ck].shadow_count[p];
-      for (const Span& sp : spans)
-        if (sp.kind == 1) {
-          float m = 0;
-          cudaEventElapsedTime(&m, sp.a, sp.b);
-          ms += m;
+        for (int p = 0; p < n_passes; p++) {
+          tasks += c2[ck].shadow_count[p];
+          if (p > 0) rays += std::min<uint64_t>(c2[ck].ray_count[p], cap);
         }
+      for (const Span& sp : spans) {
+        float m = 0;
+        cudaEventElapsedTime(&m, sp.a, sp.b);
+        if (sp.kind == 1) ms += m;
+        if (sp.kind == 0) ms_trace += m;
+      }
       if (tasks >= (1u << 20)) {
         scene->tune_ns_per_task[scene->tune_frames] = ms * 1e6 / (double)tasks;
-        if (++scene->tune_frames == 2)
+        scene->tune_ns_per_ray[scene->tune_frames] = ms_trace * 1e6 / (double)rays;
+        if (++scene->tune_frames == 2) {
           scene->shadow_mode = scene->tune_ns_per_task[1] < scene->tune_ns_per_task[0] ? 2 : 1;
+          scene->trace_mode = scene->tune_ns_per_ray[1] < scene->tune_ns_per_ray[0] ? 2 : 1;
+        }
       }
     }
     return RH_OK;

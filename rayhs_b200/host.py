@@ -207,9 +207,12 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
 
 
 def _shadow_flag(shadow: str | None) -> int:
-    """Shadow-ray schedule: None = the library's per-scene choice, 'pooled' / 'split' = forced (same image)."""
+    """Shadow-ray schedule: None = the library's per-scene choice, 'pooled' / 'split' = forced (same image); a pair
+    (shadow, trace) also forces the closest-hit schedule: 'fused' / 'split' / None."""
     if shadow is None:
         return 0
+    if isinstance(shadow, (tuple, list)):   # (shadow schedule, closest-hit schedule)
+        return _shadow_flag(shadow[0]) | {None: 0, "fused": capi.RH_FLAG_TRACE_FUSED, "split": capi.RH_FLAG_TRACE_SPLIT}[shadow[1]]
     return {"pooled": capi.RH_FLAG_SHADOW_POOLED, "split": capi.RH_FLAG_SHADOW_SPLIT}[shadow]
 
 

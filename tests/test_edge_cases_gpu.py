@@ -15,9 +15,12 @@ def both(rs, w, h, depth=None, spp=1, offsets=None, **kw):
     depth = rs.max_depth if depth is None else depth
     job = rh.Rendering(rs, rs.camera, w, h, depth)
     img = rh.render(job, spp=spp, offsets=offsets, want_hit_ids=True, shadow="pooled", **kw)
-    img_split = rh.render(job, spp=spp, offsets=offsets, shadow="split", **kw)
+    img_split = rh.render(job, spp=spp, offsets=offsets, want_hit_ids=True, shadow=("split", "split"), **kw)
+    assert np.array_equal(img.hit_ids, img_split.hit_ids), "hit ids, fused vs split closest-hit schedule"
     d = np.abs(img.pixels.astype(np.int32) - img_split.pixels.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3, "pooled vs split schedule"   # (Transparent forks: atomic order)
+    for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow"):
+        assert img.stats[k] == img_split.stats[k], k
     ref = OracleScene(rs.raw).render(rs.camera, w, h, depth, spp=spp, offsets=offsets)
     assert np.array_equal(img.hit_ids.reshape(h, w, spp, 2), ref["hit_ids"]), "hit ids"
     assert_parity(img.pixels, ref["rgb_u8"])

@@ -11,16 +11,18 @@ RES = {"cornellBox": (256, 256), "texture": (320, 180), "transform": (320, 180),
        "dragon_low": (320, 180), "dragon_full": (320, 180), "outScene": (320, 180)}
 
 
-@pytest.mark.parametrize("shadow", ["pooled", "split"])
+@pytest.mark.parametrize("shadow", [("pooled", "fused"), ("split", "split")])
 @pytest.mark.parametrize("name", SCENES)
 def test_one_sample_parity(name, shadow):
-    """rayTrace (RayHs.hs:161-166): hit ids bit-exact, image within tolerance, ray counts equal — with either
-    shadow-ray schedule (one pooled kernel per pass, or classify -> walk -> fold)."""
+    """rayTrace (RayHs.hs:161-166): hit ids bit-exact, image within tolerance, ray counts equal — with either schedule
+    of the shadow rays (one pooled kernel per pass, or classify -> walk -> fold) and of the closest-hit search (fused
+    with the shading, or intersect with per-lane refill -> shade)."""
     sc = load_scene(name)
     w, h = RES[name]
     job = rh.renderingFromScene(sc, w, h)
     img = rh.render(job, want_hit_ids=True, shadow=shadow)
-    assert img.stats["shadow_split"] == (1 if shadow == "split" else 0)
+    assert img.stats["shadow_split"] == (1 if shadow[0] == "split" else 0)
+    assert img.stats["trace_split"] == (1 if shadow[1] == "split" else 0)
     ref = oracle_for(sc).render(sc.camera, w, h, sc.max_depth)
     ids_gpu = img.hit_ids.reshape(h, w, 2)
     ids_ref = ref["hit_ids"].reshape(h, w, 2)
@@ -91,10 +93,10 @@ def test_shadow_schedule_is_chosen_per_scene_and_keeps_the_bytes():
     w, h = 1600, 900   # > 1 Mi shaded hits: counts as a timing frame
     job = rh.renderingFromScene(sc, w, h)
     frames = [rh.render(job) for _ in range(3)]
-    assert [f.stats["shadow_split"] for f in frames[:2]] == [0, 1]
+    assert [f.stats["shadow_split"] for f in frames[:2]] == [0, 1] and [f.stats["trace_split"] for f in frames[:2]] == [0, 1]
     assert np.array_equal(frames[0].pixels, frames[1].pixels) and np.array_equal(frames[0].pixels, frames[2].pixels)
-    forced = rh.render(job, shadow="split")
-    assert forced.stats["shadow_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
+    forced = rh.render(job, shadow=("split", "split"))
+    assert forced.stats["shadow_split"] == 1 and forced.stats["trace_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
 
 
 def test_offsets_regenerated_on_the_device_equal_the_uploaded_stream():
