@@ -238,7 +238,7 @@ enum {
   RH_FLAG_EXACT_BOXES = 32,  /* validation: the reference's double slab test at every box instead of the
                                 conservative float cull (same image) */
   /* Shadow-ray schedule (same image either way; DESIGN.md "Kernels").  Default: the library times both on the
-   * first two large frames of a scene and keeps the faster one for that scene. */
+   * first three large frames of a scene (warm-up, pooled, split) and keeps the faster one for that scene. */
   RH_FLAG_SHADOW_POOLED = 64, /* one kernel per pass, tree walks in warp-local rounds of 32 (coherent rays)   */
   RH_FLAG_SHADOW_SPLIT = 128, /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
   RH_FLAG_PEER_FRAMES = 256,  /* store the finished rows into rh_render_opts.peer_frames (see there) */

@@ -2100,7 +2100,7 @@ __global__ void __launch_bounds__(kClassifyBlock) shadow_fold_kernel(const __gri
 // trace_kernel<COUNT, true> then shades from the records with no tree code in it.  Meshes are walked in scene order
 // (their roots are stacked in reverse), planes and linear spheres are tested when the item is taken; ties between
 // objects go to the lower object index (Closest::offer), within a mesh to the reference's key.
-constexpr int kIsectBlock = RH_WALK_BLOCK;
+constexpr int kIsectBlock = RH_ISECT_BLOCK;
 constexpr size_t kIsectSmem = sizeof(SmemTables) + 10 * kIsectBlock * sizeof(double);
 
 template <bool COUNT>

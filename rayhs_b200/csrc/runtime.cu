@@ -153,7 +153,7 @@ struct rh_scene {
   DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index;
   SceneView view{};
   uint32_t max_tree_depth = 0;
-  // shadow schedule chosen for this scene: 0 = undecided (frame 1 runs pooled, frame 2 split, both timed), 1 = pooled, 2 = split
+  // shadow schedule chosen for this scene: 0 = undecided (timing frames, see render_on), 1 = pooled, 2 = split
   mutable int shadow_mode = 0;
   mutable int trace_mode = 0;  // closest-hit schedule, same convention: 1 = fused, 2 = split
   mutable int tune_frames = 0;
@@ -853,21 +853,22 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   const bool dev_out = (o->flags & RH_FLAG_DEVICE_OUT) != 0;
   const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
   const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
-  // Shadow and closest-hit schedules: forced by flags, else the scene's measured choice, else this is one of the two
-  // timing frames of a scene (frame 1: pooled + fused, frame 2: split + split; both kernels' times compared per unit).
+  // Shadow and closest-hit schedules: forced by flags, else the scene's measured choice, else this is one of the
+  // timing frames of a scene: frame 1 pooled + fused (not compared: first use of freshly allocated queues), frame 2 the
+  // same, frame 3 split + split; the kernels' times of frames 2 and 3 are compared per unit of work.
   const bool split_ok = shadow_split_possible(scene->view);
   const bool forced = (o->flags & (RH_FLAG_SHADOW_POOLED | RH_FLAG_SHADOW_SPLIT | RH_FLAG_TRACE_FUSED | RH_FLAG_TRACE_SPLIT)) != 0;
-  const bool decided = scene->tune_frames >= 2;
+  const bool decided = scene->tune_frames >= 3;
   const bool tuning = !forced && !decided && !(o->flags & RH_FLAG_COUNT);
   bool use_split = false, use_split_trace = false;
   if (o->flags & RH_FLAG_SHADOW_SPLIT) use_split = split_ok;
   else if (o->flags & RH_FLAG_SHADOW_POOLED) use_split = false;
   else if (decided) use_split = split_ok && scene->shadow_mode == 2;
-  else if (tuning) use_split = split_ok && scene->tune_frames == 1;
+  else if (tuning) use_split = split_ok && scene->tune_frames == 2;
   if (o->flags & RH_FLAG_TRACE_SPLIT) use_split_trace = true;
   else if (o->flags & RH_FLAG_TRACE_FUSED) use_split_trace = false;
   else if (decided) use_split_trace = scene->trace_mode == 2;
-  else if (tuning) use_split_trace = scene->tune_frames == 1;
+  else if (tuning) use_split_trace = scene->tune_frames == 2;
   const bool profile = (o->flags & RH_FLAG_PROFILE) != 0 || tuning;
   const bool exact_boxes = (o->flags & RH_FLAG_EXACT_BOXES) != 0;
 
@@ -1228,9 +1229,10 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         if (sp.kind == 0) ms_trace += m;
       }
       if (tasks >= (1u << 20)) {
-        scene->tune_ns_per_task[scene->tune_frames] = ms * 1e6 / (double)tasks;
-        scene->tune_ns_per_ray[scene->tune_frames] = ms_trace * 1e6 / (double)rays;
-        if (++scene->tune_frames == 2) {
+        const int slot = scene->tune_frames == 2 ? 1 : 0;
+        scene->tune_ns_per_task[slot] = ms * 1e6 / (double)tasks;
+        scene->tune_ns_per_ray[slot] = ms_trace * 1e6 / (double)rays;
+        if (++scene->tune_frames == 3) {
           scene->shadow_mode = scene->tune_ns_per_task[1] < scene->tune_ns_per_task[0] ? 2 : 1;
           scene->trace_mode = scene->tune_ns_per_ray[1] < scene->tune_ns_per_ray[0] ? 2 : 1;
         }
