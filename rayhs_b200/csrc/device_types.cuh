@@ -23,7 +23,7 @@ constexpr int kSmemLights = 16;
 constexpr int kBlock = 128;                // resolve kernel
 constexpr int kMaxPeers = 16;
 #ifndef RH_TRACE_BLOCK
-#define RH_TRACE_BLOCK 768
+#define RH_TRACE_BLOCK 1024
 #define RH_TRACE_MINB 1
 #define RH_SHADOW_BLOCK 768
 #define RH_SHADOW_MINB 1
@@ -52,7 +52,7 @@ constexpr int kMaxPeers = 16;
 #ifndef RH_SHADOW_FAST
 #define RH_SHADOW_FAST 1  // 0: always use the general pooled kernel (A/B and validation builds)
 #endif
-constexpr int kTraceBlock = RH_TRACE_BLOCK, kTraceMinBlocks = RH_TRACE_MINB;      // one 768-thread block per SM: 24 warps at <= 85 registers, tables staged once per SM (measured best, profiles/README.md)
+constexpr int kTraceBlock = RH_TRACE_BLOCK, kTraceMinBlocks = RH_TRACE_MINB;      // one block per SM, tables staged once per SM.  trace: 1024 threads at 64 registers (bench frame: equal to 768 at 80; incoherent synthetic scene: 57 vs 64 ms); shadow: 768 (measured best)
 constexpr int kShadowBlock = RH_SHADOW_BLOCK, kShadowMinBlocks = RH_SHADOW_MINB;
 
 // 128-byte "wide" node: one record per inner tree node holding BOTH child boxes, so a
