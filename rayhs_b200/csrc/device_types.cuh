@@ -28,6 +28,9 @@ constexpr int kMaxPeers = 16;
 #define RH_SHADOW_BLOCK 768
 #define RH_SHADOW_MINB 1
 #endif
+#ifndef RH_SHADOW_PAIRS
+#define RH_SHADOW_PAIRS 9  // (hit, light) pairs per lane whose terms the pooled fast shadow kernel keeps in shared memory: 3 hits per lane per batch with 3 lights (measured: 3 pairs 37.3 ms, 6 33.9, 9 33.7, 12 34.7 ms of shadow work per bench frame)
+#endif
 #ifndef RH_SHADOW_T
 #define RH_SHADOW_T 4   // shaded hits per lane per warp batch in the pooled shadow kernel
 #endif
