@@ -1327,6 +1327,7 @@ struct __align__(16) ShadowTables {
 };
 static_assert(sizeof(ShadowTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
 
+constexpr int kPairSlots = RH_SHADOW_PAIRS > kFastLights ? RH_SHADOW_PAIRS : kFastLights;  // one hit per lane always fits
 __device__ __forceinline__ int fast_shadow_T(uint32_t n_lights) {  // hits per lane per batch: 6 KB of pair terms per warp
   const int t = RH_SHADOW_PAIRS / (int)(n_lights ? n_lights : 1);
   return t < 1 ? 1 : (t > kShadowT ? kShadowT : t);
@@ -2442,7 +2443,7 @@ constexpr size_t kTraceSmem = sizeof(SmemTables);
 constexpr size_t kShadowSmem = sizeof(SmemTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem);
 // fast kernel: tables + per-warp vis/pool + per-warp pair terms (at most 32 * kShadowT * 3 pairs of 16 bytes)
 constexpr size_t kShadowFastSmem =
-    sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * RH_SHADOW_PAIRS * sizeof(double2));
+    sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * kPairSlots * sizeof(double2));
 static_assert(kShadowFastSmem <= 227 * 1024, "fast shadow kernel shared memory");
 
 constexpr size_t kWalkSmem = sizeof(ShadowTables) + 9 * kWalkBlock * sizeof(double);  // tables + per-thread ray columns

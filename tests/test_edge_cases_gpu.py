@@ -238,3 +238,16 @@ def test_scene_beyond_the_fast_shadow_tables_uses_the_general_pooled_kernel():
     rs = RawScene(objs, mats, lights, camera={"position": (0, 0.5, -3), "target": (0, 0, 1)})
     img, _ = both(rs, 120, 90)
     assert img.stats["shadow_split"] == 0
+
+
+def test_eleven_lights_fit_the_fast_shadow_kernels():
+    """11 lights: the most the fast shadow kernels take with one hit per lane per batch (pair terms in shared memory)."""
+    rng = np.random.RandomState(33)
+    lights = [{"kind": "point", "vec": tuple(rng.uniform(-1, 1, 3) * (1.5, 0.4, 1.5) + (0, 1.4, 0.2)), "color": (2.0, 1.8, 1.6),
+               "radius": 0.4} for _ in range(11)]
+    objs = [{"kind": "plane", "point": (0, -0.5, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 0},
+            dict(kind="mesh", material=1, **grid_mesh(10, z=0.8, wobble=0.2)),
+            {"kind": "sphere", "center": (-0.4, -0.1, 0.2), "radius": 0.35, "material": 1}]
+    mats = [{"kind": "diffuse", "color1": (0.8, 0.8, 0.7)}, {"kind": "plastic", "ior": 1.7, "color1": (0.5, 0.7, 0.4)}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0, 0.6, -3), "target": (0, 0, 0.5)})
+    both(rs, 150, 100)
