@@ -1103,7 +1103,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         chunk_ev.push_back(prof_event());  // after the wait: the span holds kernel time only
       }
 
-      RH_CUDA(cudaMemset2DAsync(sc.accum.p, chunk_samples * sizeof(double), 0, (size_t)P.n_samples * sizeof(double), 3, lane_stream));
+      for (int plane = 0; plane < 3; plane++)  // (three 1-D memsets: a 2-D one is limited to 2 GB of pitch)
+        RH_CUDA(cudaMemsetAsync((double*)sc.accum.p + (size_t)plane * chunk_samples, 0, (size_t)P.n_samples * sizeof(double), lane_stream));
       for (int pass = 0; pass < n_passes; pass++) {
         P.pass = pass;
         P.q_in.plane = (double2*)sc.rayq[(pass + 1) & 1].p;
