@@ -86,8 +86,9 @@ def main():
     lines = sass_lines(args.obj)
     # entry symbol: mangled name containing the kernel's short name and template argument
     short = re.search(r"(\w+)<", tab["name"]).group(1)
-    targ = "ILb1E" if "(bool)1" in tab["name"] else "ILb0E"
-    cands = [f for f in lines if short in f and (targ in f or "IL" not in f) and not f.startswith("$")]
+    bools = re.findall(r"\(bool\)([01])", tab["name"].split("(rhd::")[0])
+    targ = "I" + "".join(f"Lb{b}E" for b in bools) + "E" if bools else ""
+    cands = [f for f in lines if (short + targ) in f and not f.startswith("$")]
     if not cands:
         sys.exit("kernel symbol not found in object")
     entry = min(cands, key=len)
