@@ -244,7 +244,9 @@ enum {
   RH_FLAG_PEER_FRAMES = 256,  /* store the finished rows into rh_render_opts.peer_frames (see there) */
   /* Closest-hit schedule, chosen and timed per scene like the shadow schedule (same image either way). */
   RH_FLAG_TRACE_FUSED = 512,  /* one kernel per pass: closest hit + shade, 32 items per warp in lock step (coherent rays) */
-  RH_FLAG_TRACE_SPLIT = 1024  /* intersect (per-lane refill) -> shade from hit records (incoherent rays)           */
+  RH_FLAG_TRACE_SPLIT = 1024, /* intersect (per-lane refill) -> shade from hit records (incoherent rays)           */
+  RH_FLAG_NO_LIGHT_MAPS = 2048 /* validation / A-B: shadow rays ignore the per-light cube maps of nearest possible
+                                  occluder distance that rh_scene_create builds (same image; DESIGN.md "Light maps") */
 };
 
 /* Counts follow SURVEY 8d: one ray per closestIntersection (RayHs.hs:67) or
@@ -378,6 +380,17 @@ void rh_sample_offsets_f32(uint64_t seed, uint64_t n_pixels, int spp, float* out
 
 /* P3 writer byte-identical to Image.hs:60-75. */
 int rh_write_ppm(const char* path, const uint8_t* rgb, int width, int height);
+
+/* Validation hook (host only, no GPU): the cube map rh_scene_create builds for one point light and the triangles of
+ * one mesh — per cell a lower bound of the distance from the light to every triangle that covers a direction of the
+ * cell, +inf where none does.  The shadow kernels skip a mesh's tree walk when |p - L| is below the bound of the cell
+ * of p - L: no triangle found there could be in front of the light (inFrontOfLight, RayHs.hs:84-87).  The reference
+ * has no counterpart; the hook exists so that tests can check the map against brute-force shadow queries.
+ * out: 6 * res * res floats, face 2k + (v[k] < 0) of the largest |v[k]|, rows of `res` cells, cell coordinates
+ * (v[a], v[b]) / |v[k]| with (a, b) = (1,2), (0,2), (0,1) for k = 0, 1, 2.  *useful = 0 when the library would not
+ * use the map (a triangle touches the light, or almost no cell is empty). */
+int rh_light_map_build(const double light_pos[3], const rh_tri* tris, uint32_t n_tris, int res, float* out, int* useful,
+                       double* empty_fraction);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@ NVCC_FLAGS = [
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-unused-function"]
 
 CUDA_SOURCES = ["kernels.cu", "runtime.cu"]
-CXX_SOURCES = ["frontend.cpp", "host_build.cpp"]
+CXX_SOURCES = ["frontend.cpp", "host_build.cpp", "light_maps.cpp"]
 HEADERS = [os.path.join(CSRC, h) for h in ("device_types.cuh", "common.h")] + [os.path.join(ROOT, "include", "rayhs_b200.h")]
 
 

@@ -23,6 +23,7 @@ RH_PROJ_ORTHOGRAPHIC, RH_PROJ_PERSPECTIVE = 0, 1
 RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64, RH_OFFSETS_SPLITMIX64 = 0, 1, 2, 3, 4
 RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE, RH_FLAG_EXACT_BOXES = 1, 2, 4, 8, 16, 32
 RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES, RH_FLAG_TRACE_FUSED, RH_FLAG_TRACE_SPLIT = 64, 128, 256, 512, 1024
+RH_FLAG_NO_LIGHT_MAPS = 2048
 RH_NO_NODE = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -156,6 +157,8 @@ SIGNATURES = {
     "rh_sample_offsets_f64": (None, [C.c_uint64, C.c_uint64, C.c_int, vp]),
     "rh_sample_offsets_f32": (None, [C.c_uint64, C.c_uint64, C.c_int, vp]),
     "rh_write_ppm": (C.c_int, [C.c_char_p, vp, C.c_int, C.c_int]),
+    "rh_light_map_build": (C.c_int, [C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, C.c_int, vp, C.POINTER(C.c_int),
+                                     C.POINTER(C.c_double)]),
 }
 
 _lib = None

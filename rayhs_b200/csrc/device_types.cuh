@@ -134,8 +134,13 @@ struct SceneView {
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables
   float abs_max;            // largest |coordinate - center| of any tree box (pads the fp32 slab test)
-  uint32_t pad_;
+  uint32_t light_map_res;   // cells per edge of a cube-map face
   double center[3];         // the float boxes of wide32 are stored relative to this point
+  // Per (point light, occluder mesh) cube maps of the nearest possible occluder distance (light_maps.cpp): map k is
+  // light_maps[k * 6 * res * res ..], face-major; light_map_index[light * kOccMeshes + mesh] = k or kEmpty.
+  // Null when the scene has none (no point light, no mesh, maps useless or switched off).
+  const float* light_maps;
+  const uint32_t* light_map_index;
 };
 
 // Camera with everything `rayFromPixel` recomputes per pixel hoisted to the host
@@ -206,7 +211,7 @@ struct ChunkParams {
   int32_t offset_tile;
   int32_t pass;           // wavefront pass (0 = primary)
   int32_t exact_boxes;    // RH_FLAG_EXACT_BOXES: double slab test for every ray (validation)
-  int32_t pad2_;
+  int32_t no_light_maps;  // RH_FLAG_NO_LIGHT_MAPS: shadow rays ignore the lights' cube maps (validation, A/B)
   const void* offsets;    // device
   unsigned long long offset_seed;  // RH_OFFSETS_SPLITMIX64
   double* accum;          // 3 planes of accum_stride (r,g,b), chunk-local sample order

@@ -217,6 +217,41 @@ __device__ __forceinline__ bool slab32(const RayF& f, float lx, float ly, float 
   return !(tmax < 0.0f || tmin > tmax);
 }
 
+// Cell of the cube maps around a point light (light_maps.cpp) for the direction of p - L, in float: the maps are
+// marked one cell beyond every triangle, far more than the ~1e-6 of a face these roundings can move a direction.
+// Face 2k + (v[k] < 0) for the largest |v[k]|, coordinates (v[a], v[b]) / |v[k]| with (a, b) = (1,2), (0,2), (0,1).
+// kEmpty when p is (nearly) the light itself or not finite: no cull then.
+__device__ __forceinline__ uint32_t light_map_cell(const V3& p, const V3& lp, uint32_t R) {
+  const float vx = (float)(p.x - lp.x), vy = (float)(p.y - lp.y), vz = (float)(p.z - lp.z);
+  const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
+  uint32_t face;
+  float w, s, t;
+  if (ax >= ay && ax >= az) {
+    face = vx < 0 ? 1u : 0u;
+    w = ax, s = vy, t = vz;
+  } else if (ay >= az) {
+    face = vy < 0 ? 3u : 2u;
+    w = ay, s = vx, t = vz;
+  } else {
+    face = vz < 0 ? 5u : 4u;
+    w = az, s = vx, t = vy;
+  }
+  if (!(w > 1e-30f && w < 1e30f)) return kEmpty;
+  const float iw = __frcp_rn(w), half = 0.5f * (float)R;
+  const int top = (int)R - 1;
+  const int ci = min(max((int)floorf((s * iw + 1.0f) * half), 0), top);
+  const int cj = min(max((int)floorf((t * iw + 1.0f) * half), 0), top);
+  return (face * R + (uint32_t)cj) * R + (uint32_t)ci;
+}
+
+// True when no triangle of the mesh behind cube map `mi` can lie between p and the light: every triangle that covers
+// the direction of p - L is farther from the light than p is (the map holds a lower bound of that distance per cell,
+// +inf where nothing covers it).  inFrontOfLight (RayHs.hs:84-87) would discard whatever the walk found.
+__device__ __forceinline__ bool light_map_clears(const SceneView& S, uint32_t mi, uint32_t cell, float dist_up) {
+  const size_t cells = (size_t)6 * S.light_map_res * S.light_map_res;
+  return dist_up < __ldg(S.light_maps + (size_t)mi * cells + cell);
+}
+
 // Closest-hit candidate: key (t asc, leaf desc, position-in-leaf asc) inside one mesh
 // (KDTree.hs:109-115 right child wins ties; Geometry.hs:54-57 first minimum inside a leaf),
 // strict `<` across objects (RayHs.hs:67-71 first object wins ties).  The device triangle record
@@ -1124,6 +1159,7 @@ struct ShadowWarpSmem {
   uint32_t vis[32 * kShadowT];       // bit li: light li is occluded for this hit
   uint16_t pool[32 * kShadowT + 32]; // hit-in-batch | light << 8
 };
+static_assert(sizeof(ShadowWarpSmem) % 16 == 0, "the pair terms follow the per-warp regions");
 static_assert(32 * kShadowT <= 256, "pool entries keep the hit index in 8 bits");
 
 template <bool COUNT>
@@ -1324,6 +1360,8 @@ struct __align__(16) ShadowTables {
   double rootbox[kOccMeshes + 1][6];
   uint32_t mesh_roots[kOccMeshes + 1];  // the sphere tree's super-root follows the meshes'
   uint8_t light_side[kFastLights][kOccMeshes + 1];
+  // per (light, mesh root): number of its cube map in SceneView::light_maps, or kEmpty (light_maps.cpp)
+  uint32_t light_map[kFastLights][kOccMeshes + 1];
 };
 static_assert(sizeof(ShadowTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
 
@@ -1351,6 +1389,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
   copy16(sm.spheres, S.occ_spheres, n_spheres * (uint32_t)sizeof(OccSphere));
   copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
   const uint32_t n_roots = n_meshes + (sphere_root != kEmpty ? 1u : 0u);
+  const bool use_maps = S.light_map_index != nullptr && !P.no_light_maps;
   if (threadIdx.x < n_roots) {
     const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : sphere_root;
     sm.mesh_roots[threadIdx.x] = root;
@@ -1371,6 +1410,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
         if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
       }
     sm.light_side[li][m] = (uint8_t)side;
+    sm.light_map[li][m] = (S.light_map_index && m < n_meshes) ? S.light_map_index[li * kOccMeshes + m] : kEmpty;
   }
   __syncthreads();
   Ctx cx;
@@ -1561,9 +1601,21 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
               } else if (P.exact_boxes || needs_exact_walk(r, S)) {
                 need_walk = true;
               } else {
+                // the light's cube maps: a mesh none of whose triangles can lie between p and the light is not walked
+                uint32_t skip = 0;
+                if (use_maps && !q.directional) {
+                  const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
+                  const float dist_up = __double2float_ru(q.dd);
+                  if (cell != kEmpty)
+                    for (uint32_t m = 0; m < n_meshes; m++) {
+                      const uint32_t mi = sm.light_map[li][m];
+                      if (mi != kEmpty && light_map_clears(S, mi, cell, dist_up)) skip |= 1u << m;
+                    }
+                }
                 const RayF f = make_rayf(r, S);
                 const float ffar = __double2float_ru(q.far);
                 for (uint32_t m = 0; m < n_roots && !need_walk; m++) {
+                  if ((skip >> m) & 1u) continue;
                   const uint32_t root = sm.mesh_roots[m];
                   const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
                   const float4 b0 = np[0], b1 = np[1];
@@ -1660,6 +1712,7 @@ __device__ __forceinline__ void stage_shadow_tables(ShadowTables& sm, const Scen
         if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
       }
     sm.light_side[li][m] = (uint8_t)side;
+    sm.light_map[li][m] = (S.light_map_index && m < n_meshes) ? S.light_map_index[li * kOccMeshes + m] : kEmpty;
   }
   __syncthreads();
 }
@@ -1749,8 +1802,8 @@ __device__ __forceinline__ bool primitives_occlude(const ShadowTables& sm, uint3
 // beyond the same face of a (padded) root box, that part is outside the box; otherwise the root boxes get the float
 // slab test (slot 0 of each super-root).
 template <bool COUNT>
-__device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const SceneView& S, bool exact_boxes, uint32_t n_roots,
-                                                uint32_t li, const V3& p, const LightPair& q, Cnt<COUNT>& cnt) {
+__device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const SceneView& S, bool exact_boxes, bool use_maps,
+                                                uint32_t n_roots, uint32_t li, const V3& p, const LightPair& q, Cnt<COUNT>& cnt) {
   bool may = exact_boxes;
   for (uint32_t m = 0; m < n_roots; m++) {
     const double* rb = sm.rootbox[m];
@@ -1763,10 +1816,21 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
   r.o = q.o;
   r.d = q.ld;
   if (exact_boxes || needs_exact_walk(r, S)) return true;
+  uint32_t skip = 0;  // meshes the light's cube maps clear (see shadow_kernel_fast)
+  if (use_maps && !q.directional) {
+    const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
+    const float dist_up = __double2float_ru(q.dd);
+    if (cell != kEmpty)
+      for (uint32_t m = 0; m < S.n_occ_meshes; m++) {
+        const uint32_t mi = sm.light_map[li][m];
+        if (mi != kEmpty && light_map_clears(S, mi, cell, dist_up)) skip |= 1u << m;
+      }
+  }
   const RayF f = make_rayf(r, S);
   const float ffar = __double2float_ru(q.far);
   bool need = false;
   for (uint32_t m = 0; m < n_roots && !need; m++) {
+    if ((skip >> m) & 1u) continue;
     const float4* np = (const float4*)&S.wide32[sm.mesh_roots[m]];
     const float4 b0 = __ldg(np), b1 = __ldg(np + 1);
     float tm;
@@ -1786,6 +1850,7 @@ __global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(cons
   stage_shadow_tables(sm, S, false);
   const uint32_t n_lights = S.n_lights, n_planes = S.n_occ_planes, n_spheres = S.n_occ_spheres;
   const uint32_t n_roots = S.n_occ_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  const bool use_maps = S.light_map_index != nullptr && !P.no_light_maps;
   Cnt<COUNT> cnt;
   cnt.zero();
   ChunkCtl* ctl = P.ctl;
@@ -1817,7 +1882,7 @@ __global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(cons
           settled |= 1u << li;  // Just _ -> black
           continue;
         }
-        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, n_roots, li, p, q, cnt)) {
+        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, use_maps, n_roots, li, p, q, cnt)) {
           pending |= 1u << li;
           continue;
         }

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -150,7 +151,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index, light_maps, light_map_index;
   SceneView view{};
   uint32_t max_tree_depth = 0;
   // shadow schedule chosen for this scene: 0 = undecided (timing frames, see render_on), 1 = pooled, 2 = split
@@ -175,6 +176,9 @@ namespace {
 // leaves hold object indices and every candidate still gets the reference's exact double test
 // (Geometry.hs:81-95).  The winner is the same: smallest time, lowest object index on a tie (RayHs.hs:67-71).
 // Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
+constexpr int kLightMapRes = 512;                       // cells per edge of a cube-map face (6.3 MB per map)
+constexpr size_t kLightMapBudget = (size_t)256 << 20;   // all maps of a scene; the resolution halves until they fit
+constexpr double kLightMapMinEmpty = 0.02;              // a map with fewer empty cells than this is not worth its lookups
 constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
 constexpr uint32_t kSphereLeaf = 4;
 constexpr uint32_t kSphereTreeFlag = 4;  // WideNode::refine bit 2: the record belongs to the sphere tree
@@ -749,6 +753,58 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.n_occ_meshes = (uint32_t)occ_meshes.size();
   v.shadow_fast = occ_planes.size() <= (size_t)kOccPlanes && occ_spheres.size() <= (size_t)kOccSpheres &&
                   occ_meshes.size() <= (size_t)kOccMeshes && d->n_lights <= (uint32_t)kFastLights;
+  // Cube maps of the nearest possible occluder distance, one per (point light, occluder mesh): light_maps.cpp.
+  // Only the shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
+  v.light_maps = nullptr;
+  v.light_map_index = nullptr;
+  v.light_map_res = 0;
+  {
+    const char* env = getenv("RAYHS_B200_LIGHT_MAPS");
+    const char* env_res = getenv("RAYHS_B200_LIGHT_MAP_RES");
+    size_t n_pairs = 0;
+    for (uint32_t li = 0; li < d->n_lights; li++)
+      if (d->lights[li].kind == RH_LIGHT_POINT) n_pairs += occ_meshes.size();
+    if (v.shadow_fast && n_pairs && !(env && env[0] == '0')) {
+      int R = env_res ? std::max(16, std::min(4096, atoi(env_res))) : kLightMapRes;
+      while (R > 64 && n_pairs * 6 * (size_t)R * R * sizeof(float) > kLightMapBudget) R /= 2;
+      const size_t cells = (size_t)6 * R * R;
+      try {
+        std::vector<uint32_t> index((size_t)d->n_lights * kOccMeshes, kEmpty);
+        std::vector<float> maps, one(cells);
+        uint32_t n_maps = 0;
+        for (size_t m = 0; m < occ_meshes.size(); m++) {
+          std::vector<uint32_t> slots, dfs{occ_meshes[m]};  // the mesh's triangles: leaves of its cull tree
+          while (!dfs.empty()) {
+            const WideNode& w = cull[dfs.back()];
+            dfs.pop_back();
+            for (int c = 0; c < 2; c++) {
+              if (w.child[c] == kEmpty) continue;
+              if (w.child[c] & kLeafBit)
+                for (uint32_t k = 0; k < (w.child[c] & kCountMask); k++) slots.push_back(w.first[c] + k);
+              else dfs.push_back(w.child[c]);
+            }
+          }
+          for (uint32_t li = 0; li < d->n_lights; li++) {
+            if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+            double empty = 0;
+            if (!rh::build_light_map(d->lights[li].vec, dtris.data(), slots.data(), slots.size(), R, one.data(), kLightMapMinEmpty, &empty))
+              continue;
+            index[(size_t)li * kOccMeshes + m] = n_maps++;
+            maps.insert(maps.end(), one.begin(), one.end());
+          }
+        }
+        if (n_maps) {
+          if ((rc = upload(S->light_maps, maps.data(), maps.size()))) return rc;
+          if ((rc = upload(S->light_map_index, index.data(), index.size()))) return rc;
+          v.light_maps = (const float*)S->light_maps.p;
+          v.light_map_index = (const uint32_t*)S->light_map_index.p;
+          v.light_map_res = (uint32_t)R;
+        }
+      } catch (const std::bad_alloc&) {
+        return rh::set_error(RH_ERR_OOM, "rh_scene_create: out of host memory");
+      }
+    }
+  }
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
   v.abs_max = abs_max;
@@ -782,7 +838,8 @@ void scene_destroy(rh_scene* s) {
   if (!s) return;
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
   for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels,
-                    &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes, &s->exact_index})
+                    &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes, &s->exact_index, &s->light_maps,
+                    &s->light_map_index})
     b->release();
   delete s;
 }
@@ -1053,6 +1110,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.band_height = bh;
       P.max_depth = o->max_depth;
       P.exact_boxes = exact_boxes ? 1 : 0;
+      P.no_light_maps = (o->flags & RH_FLAG_NO_LIGHT_MAPS) ? 1 : 0;
       P.offset_mode = mode;
       P.offset_index = off_index;
       P.offset_tile = o->offset_tile;

@@ -174,7 +174,7 @@ def _offset_mode(offsets, tile: int):
 def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, want_hit_ids: bool = False,
            shard_index: int = 0, shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0,
            count: bool = False, profile: bool = False, exact_boxes: bool = False, out: np.ndarray | None = None,
-           shadow: str | None = None, seed: int | None = None) -> Image:
+           shadow: str | None = None, seed: int | None = None, light_maps: bool = True) -> Image:
     """One rh_render call with HOST buffers (numpy or pinned torch CPU tensors for `offsets`).
     `seed` (instead of `offsets`): the kernel regenerates sample_offsets(width*height, spp, seed) on the device.
     Returns the shard-compact RGB8 rows when shard_count > 1."""
@@ -196,7 +196,8 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
     bh = band_height or L.rh_default_band_height(job.height, shard_count)
     rows = L.rh_shard_rows(job.height, shard_count, bh)
     flags = ((capi.RH_FLAG_HIT_IDS if want_hit_ids else 0) | (capi.RH_FLAG_COUNT if count else 0)
-             | (capi.RH_FLAG_PROFILE if profile else 0) | (capi.RH_FLAG_EXACT_BOXES if exact_boxes else 0) | _shadow_flag(shadow))
+             | (capi.RH_FLAG_PROFILE if profile else 0) | (capi.RH_FLAG_EXACT_BOXES if exact_boxes else 0) | _shadow_flag(shadow)
+             | (0 if light_maps else capi.RH_FLAG_NO_LIGHT_MAPS))
     o = _opts(job, spp, mode, off_ptr, offset_tile, shard_index, shard_count, bh, chunk_samples, flags)
     rgb = out if out is not None else np.empty((rows, job.width, 3), dtype=np.uint8)
     ids = np.empty((rows, job.width, spp, 2), dtype=np.int32) if want_hit_ids else None
@@ -218,7 +219,8 @@ def _shadow_flag(shadow: str | None) -> int:
 
 def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offset_tile: int = 0, shard_index: int = 0,
                   shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0, count: bool = False,
-                  profile: bool = False, shadow: str | None = None, seed: int | None = None, peer_frames=None) -> dict:
+                  profile: bool = False, shadow: str | None = None, seed: int | None = None, peer_frames=None,
+                  light_maps: bool = True) -> dict:
     """rh_render into a DEVICE framebuffer (torch CUDA uint8 tensor [rows, width, 3]).  `offsets_dev` is the
     full-frame [height*width, spp, 2] float64/float32 stream (or the [tile*tile, spp, 2] tile), either a CUDA
     tensor (already uploaded) or a pinned CPU tensor (uploaded chunk by chunk inside the call).  The call
@@ -232,7 +234,7 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     if peer_frames is None and (tuple(rgb_dev.shape) != (rows, job.width, 3) or rgb_dev.dtype != torch.uint8 or not rgb_dev.is_cuda):
         raise ValueError("rgb_dev must be a CUDA uint8 tensor of shape [rows, width, 3]")
     flags = (capi.RH_FLAG_DEVICE_OUT | (capi.RH_FLAG_COUNT if count else 0) | (capi.RH_FLAG_PROFILE if profile else 0)
-             | _shadow_flag(shadow))
+             | _shadow_flag(shadow) | (0 if light_maps else capi.RH_FLAG_NO_LIGHT_MAPS))
     if off is not None and off.is_cuda:
         flags |= capi.RH_FLAG_DEVICE_OFFSETS
         torch.cuda.current_stream().synchronize()
