@@ -12,4 +12,16 @@ int set_error(int code, const std::string& msg);
 // triangles tris[slots[..]] covering each direction; false when the map would be useless or unsafe.
 bool build_light_map(const double L[3], const rh_tri* tris, const unsigned* slots, size_t n, int R, float* out, double min_empty,
                      double* empty_fraction);
+
+// light_maps.cpp, "lit triangles": can any other triangle of a mesh shadow a point of triangle T0 from the point light
+// at L?  The query region K is the hull of T0 (widened a little) and L, minus the slab within 1e-8 of T0's plane: a
+// shadow ray from a point p of T0 starts 1e-6 along the unit light direction (rayEps, Geometry.hs:36) and only counts
+// hits at t >= 1e-6 (Mesh.hs:76), i.e. at least 2e-6 |cos| above the plane, and the query is only made for |cos| >= 0.01.
+struct LitQuery {
+  double n[4][3], d[4];  // K = { x : n[i].x + d[i] >= 0 for all i }
+  double lo[3], hi[3];   // bounding box of K
+};
+bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q);         // false: grazing light or degenerate triangle
+bool lit_query_box_outside(const LitQuery& q, const double* lo, const double* hi);  // the box cannot meet K
+bool lit_query_tri_meets(const LitQuery& q, const rh_tri& t);                  // the triangle meets K
 }  // namespace rh

@@ -141,6 +141,9 @@ struct SceneView {
   // Null when the scene has none (no point light, no mesh, maps useless or switched off).
   const float* light_maps;
   const uint32_t* light_map_index;
+  // Lit triangles (light_maps.cpp), per triangle slot: bit l = nothing of the triangle's own mesh can shadow a point
+  // of it from point light l (l < 12); bits 12-15 = the mesh's index in occ_meshes.  Null when the scene has none.
+  const uint16_t* lit_flags;
 };
 
 // Camera with everything `rayFromPixel` recomputes per pixel hoisted to the host
@@ -188,10 +191,11 @@ struct RayQueue {
   double2* plane;  // plane k at plane + k*capacity
   uint32_t capacity;
 };
-// Shadow queue: 5 planes (px,py) (pz,nx) (ny,nz) (cr,cg) (cb,w) + sample ids (bit 31 = ambient term).
+// Shadow queue: 5 planes (px,py) (pz,nx) (ny,nz) (cr,cg) (cb,w) + sample ids (bit 31 = ambient term) + lit flags.
 struct ShadowQueue {
   double2* plane;
   uint32_t* sample;
+  uint32_t* lit;  // lit_flags of the hit triangle, 0 for other hits
   uint32_t capacity;
 };
 

@@ -717,6 +717,7 @@ struct ShadowTask {
   V3 p, n, cd;
   double w;
   uint32_t sample;  // bit 31: add the 0.2*cd ambient term (Diffuse, RayHs.hs:111-114)
+  uint32_t lit;     // SceneView::lit_flags of the hit triangle (mesh hits), else 0
 };
 
 __device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const ShadowQueue& q, uint32_t* counter,
@@ -736,6 +737,7 @@ __device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const
       q.plane[3 * cap + idx] = make_double2(t.cd.x, t.cd.y);
       q.plane[4 * cap + idx] = make_double2(t.cd.z, t.w);
       q.sample[idx] = t.sample;
+      q.lit[idx] = t.lit;
     } else {
       *overflow = 1;
     }
@@ -826,6 +828,7 @@ __device__ __forceinline__ void shade(const Ctx& cx, const ChunkParams& P, const
       em.s.cd = color_at<COUNT>(cx, mat, tu, tv, cnt);
       em.s.w = w;
       em.s.sample = sample | (mkind == RH_MAT_DIFFUSE ? 0x80000000u : 0u);
+      em.s.lit = (ob.kind == RH_OBJ_MESH && cx.S->lit_flags) ? (uint32_t)__ldg(cx.S->lit_flags + best.slot) : 0u;
       if (mkind == RH_MAT_DIFFUSE) break;
     }
     // fallthrough: Plastic adds the Fresnel-weighted mirror term
@@ -1590,7 +1593,15 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
               // origin is within 1.000001e-6 of p in every coordinate, so when p and the light lie beyond the same face
               // of a (padded) root box, that part is outside the box: nothing to walk.
               bool may = P.exact_boxes != 0;
+              // Lit triangles (light_maps.cpp): when the hit lies on a triangle that nothing of its own mesh can
+              // shadow from this light, that mesh is not walked for this pair.
+              uint32_t skip = 0;
+              if (use_maps) {
+                const uint32_t f = P.q_shadow.lit[item];
+                if ((f >> li) & 1u) skip = 1u << (f >> 12);
+              }
               for (uint32_t m = 0; m < n_roots; m++) {
+                if ((skip >> m) & 1u) continue;
                 const double* rb = sm.rootbox[m];
                 const uint32_t side = (p.x < rb[0] ? 1u : 0u) | (p.y < rb[1] ? 2u : 0u) | (p.z < rb[2] ? 4u : 0u) |
                                       (p.x > rb[3] ? 8u : 0u) | (p.y > rb[4] ? 16u : 0u) | (p.z > rb[5] ? 32u : 0u);
@@ -1602,7 +1613,6 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
                 need_walk = true;
               } else {
                 // the light's cube maps: a mesh none of whose triangles can lie between p and the light is not walked
-                uint32_t skip = 0;
                 if (use_maps && !q.directional) {
                   const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
                   const float dist_up = __double2float_ru(q.dd);
@@ -1803,9 +1813,13 @@ __device__ __forceinline__ bool primitives_occlude(const ShadowTables& sm, uint3
 // slab test (slot 0 of each super-root).
 template <bool COUNT>
 __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const SceneView& S, bool exact_boxes, bool use_maps,
-                                                uint32_t n_roots, uint32_t li, const V3& p, const LightPair& q, Cnt<COUNT>& cnt) {
+                                                uint32_t lit, uint32_t n_roots, uint32_t li, const V3& p, const LightPair& q,
+                                                Cnt<COUNT>& cnt) {
   bool may = exact_boxes;
+  uint32_t skip = 0;  // meshes that need no walk: lit triangle (see shadow_kernel_fast), then the light's cube maps
+  if (use_maps && ((lit >> li) & 1u)) skip = 1u << (lit >> 12);
   for (uint32_t m = 0; m < n_roots; m++) {
+    if ((skip >> m) & 1u) continue;
     const double* rb = sm.rootbox[m];
     const uint32_t side = (p.x < rb[0] ? 1u : 0u) | (p.y < rb[1] ? 2u : 0u) | (p.z < rb[2] ? 4u : 0u) |
                           (p.x > rb[3] ? 8u : 0u) | (p.y > rb[4] ? 16u : 0u) | (p.z > rb[5] ? 32u : 0u);
@@ -1816,7 +1830,6 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
   r.o = q.o;
   r.d = q.ld;
   if (exact_boxes || needs_exact_walk(r, S)) return true;
-  uint32_t skip = 0;  // meshes the light's cube maps clear (see shadow_kernel_fast)
   if (use_maps && !q.directional) {
     const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
     const float dist_up = __double2float_ru(q.dd);
@@ -1867,6 +1880,7 @@ __global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(cons
     if (item < n_items) {
       const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
       const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
+      const uint32_t lit = use_maps ? P.q_shadow.lit[item] : 0u;
       V3 acc = mk(0, 0, 0), cd = mk(0, 0, 0);  // foldl ... black lts
       bool have_cd = false;
       for (uint32_t li = 0; li < n_lights; li++) {
@@ -1882,7 +1896,7 @@ __global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(cons
           settled |= 1u << li;  // Just _ -> black
           continue;
         }
-        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, use_maps, n_roots, li, p, q, cnt)) {
+        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, use_maps, lit, n_roots, li, p, q, cnt)) {
           pending |= 1u << li;
           continue;
         }

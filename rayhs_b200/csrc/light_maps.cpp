@@ -164,6 +164,90 @@ void raster_face(float* face, int R, const P3 tri[3], int k, double sgn, float v
 
 }  // namespace
 
+// ------------------------------------------------------------------ lit triangles
+// A triangle T0 is "lit" by a point light when no other triangle of its mesh meets K (common.h).  Then for every
+// shaded point p of T0 the shadow query towards that light finds nothing in this mesh: a hit the reference accepts
+// lies on a triangle, on the segment from p to L (inFrontOfLight, RayHs.hs:84-87), at least 2e-8 above T0's plane —
+// inside K.  T0 itself cannot be hit (its plane is behind the ray origin: t < 0).  Margins: the base is taken at 1e-8
+// instead of 2e-8, and the side planes of K are moved outward by 1e-9 (1 + |coordinates|): a shaded point may lie
+// outside T0 by the roundings of its own hit test — at most ~1e-16 |o - p0| / cos(view angle), and Mesh.hs:73's
+// |det| >= 1e-6 keeps that below 1e-10 for triangles up to unit size — plus a few ulps of p = o + t d.  (A neighbour
+// across an edge that rises more steeply than ~84 degrees above T0's plane therefore counts as blocking: inside the
+// 1e-9 rim it can reach the 1e-8 base.)  Coordinates of 1e6 and more get no flags.
+bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q) {
+  const P3 a = {t0.p0[0], t0.p0[1], t0.p0[2]};
+  const P3 b = add(a, P3{t0.e1[0], t0.e1[1], t0.e1[2]}), c = add(a, P3{t0.e2[0], t0.e2[1], t0.e2[2]});
+  const P3 l = {L[0], L[1], L[2]};
+  double coord = 0;
+  for (int k = 0; k < 3; k++) coord = std::max(coord, std::max(std::max(std::fabs(a[k]), std::fabs(b[k])), std::max(std::fabs(c[k]), std::fabs(l[k]))));
+  if (!(coord < 1e6)) return false;
+  const P3 ab = sub(b, a), ac = sub(c, a);
+  P3 n0 = {ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+  const double area2 = len(n0);
+  if (!(area2 > 1e-18)) return false;
+  n0 = scale(1 / area2, n0);
+  double h = dot(n0, sub(l, a));  // height of the light above T0's plane
+  if (h < 0) {
+    n0 = scale(-1, n0);
+    h = -h;
+  }
+  const double far = std::max(len(sub(l, a)), std::max(len(sub(l, b)), len(sub(l, c))));
+  if (!(h >= 0.011 * (far + 1e-6))) return false;  // |cos| >= 0.01 for every point of the (widened) triangle
+  // base: n0.(x - a) >= 1e-8
+  for (int k = 0; k < 3; k++) q->n[0][k] = n0[k];
+  q->d[0] = -dot(n0, a) - 1e-8;
+  // sides: plane through an edge and the light, normal towards the third vertex, moved outward
+  const double eps = 1e-9 * (1 + coord);
+  const P3 v[3] = {a, b, c};
+  for (int e = 0; e < 3; e++) {
+    const P3 p = v[e], r = v[(e + 1) % 3], o = v[(e + 2) % 3];
+    const P3 pr = sub(r, p), pl = sub(l, p);
+    P3 m = {pr.y * pl.z - pr.z * pl.y, pr.z * pl.x - pr.x * pl.z, pr.x * pl.y - pr.y * pl.x};
+    const double ml = len(m);
+    if (!(ml > 1e-18)) return false;
+    m = scale(1 / ml, m);
+    if (dot(m, sub(o, p)) < 0) m = scale(-1, m);
+    for (int k = 0; k < 3; k++) q->n[1 + e][k] = m[k];
+    q->d[1 + e] = -dot(m, p) + eps;
+  }
+  for (int k = 0; k < 3; k++) {
+    q->lo[k] = std::min(std::min(a[k], b[k]), std::min(c[k], l[k])) - 2 * eps;
+    q->hi[k] = std::max(std::max(a[k], b[k]), std::max(c[k], l[k])) + 2 * eps;
+  }
+  return true;
+}
+
+bool lit_query_box_outside(const LitQuery& q, const double* lo, const double* hi) {
+  for (int k = 0; k < 3; k++)
+    if (lo[k] > q.hi[k] || hi[k] < q.lo[k]) return true;
+  for (int i = 0; i < 4; i++) {  // the corner of the box farthest along the plane normal
+    double s = q.d[i];
+    for (int k = 0; k < 3; k++) s += q.n[i][k] * (q.n[i][k] >= 0 ? hi[k] : lo[k]);
+    if (s < 0) return true;
+  }
+  return false;
+}
+
+bool lit_query_tri_meets(const LitQuery& q, const rh_tri& t) {
+  Poly p, r;
+  p.n = 3;
+  p.v[0] = {t.p0[0], t.p0[1], t.p0[2]};
+  p.v[1] = add(p.v[0], P3{t.e1[0], t.e1[1], t.e1[2]});
+  p.v[2] = add(p.v[0], P3{t.e2[0], t.e2[1], t.e2[2]});
+  for (int i = 0; i < 4; i++) {  // clip to K, one half-space at a time
+    r.n = 0;
+    for (int j = 0; j < p.n; j++) {
+      const P3 u = p.v[j], w = p.v[(j + 1) % p.n];
+      const double fu = dot(P3{q.n[i][0], q.n[i][1], q.n[i][2]}, u) + q.d[i], fw = dot(P3{q.n[i][0], q.n[i][1], q.n[i][2]}, w) + q.d[i];
+      if (fu >= 0) r.v[r.n++] = u;
+      if ((fu >= 0) != (fw >= 0)) r.v[r.n++] = add(u, scale(fu / (fu - fw), sub(w, u)));
+    }
+    if (r.n == 0) return false;
+    p = r;
+  }
+  return true;
+}
+
 // Fills out[6 * R * R] (face-major, rows of R cells) for the light at L and the triangles tris[slots[0 .. n)].
 // Returns false when the map would be useless or unsafe — a triangle (nearly) touches the light, or fewer than
 // `min_empty` of the cells stay empty (a light buried in a triangle soup) — and true otherwise, with the fraction
@@ -226,6 +310,35 @@ extern "C" int rh_light_map_build(const double light_pos[3], const rh_tri* tris,
     if (empty_fraction) *empty_fraction = empty;
   } catch (const std::bad_alloc&) {
     return rh::set_error(RH_ERR_OOM, "rh_light_map_build: out of host memory");
+  }
+  return RH_OK;
+}
+
+extern "C" int rh_lit_triangles(const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out) {
+  if (!light_pos || (!tris && n_tris) || (!out && n_tris)) return rh::set_error(RH_ERR_ARG, "rh_lit_triangles: null argument");
+  // groups of eight consecutive triangles with their bounding box, so that the box test is exercised too
+  const uint32_t n_groups = (n_tris + 7) / 8;
+  try {
+    std::vector<double> lo((size_t)n_groups * 3, std::numeric_limits<double>::infinity()), hi((size_t)n_groups * 3, -std::numeric_limits<double>::infinity());
+    for (uint32_t i = 0; i < n_tris; i++)
+      for (int k = 0; k < 3; k++) {
+        const double a = tris[i].p0[k], b = a + tris[i].e1[k], c = a + tris[i].e2[k];
+        lo[(size_t)(i / 8) * 3 + k] = std::min(lo[(size_t)(i / 8) * 3 + k], std::min(a, std::min(b, c)));
+        hi[(size_t)(i / 8) * 3 + k] = std::max(hi[(size_t)(i / 8) * 3 + k], std::max(a, std::max(b, c)));
+      }
+    for (uint32_t i = 0; i < n_tris; i++) {
+      rh::LitQuery q;
+      out[i] = 0;
+      if (!rh::lit_query_make(tris[i], light_pos, &q)) continue;
+      bool blocked = false;
+      for (uint32_t g = 0; g < n_groups && !blocked; g++) {
+        if (rh::lit_query_box_outside(q, &lo[(size_t)g * 3], &hi[(size_t)g * 3])) continue;
+        for (uint32_t j = g * 8; j < std::min(n_tris, g * 8 + 8) && !blocked; j++) blocked = j != i && rh::lit_query_tri_meets(q, tris[j]);
+      }
+      out[i] = blocked ? 0 : 1;
+    }
+  } catch (const std::bad_alloc&) {
+    return rh::set_error(RH_ERR_OOM, "rh_lit_triangles: out of host memory");
   }
   return RH_OK;
 }

@@ -151,7 +151,7 @@ std::unique_ptr<Device> g_dev;  // rh_init
 
 struct rh_scene {
   Device* device = nullptr;
-  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index, light_maps, light_map_index;
+  DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index, light_maps, light_map_index, lit_flags;
   SceneView view{};
   uint32_t max_tree_depth = 0;
   // shadow schedule chosen for this scene: 0 = undecided (timing frames, see render_on), 1 = pooled, 2 = split
@@ -178,6 +178,7 @@ namespace {
 // Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
 constexpr int kLightMapRes = 512;                       // cells per edge of a cube-map face (6.3 MB per map)
 constexpr size_t kLightMapBudget = (size_t)256 << 20;   // all maps of a scene; the resolution halves until they fit
+constexpr size_t kLitMaxTris = 400000;                  // meshes beyond this get no lit-triangle flags (host time: ~10 us per triangle and light)
 constexpr double kLightMapMinEmpty = 0.02;              // a map with fewer empty cells than this is not worth its lookups
 constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
 constexpr uint32_t kSphereLeaf = 4;
@@ -756,11 +757,13 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   // Cube maps of the nearest possible occluder distance, one per (point light, occluder mesh): light_maps.cpp.
   // Only the shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
   v.light_maps = nullptr;
+  v.lit_flags = nullptr;
   v.light_map_index = nullptr;
   v.light_map_res = 0;
   {
     const char* env = getenv("RAYHS_B200_LIGHT_MAPS");
     const char* env_res = getenv("RAYHS_B200_LIGHT_MAP_RES");
+    const char* env_lit = getenv("RAYHS_B200_LIT_TRIANGLES");  // 0: no lit-triangle flags (A/B)
     size_t n_pairs = 0;
     for (uint32_t li = 0; li < d->n_lights; li++)
       if (d->lights[li].kind == RH_LIGHT_POINT) n_pairs += occ_meshes.size();
@@ -771,7 +774,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       try {
         std::vector<uint32_t> index((size_t)d->n_lights * kOccMeshes, kEmpty);
         std::vector<float> maps, one(cells);
+        std::vector<uint16_t> lit;
         uint32_t n_maps = 0;
+        size_t n_lit = 0;
         for (size_t m = 0; m < occ_meshes.size(); m++) {
           std::vector<uint32_t> slots, dfs{occ_meshes[m]};  // the mesh's triangles: leaves of its cull tree
           while (!dfs.empty()) {
@@ -784,6 +789,37 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
               else dfs.push_back(w.child[c]);
             }
           }
+          // lit triangles: per triangle and point light, can another triangle of this mesh shadow it at all?
+          if (slots.size() <= kLitMaxTris && !(env_lit && env_lit[0] == '0')) {
+            if (lit.empty()) lit.assign(dtris.size(), 0);
+            std::vector<uint32_t> walk;
+            for (uint32_t s0 : slots) {
+              uint32_t bits = 0;
+              for (uint32_t li = 0; li < d->n_lights && li < 12; li++) {
+                if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+                rh::LitQuery q;
+                if (!rh::lit_query_make(dtris[s0], d->lights[li].vec, &q)) continue;
+                bool blocked = false;
+                walk.assign(1, occ_meshes[m]);
+                while (!walk.empty() && !blocked) {
+                  const WideNode& w = cull[walk.back()];
+                  walk.pop_back();
+                  for (int c = 0; c < 2 && !blocked; c++) {
+                    if (w.child[c] == kEmpty || rh::lit_query_box_outside(q, w.box + 6 * c, w.box + 6 * c + 3)) continue;
+                    if (w.child[c] & kLeafBit) {
+                      for (uint32_t k = 0; k < (w.child[c] & kCountMask) && !blocked; k++)
+                        blocked = (w.first[c] + k != s0) && rh::lit_query_tri_meets(q, dtris[w.first[c] + k]);
+                    } else {
+                      walk.push_back(w.child[c]);
+                    }
+                  }
+                }
+                if (!blocked) bits |= 1u << li;
+              }
+              lit[s0] = (uint16_t)(bits | ((uint32_t)m << 12));
+              n_lit += bits != 0;
+            }
+          }
           for (uint32_t li = 0; li < d->n_lights; li++) {
             if (d->lights[li].kind != RH_LIGHT_POINT) continue;
             double empty = 0;
@@ -792,6 +828,10 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
             index[(size_t)li * kOccMeshes + m] = n_maps++;
             maps.insert(maps.end(), one.begin(), one.end());
           }
+        }
+        if (n_lit) {
+          if ((rc = upload(S->lit_flags, lit.data(), lit.size()))) return rc;
+          v.lit_flags = (const uint16_t*)S->lit_flags.p;
         }
         if (n_maps) {
           if ((rc = upload(S->light_maps, maps.data(), maps.size()))) return rc;
@@ -839,7 +879,7 @@ void scene_destroy(rh_scene* s) {
   if (s->device && s->device->dev >= 0) cudaSetDevice(s->device->dev);
   for (DevBuf* b : {&s->wide, &s->wide32, &s->tris, &s->shade, &s->objects, &s->materials, &s->lights, &s->textures, &s->texels,
                     &s->lin_objs, &s->sphere_refs, &s->occ_planes, &s->occ_spheres, &s->occ_meshes, &s->exact_index, &s->light_maps,
-                    &s->light_map_index})
+                    &s->light_map_index, &s->lit_flags})
     b->release();
   delete s;
 }
@@ -1045,7 +1085,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       for (int k = 0; k < 2; k++)
         if ((rc = sc.rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
       if ((rc = sc.shq.reserve(cap * 5 * sizeof(double2)))) return rc;
-      if ((rc = sc.shq_sample.reserve(cap * sizeof(uint32_t)))) return rc;
+      if ((rc = sc.shq_sample.reserve(2 * cap * sizeof(uint32_t)))) return rc;  // sample ids, then lit flags
       if (use_split_trace && (rc = sc.hits.reserve(cap * sizeof(double4)))) return rc;
       if (split) {
         if ((rc = sc.walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
@@ -1128,6 +1168,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.counters = (FrameCounters*)D->counters.p;
       P.q_shadow.plane = (double2*)sc.shq.p;
       P.q_shadow.sample = (uint32_t*)sc.shq_sample.p;
+      P.q_shadow.lit = (uint32_t*)sc.shq_sample.p + cap;
       P.q_shadow.capacity = (uint32_t)cap;
       P.walk_q = (uint2*)sc.walk_q.p;
       P.deferred_q = (uint32_t*)sc.deferred_q.p;

@@ -158,3 +158,31 @@ def test_bad_arguments():
     assert capi.lib().rh_light_map_build(L, None, 0, 0, out.ctypes.data, None, None) == capi.RH_ERR_ARG
     capi.check(capi.lib().rh_light_map_build(L, None, 0, 1, out.ctypes.data, None, None))
     assert np.isinf(out).all()
+
+
+@pytest.mark.parametrize("name", ["dragon_superlow", "cornellBox"])
+def test_points_of_lit_triangles_see_the_light(name):
+    """Lit-triangle flags: from any point of a flagged triangle (corners and edges included, and a little outside, as a
+    rounded hit point can be) the brute-force shadow query against the whole mesh finds no occluder."""
+    sc, tris_ptr, n, p0, e1, e2, lights = scene_tris(name)
+    rng = np.random.default_rng(11)
+    total_lit = 0
+    for L in lights:
+        flags = np.zeros(n, dtype=np.uint8)
+        capi.check(capi.lib().rh_lit_triangles((C.c_double * 3)(*L), tris_ptr, n, flags.ctypes.data))
+        lit = np.flatnonzero(flags)
+        total_lit += len(lit)
+        if not len(lit):
+            continue
+        k = rng.choice(lit, 3000)
+        a, b = rng.uniform(0, 1, len(k)), rng.uniform(0, 1, len(k))
+        flip = a + b > 1
+        a, b = np.where(flip, 1 - a, a), np.where(flip, 1 - b, b)
+        snap = rng.integers(0, 4, len(k))  # a quarter each: interior, on edge e1, on edge e2, at the corner p0
+        a = np.where((snap == 2) | (snap == 3), 0.0, a) - np.where(snap == 3, 1e-12, 0.0)
+        b = np.where((snap == 1) | (snap == 3), 0.0, b) - np.where(snap == 1, 1e-12, 0.0)
+        p = p0[k] + a[:, None] * e1[k] + b[:, None] * e2[k]
+        occ = occluded(p, L, p0, e1, e2)
+        assert not occ.any(), (name, L, int(occ.sum()), k[occ][:5])
+    assert total_lit > 0.1 * n, (total_lit, n)
+    print(name, "lit (triangle, light) pairs:", total_lit, "of", n * len(lights))
