@@ -96,11 +96,12 @@ def algorithmic_bytes(st: dict, spp_bytes: int) -> dict:
     """bytes the two traversal kernels must fetch/store per frame, from the
     instrumented (RH_FLAG_COUNT) kernels' own counters.  Record sizes: wide node 64 B (two float child
     boxes; the exact double record counts as two), triangle 80 B, object record 96 B, shading record
-    128 B, texel 24 B, ray-queue entry 64 B, shadow task 84 B."""
+    128 B, texel 24 B, ray-queue entry 64 B, shadow task 88 B (84 + 4 of lit flags).  The light-map lookups (4 B per
+    pair that reaches them) are not counted."""
     trace = (64 * st["node_visits"] + 80 * st["tri_tests"] + 96 * st["prim_tests"] + 128 * st["shade_fetches"]
-             + 24 * st["texel_fetches"] + spp_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 84 * st["shadow_tasks"])
+             + 24 * st["texel_fetches"] + spp_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 88 * st["shadow_tasks"])
     shadow = (64 * st["shadow_node_visits"] + 80 * st["shadow_tri_tests"] + 96 * st["shadow_prim_tests"]
-              + 84 * st["shadow_tasks"] + 24 * st["shadow_tasks"])
+              + 88 * st["shadow_tasks"] + 24 * st["shadow_tasks"])
     return {"trace": trace, "shadow": shadow}
 
 

@@ -1524,6 +1524,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
         if (j < n_here) {
           const uint32_t item = base + j;
           const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
+          const uint32_t lit = use_maps ? P.q_shadow.lit[item] : 0u;  // (asked for here, needed far below)
           const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
           const Pair q = make_pair(L, p);
           const double ldn = dot(q.ld, n);
@@ -1596,10 +1597,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
               // Lit triangles (light_maps.cpp): when the hit lies on a triangle that nothing of its own mesh can
               // shadow from this light, that mesh is not walked for this pair.
               uint32_t skip = 0;
-              if (use_maps) {
-                const uint32_t f = P.q_shadow.lit[item];
-                if ((f >> li) & 1u) skip = 1u << (f >> 12);
-              }
+              if ((lit >> li) & 1u) skip = 1u << (lit >> 12);
               for (uint32_t m = 0; m < n_roots; m++) {
                 if ((skip >> m) & 1u) continue;
                 const double* rb = sm.rootbox[m];
