@@ -251,3 +251,29 @@ def test_eleven_lights_fit_the_fast_shadow_kernels():
     mats = [{"kind": "diffuse", "color1": (0.8, 0.8, 0.7)}, {"kind": "plastic", "ior": 1.7, "color1": (0.5, 0.7, 0.4)}]
     rs = RawScene(objs, mats, lights, camera={"position": (0, 0.6, -3), "target": (0, 0, 0.5)})
     both(rs, 150, 100)
+
+
+def test_planes_that_shadow_from_either_side():
+    """Occluder planes between the shaded points and the lights: a slanted shelf with a non-unit normal, a back wall a light
+    sits behind, point lights on both sides of the shelf (one almost in its plane), a directional light that grazes the
+    floor and one that is parallel to the shelf.  The shadow kernels decide most (pair, plane) cases from which side of
+    the plane the ray starts (stage_plane_sides); the image must still be the oracle's, byte for byte."""
+    lights = [{"kind": "point", "vec": (0.3, 1.6, 0.4), "color": (2.0, 1.9, 1.8), "radius": 0.6},     # above the shelf
+              {"kind": "point", "vec": (-0.8, 0.2, -0.2), "color": (1.2, 1.4, 1.6), "radius": 0.5},   # below it
+              {"kind": "point", "vec": (0.5, 0.9 + 1e-7, 0.5), "color": (1.0, 1.0, 1.0), "radius": 0.3},  # (almost) in its plane
+              {"kind": "point", "vec": (0.0, 0.4, 3.5), "color": (1.5, 1.5, 1.5), "radius": 0.8},     # behind the back wall
+              {"kind": "directional", "vec": (0.6, 1e-4, -0.3), "color": (0.5, 0.4, 0.3)},            # grazes the floor
+              {"kind": "directional", "vec": (2.0, 0.4, 0.0), "color": (0.3, 0.4, 0.5)}]              # parallel to the shelf
+    objs = [{"kind": "plane", "point": (0, -0.6, 0), "normal": (0, 1, 0), "tangent": (1, 0, 0), "material": 0},
+            {"kind": "plane", "point": (0.5, 0.9, 0.5), "normal": (-0.6, 3.0, 0.0), "tangent": (1, 0.2, 0), "material": 1},  # the shelf
+            {"kind": "plane", "point": (0, 0, 3.0), "normal": (0, 0, -1), "tangent": (1, 0, 0), "material": 0},
+            {"kind": "sphere", "center": (-0.3, -0.2, 0.6), "radius": 0.4, "material": 1},
+            {"kind": "sphere", "center": (0.7, 1.3, 0.9), "radius": 0.25, "material": 0},
+            dict(kind="mesh", material=1, **grid_mesh(6, z=1.4, wobble=0.15))]
+    mats = [{"kind": "diffuse", "color1": (0.8, 0.8, 0.7)}, {"kind": "plastic", "ior": 1.6, "color1": (0.5, 0.6, 0.8)}]
+    rs = RawScene(objs, mats, lights, camera={"position": (0.2, 0.3, -3.2), "target": (0, 0.3, 1)})
+    img, ref = both(rs, 200, 150)
+    assert np.array_equal(img.pixels, ref["rgb_u8"])
+    rs2 = RawScene(objs, mats, lights, camera={"position": (0.2, 1.8, -2.0), "target": (0, 0.5, 1)})  # from above the shelf
+    img2, ref2 = both(rs2, 160, 120)
+    assert np.array_equal(img2.pixels, ref2["rgb_u8"])
