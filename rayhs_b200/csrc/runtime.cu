@@ -154,6 +154,7 @@ struct rh_scene {
   DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index, light_maps, light_map_index, lit_flags;
   SceneView view{};
   uint32_t max_tree_depth = 0;
+  bool has_transparent = false;  // some material is Transparent (Material.hs:18): frames need the probe passes
   // shadow schedule chosen for this scene: 0 = undecided (timing frames, see render_on), 1 = pooled, 2 = split
   mutable int shadow_mode = 0;
   mutable int trace_mode = 0;  // closest-hit schedule, same convention: 1 = fused, 2 = split
@@ -666,6 +667,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   auto S = std::make_unique<rh_scene>();
   S->device = D;
   S->max_tree_depth = depth;
+  for (uint32_t i = 0; i < d->n_materials; i++) S->has_transparent |= d->materials[i].kind == RH_MAT_TRANSPARENT;
   int rc;
   // conservative float copy of the boxes: lower bounds rounded down, upper bounds rounded up
   // ... stored relative to the middle of all boxes, so that a scene far from the coordinate origin keeps float's full
@@ -972,7 +974,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   RH_CUDA(cudaSetDevice(D->dev));
   const CameraParams cam = make_camera(*camera, W, H);
   const size_t row_samples = (size_t)W * spp;
-  const int n_passes = 2 * o->max_depth + 1;
+  // A Transparent hit inserts a probe pass per level (RayHs.hs:136-143): up to 2D + 1 passes.  Without a Transparent
+  // material the rays of pass k all have depth k, and pass D emits nothing: D + 1 passes, no empty launches after them.
+  const int n_passes = scene->has_transparent ? 2 * o->max_depth + 1 : o->max_depth + 1;
   const size_t off_elem = (mode == RH_OFFSETS_F32) ? sizeof(float) * 2 : sizeof(double) * 2;
   const bool host_offsets =
       (mode == RH_OFFSETS_F64 || mode == RH_OFFSETS_F32) && !(o->flags & RH_FLAG_DEVICE_OFFSETS);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Renders the bench workload (C4: dragon full-res, 3840x2160, 16 spp) `frames` times with device-resident
 offsets and prints the stats of the last frame.  Used under ncu: every frame launches exactly
-chunks*(2*passes+1) kernels in a fixed order, so `-k regex:shadow_kernel -s N -c 1` picks a known chunk."""
+chunks*(2*passes+1) kernels in a fixed order (passes = maxDepth + 1, or 2 maxDepth + 1 with a Transparent material), so `-k regex:shadow_kernel -s N -c 1` picks a known chunk."""
 import argparse
 import json
 import os
