@@ -8,7 +8,9 @@
 // itself cannot be run here.  This file follows the Haskell source line by line
 // (citations are /root/reference/src/<file>:<line>), evaluates in IEEE double with
 // -ffp-contract=off (GHC emits no fused multiply-adds), and is pinned only by the
-// hand-derived known answers of SURVEY.md App. D (tests/test_oracle.py).
+// hand-derived known answers of SURVEY.md App. D (tests/test_oracle.py) and by a second,
+// independent restatement of the whole path in Python (tests/pyref.py,
+// tests/test_pyref_pins_oracle.py: same colours, bytes and ray counts).
 //
 // It includes include/rayhs_b200.h for the POD *input* structs only (rh_raw_scene,
 // rh_camera, rh_material, rh_light, rh_texture); it builds its own tree with the
