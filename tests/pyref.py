@@ -283,17 +283,27 @@ def ray_from_pixel(cam, w, h, px, py):  # Projection.hs:22-46, Mat.hs:83-93, 40-
     return o + pos, np.array([dot(rows[0], d), dot(rows[1], d), dot(rows[2], d)])
 
 
-def render(raw, cam, w, h, max_depth):
-    """rayTrace (RayHs.hs:161-166) for pixels (i mod w, i div w), no half-pixel offset (Image.hs:31-32).
+def render(raw, cam, w, h, max_depth, spp=1, offsets=None):
+    """rayTrace (RayHs.hs:161-166) for pixels (i mod w, i div w), no half-pixel offset (Image.hs:31-32); with `offsets`
+    [w*h, spp, 2] distributedRayTrace (RayHs.hs:169-195): samples at (i + ox, j + oy), average = (1/n) * foldl (+) black.
     Returns (rgb float64 [h, w, 3], rgb u8 via toIntC, ray counts)."""
     sc = Scene(raw)
     img = np.zeros((h, w, 3))
     count = dict(primary=0, reflect=0, probe=0, exit=0, shadow=0)
     for j in range(h):
         for i in range(w):
-            o, d = ray_from_pixel(cam, float(w), float(h), float(i), float(j))
-            count["primary"] += 1
-            img[j, i] = trace_ray(sc, 0, max_depth, o, d, count)
+            if offsets is None:
+                o, d = ray_from_pixel(cam, float(w), float(h), float(i), float(j))
+                count["primary"] += 1
+                img[j, i] = trace_ray(sc, 0, max_depth, o, d, count)
+            else:
+                acc = np.zeros(3)
+                for s in range(spp):
+                    ox, oy = offsets[j * w + i, s]
+                    o, d = ray_from_pixel(cam, float(w), float(h), float(i) + ox, float(j) + oy)
+                    count["primary"] += 1
+                    acc = acc + trace_ray(sc, 0, max_depth, o, d, count)
+                img[j, i] = (1 / spp) * acc
     with np.errstate(invalid="ignore"):
         u8 = np.clip(np.trunc(255 * np.where(np.isnan(img), 1.0, np.minimum(img, 1.0))), 0, 255).astype(np.uint8)  # Image.hs:54-55
     return img, u8, count

@@ -55,3 +55,18 @@ def test_every_material_kind_and_both_projections():
     rs2 = RawScene(objs, mats, lights, textures=[tex], camera={"position": (0.1, 0.3, -3), "target": (0, 0.1, 0.5), "projection": "orthographic"})
     # Projection.hs:30-32: the orthographic view plane is in pixel units — a 6 x 4 pixel frame spans the scene
     check(rs2.raw_struct, rs2.camera, 6, 4, 2, OracleScene(rs2.raw))
+
+
+def test_multi_sample_pixels():
+    """distributedRayTrace (RayHs.hs:169-195): spp samples at (i + x - 0.5, j + y - 0.5), unweighted mean before toIntC."""
+    import rayhs_b200 as rh
+
+    sc = load_scene("cornellBox")
+    raw = sc.raw.contents if hasattr(sc.raw, "contents") else sc.raw
+    w, h, spp = 12, 12, 5
+    off = rh.sample_offsets(w * h, spp, seed=24)
+    ref = oracle_for(sc).render(sc.camera, w, h, sc.max_depth, spp=spp, offsets=off)
+    img, u8, count = pyref.render(raw, sc.camera, w, h, sc.max_depth, spp=spp, offsets=np.asarray(off).reshape(w * h, spp, 2))
+    assert count == ref["rays"]
+    assert np.allclose(img, ref["rgb_f64"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(u8, ref["rgb_u8"])
