@@ -392,13 +392,14 @@ int rh_write_ppm(const char* path, const uint8_t* rgb, int width, int height);
 int rh_light_map_build(const double light_pos[3], const rh_tri* tris, uint32_t n_tris, int res, float* out, int* useful,
                        double* empty_fraction);
 
-/* Validation hook (host only): the "lit triangle" flags rh_scene_create computes per point light and mesh.  out[i] = 1
- * when no other triangle of tris[0 .. n_tris) can shadow any point of triangle i from the light: nothing else meets the
- * hull of the triangle and the light above 1e-8 of the triangle's plane (a shadow ray starts 1e-6 along the light
- * direction and counts hits from t = 1e-6 on: Geometry.hs:36, Mesh.hs:76), and the light is not grazing (|cos| >=
- * 0.01).  The shadow kernels skip the walk of a hit's own mesh for such a triangle.  Brute force here (O(n^2)); the
- * library walks the mesh's tree. */
-int rh_lit_triangles(const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out);
+/* Validation hook (host only): the "lit triangle" flags rh_scene_create computes per light and mesh.  out[i] = 1 when
+ * no other triangle of tris[0 .. n_tris) can shadow any point of triangle i from the light: nothing else meets the hull
+ * of the triangle and the light (RH_LIGHT_POINT; light_pos = its position) or the prism over the triangle along the
+ * light's vector (RH_LIGHT_DIRECTIONAL; light_pos = that vector) above 1e-8 of the triangle's plane (a shadow ray
+ * starts 1e-6 along the light direction and counts hits from t = 1e-6 on: Geometry.hs:36, Mesh.hs:76), and the light
+ * is not grazing.  The shadow kernels skip the walk of a hit's own mesh for such a triangle.  Brute force here
+ * (O(n^2)); the library walks the mesh's tree. */
+int rh_lit_triangles(int light_kind, const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out);
 
 #ifdef __cplusplus
 }

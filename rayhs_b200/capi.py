@@ -159,7 +159,7 @@ SIGNATURES = {
     "rh_write_ppm": (C.c_int, [C.c_char_p, vp, C.c_int, C.c_int]),
     "rh_light_map_build": (C.c_int, [C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, C.c_int, vp, C.POINTER(C.c_int),
                                      C.POINTER(C.c_double)]),
-    "rh_lit_triangles": (C.c_int, [C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, vp]),
+    "rh_lit_triangles": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, vp]),
 }
 
 _lib = None

@@ -21,7 +21,8 @@ struct LitQuery {
   double n[4][3], d[4];  // K = { x : n[i].x + d[i] >= 0 for all i }
   double lo[3], hi[3];   // bounding box of K
 };
-bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q);         // false: grazing light or degenerate triangle
+bool lit_query_make(const rh_tri& t0, const double L[3], bool directional, LitQuery* q);  // false: grazing light or degenerate triangle
+// (directional: L is the light's vector, K the prism over T0 along it)
 bool lit_query_box_outside(const LitQuery& q, const double* lo, const double* hi);  // the box cannot meet K
 bool lit_query_tri_meets(const LitQuery& q, const rh_tri& t);                  // the triangle meets K
 }  // namespace rh

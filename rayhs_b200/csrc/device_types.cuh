@@ -142,7 +142,8 @@ struct SceneView {
   const float* light_maps;
   const uint32_t* light_map_index;
   // Lit triangles (light_maps.cpp), per triangle slot: bit l = nothing of the triangle's own mesh can shadow a point
-  // of it from point light l (l < 12); bits 12-15 = the mesh's index in occ_meshes.  Null when the scene has none.
+  // of it from light l (l < 12, point or directional); bits 12-15 = the mesh's index in occ_meshes.  Null when the
+  // scene has none.
   const uint16_t* lit_flags;
 };
 

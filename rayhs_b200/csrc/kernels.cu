@@ -1393,6 +1393,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
   copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
   const uint32_t n_roots = n_meshes + (sphere_root != kEmpty ? 1u : 0u);
   const bool use_maps = S.light_map_index != nullptr && !P.no_light_maps;
+  const bool use_lit = S.lit_flags != nullptr && !P.no_light_maps;
   if (threadIdx.x < n_roots) {
     const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : sphere_root;
     sm.mesh_roots[threadIdx.x] = root;
@@ -1524,7 +1525,7 @@ __global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_
         if (j < n_here) {
           const uint32_t item = base + j;
           const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
-          const uint32_t lit = use_maps ? P.q_shadow.lit[item] : 0u;  // (asked for here, needed far below)
+          const uint32_t lit = use_lit ? P.q_shadow.lit[item] : 0u;  // (asked for here, needed far below)
           const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
           const Pair q = make_pair(L, p);
           const double ldn = dot(q.ld, n);
@@ -1815,7 +1816,7 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
                                                 Cnt<COUNT>& cnt) {
   bool may = exact_boxes;
   uint32_t skip = 0;  // meshes that need no walk: lit triangle (see shadow_kernel_fast), then the light's cube maps
-  if (use_maps && ((lit >> li) & 1u)) skip = 1u << (lit >> 12);
+  if ((lit >> li) & 1u) skip = 1u << (lit >> 12);  // (lit is 0 when the flags are switched off)
   for (uint32_t m = 0; m < n_roots; m++) {
     if ((skip >> m) & 1u) continue;
     const double* rb = sm.rootbox[m];
@@ -1878,7 +1879,7 @@ __global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(cons
     if (item < n_items) {
       const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
       const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
-      const uint32_t lit = use_maps ? P.q_shadow.lit[item] : 0u;
+      const uint32_t lit = (S.lit_flags != nullptr && !P.no_light_maps) ? P.q_shadow.lit[item] : 0u;
       V3 acc = mk(0, 0, 0), cd = mk(0, 0, 0);  // foldl ... black lts
       bool have_cd = false;
       for (uint32_t li = 0; li < n_lights; li++) {

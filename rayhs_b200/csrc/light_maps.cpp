@@ -165,7 +165,8 @@ void raster_face(float* face, int R, const P3 tri[3], int k, double sgn, float v
 }  // namespace
 
 // ------------------------------------------------------------------ lit triangles
-// A triangle T0 is "lit" by a point light when no other triangle of its mesh meets K (common.h).  Then for every
+// A triangle T0 is "lit" by a light when no other triangle of its mesh meets K (common.h; for a directional light K is
+// the prism over T0 along the light's vector instead of the hull with the light's position).  Then for every
 // shaded point p of T0 the shadow query towards that light finds nothing in this mesh: a hit the reference accepts
 // lies on a triangle, on the segment from p to L (inFrontOfLight, RayHs.hs:84-87), at least 2e-8 above T0's plane —
 // inside K.  T0 itself cannot be hit (its plane is behind the ray origin: t < 0).  Margins: the base is taken at 1e-8
@@ -174,10 +175,10 @@ void raster_face(float* face, int R, const P3 tri[3], int k, double sgn, float v
 // |det| >= 1e-6 keeps that below 1e-10 for triangles up to unit size — plus a few ulps of p = o + t d.  (A neighbour
 // across an edge that rises more steeply than ~84 degrees above T0's plane therefore counts as blocking: inside the
 // 1e-9 rim it can reach the 1e-8 base.)  Coordinates of 1e6 and more get no flags.
-bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q) {
+bool lit_query_make(const rh_tri& t0, const double L[3], bool directional, LitQuery* q) {
   const P3 a = {t0.p0[0], t0.p0[1], t0.p0[2]};
   const P3 b = add(a, P3{t0.e1[0], t0.e1[1], t0.e1[2]}), c = add(a, P3{t0.e2[0], t0.e2[1], t0.e2[2]});
-  const P3 l = {L[0], L[1], L[2]};
+  const P3 l = {L[0], L[1], L[2]};  // the light's position, or its direction vector (Light.hs:8-9)
   double coord = 0;
   for (int k = 0; k < 3; k++) coord = std::max(coord, std::max(std::max(std::fabs(a[k]), std::fabs(b[k])), std::max(std::fabs(c[k]), std::fabs(l[k]))));
   if (!(coord < 1e6)) return false;
@@ -186,22 +187,29 @@ bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q) {
   const double area2 = len(n0);
   if (!(area2 > 1e-18)) return false;
   n0 = scale(1 / area2, n0);
-  double h = dot(n0, sub(l, a));  // height of the light above T0's plane
+  // Point light: height of the light above T0's plane, and |cos| >= 0.01 for every point of the (widened) triangle.
+  // Directional light: the shadow ray is (p + 1e-6 d, d) with the light's own, un-normalised vector d (Light.hs:14,
+  // RayHs.hs:93) and counts hits from t = 1e-6 on: at least 2e-6 |n0.d| above the plane, so |n0.d| >= 0.011 will do.
+  double h = directional ? dot(n0, l) : dot(n0, sub(l, a));
   if (h < 0) {
     n0 = scale(-1, n0);
     h = -h;
   }
-  const double far = std::max(len(sub(l, a)), std::max(len(sub(l, b)), len(sub(l, c))));
-  if (!(h >= 0.011 * (far + 1e-6))) return false;  // |cos| >= 0.01 for every point of the (widened) triangle
+  if (directional) {
+    if (!(h >= 0.011)) return false;
+  } else {
+    const double far = std::max(len(sub(l, a)), std::max(len(sub(l, b)), len(sub(l, c))));
+    if (!(h >= 0.011 * (far + 1e-6))) return false;
+  }
   // base: n0.(x - a) >= 1e-8
   for (int k = 0; k < 3; k++) q->n[0][k] = n0[k];
   q->d[0] = -dot(n0, a) - 1e-8;
-  // sides: plane through an edge and the light, normal towards the third vertex, moved outward
+  // sides: plane through an edge and the light (or along its direction), normal towards the third vertex, moved outward
   const double eps = 1e-9 * (1 + coord);
   const P3 v[3] = {a, b, c};
   for (int e = 0; e < 3; e++) {
     const P3 p = v[e], r = v[(e + 1) % 3], o = v[(e + 2) % 3];
-    const P3 pr = sub(r, p), pl = sub(l, p);
+    const P3 pr = sub(r, p), pl = directional ? l : sub(l, p);
     P3 m = {pr.y * pl.z - pr.z * pl.y, pr.z * pl.x - pr.x * pl.z, pr.x * pl.y - pr.y * pl.x};
     const double ml = len(m);
     if (!(ml > 1e-18)) return false;
@@ -210,9 +218,17 @@ bool lit_query_make(const rh_tri& t0, const double L[3], LitQuery* q) {
     for (int k = 0; k < 3; k++) q->n[1 + e][k] = m[k];
     q->d[1 + e] = -dot(m, p) + eps;
   }
+  const double inf = std::numeric_limits<double>::infinity();
   for (int k = 0; k < 3; k++) {
-    q->lo[k] = std::min(std::min(a[k], b[k]), std::min(c[k], l[k])) - 2 * eps;
-    q->hi[k] = std::max(std::max(a[k], b[k]), std::max(c[k], l[k])) + 2 * eps;
+    q->lo[k] = std::min(a[k], std::min(b[k], c[k])) - 2 * eps;
+    q->hi[k] = std::max(a[k], std::max(b[k], c[k])) + 2 * eps;
+    if (directional) {  // the prism runs to infinity along d
+      if (l[k] > 0) q->hi[k] = inf;
+      if (l[k] < 0) q->lo[k] = -inf;
+    } else {
+      q->lo[k] = std::min(q->lo[k], l[k] - 2 * eps);
+      q->hi[k] = std::max(q->hi[k], l[k] + 2 * eps);
+    }
   }
   return true;
 }
@@ -314,8 +330,9 @@ extern "C" int rh_light_map_build(const double light_pos[3], const rh_tri* tris,
   return RH_OK;
 }
 
-extern "C" int rh_lit_triangles(const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out) {
+extern "C" int rh_lit_triangles(int light_kind, const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out) {
   if (!light_pos || (!tris && n_tris) || (!out && n_tris)) return rh::set_error(RH_ERR_ARG, "rh_lit_triangles: null argument");
+  if (light_kind != RH_LIGHT_POINT && light_kind != RH_LIGHT_DIRECTIONAL) return rh::set_error(RH_ERR_ARG, "rh_lit_triangles: unknown light kind");
   // groups of eight consecutive triangles with their bounding box, so that the box test is exercised too
   const uint32_t n_groups = (n_tris + 7) / 8;
   try {
@@ -329,7 +346,7 @@ extern "C" int rh_lit_triangles(const double light_pos[3], const rh_tri* tris, u
     for (uint32_t i = 0; i < n_tris; i++) {
       rh::LitQuery q;
       out[i] = 0;
-      if (!rh::lit_query_make(tris[i], light_pos, &q)) continue;
+      if (!rh::lit_query_make(tris[i], light_pos, light_kind == RH_LIGHT_DIRECTIONAL, &q)) continue;
       bool blocked = false;
       for (uint32_t g = 0; g < n_groups && !blocked; g++) {
         if (rh::lit_query_box_outside(q, &lo[(size_t)g * 3], &hi[(size_t)g * 3])) continue;

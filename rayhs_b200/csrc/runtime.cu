@@ -756,8 +756,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.n_occ_meshes = (uint32_t)occ_meshes.size();
   v.shadow_fast = occ_planes.size() <= (size_t)kOccPlanes && occ_spheres.size() <= (size_t)kOccSpheres &&
                   occ_meshes.size() <= (size_t)kOccMeshes && d->n_lights <= (uint32_t)kFastLights;
-  // Cube maps of the nearest possible occluder distance, one per (point light, occluder mesh): light_maps.cpp.
-  // Only the shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
+  // Light-space tables of the shadow kernels (light_maps.cpp): cube maps of the nearest possible occluder distance, one
+  // per (point light, occluder mesh), and lit-triangle flags per (triangle, light of either kind).  Only the
+  // shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
   v.light_maps = nullptr;
   v.lit_flags = nullptr;
   v.light_map_index = nullptr;
@@ -769,9 +770,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
     size_t n_pairs = 0;
     for (uint32_t li = 0; li < d->n_lights; li++)
       if (d->lights[li].kind == RH_LIGHT_POINT) n_pairs += occ_meshes.size();
-    if (v.shadow_fast && n_pairs && !(env && env[0] == '0')) {
+    if (v.shadow_fast && !occ_meshes.empty() && d->n_lights && !(env && env[0] == '0')) {
       int R = env_res ? std::max(16, std::min(4096, atoi(env_res))) : kLightMapRes;
-      while (R > 64 && n_pairs * 6 * (size_t)R * R * sizeof(float) > kLightMapBudget) R /= 2;
+      while (R > 64 && std::max<size_t>(n_pairs, 1) * 6 * (size_t)R * R * sizeof(float) > kLightMapBudget) R /= 2;
       const size_t cells = (size_t)6 * R * R;
       try {
         std::vector<uint32_t> index((size_t)d->n_lights * kOccMeshes, kEmpty);
@@ -791,16 +792,15 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
               else dfs.push_back(w.child[c]);
             }
           }
-          // lit triangles: per triangle and point light, can another triangle of this mesh shadow it at all?
+          // lit triangles: per triangle and light, can another triangle of this mesh shadow it at all?
           if (slots.size() <= kLitMaxTris && !(env_lit && env_lit[0] == '0')) {
             if (lit.empty()) lit.assign(dtris.size(), 0);
             std::vector<uint32_t> walk;
             for (uint32_t s0 : slots) {
               uint32_t bits = 0;
               for (uint32_t li = 0; li < d->n_lights && li < 12; li++) {
-                if (d->lights[li].kind != RH_LIGHT_POINT) continue;
                 rh::LitQuery q;
-                if (!rh::lit_query_make(dtris[s0], d->lights[li].vec, &q)) continue;
+                if (!rh::lit_query_make(dtris[s0], d->lights[li].vec, d->lights[li].kind == RH_LIGHT_DIRECTIONAL, &q)) continue;
                 bool blocked = false;
                 walk.assign(1, occ_meshes[m]);
                 while (!walk.empty() && !blocked) {

@@ -54,14 +54,18 @@ def round_up_f32(x):
     return np.where(f.astype(np.float64) < x, np.nextafter(f, np.float32(np.inf)), f)
 
 
-def occluded(p, L, p0, e1, e2, chunk=256):
-    """shadowIntersection against the mesh alone, brute force: ray (p + eps*ld, ld), ld = (L - p)/dist (Light.hs:15-17)."""
+def occluded(p, L, p0, e1, e2, chunk=256, directional=False):
+    """shadowIntersection against the mesh alone, brute force: ray (p + eps*ld, ld), ld = (L - p)/dist for a point light at
+    L (Light.hs:15-17), ld = L itself for a directional light (Light.hs:14), whose hits are always in front (RayHs.hs:85)."""
     out = np.zeros(len(p), dtype=bool)
     for s in range(0, len(p), chunk):
         pp = p[s:s + chunk]
-        dv = L - pp
-        dd = np.sqrt((dv * dv).sum(1))
-        ld = dv * (1 / dd)[:, None]
+        if directional:
+            ld = np.broadcast_to(L, pp.shape).copy()
+        else:
+            dv = L - pp
+            dd = np.sqrt((dv * dv).sum(1))
+            ld = dv * (1 / dd)[:, None]
         o = pp + EPS * ld
         D, O = ld[:, None, :], o[:, None, :]
         pv = np.cross(D, e2[None])
@@ -76,6 +80,8 @@ def occluded(p, L, p0, e1, e2, chunk=256):
         hit = ~((np.abs(det) < EPS) | (u < 0) | (u > 1) | (vv < 0) | (u + vv > 1) | (tt < EPS) | np.isnan(u) | np.isnan(vv) | np.isnan(tt))
         dl2 = ((o - L) ** 2).sum(1)  # inFrontOfLight, RayHs.hs:84-87
         front = dl2[:, None] > (tt * tt) * (ld * ld).sum(1)[:, None]
+        if directional:
+            front = np.ones_like(hit)
         out[s:s + chunk] = (hit & front).any(1)
     return out
 
@@ -163,13 +169,17 @@ def test_bad_arguments():
 @pytest.mark.parametrize("name", ["dragon_superlow", "cornellBox"])
 def test_points_of_lit_triangles_see_the_light(name):
     """Lit-triangle flags: from any point of a flagged triangle (corners and edges included, and a little outside, as a
-    rounded hit point can be) the brute-force shadow query against the whole mesh finds no occluder."""
+    rounded hit point can be) the brute-force shadow query against the whole mesh finds no occluder — for the scene's
+    point lights and for directional lights (un-normalised vectors, as the reference uses them)."""
     sc, tris_ptr, n, p0, e1, e2, lights = scene_tris(name)
     rng = np.random.default_rng(11)
+    cases = [(capi.RH_LIGHT_POINT, L) for L in lights]
+    cases += [(capi.RH_LIGHT_DIRECTIONAL, np.array(v)) for v in ((0.0, 1.0, 0.0), (0.3, 0.6, -1.2), (-2.0, 0.5, 0.4), (0.02, -0.03, 0.01))]
     total_lit = 0
-    for L in lights:
+    for kind, L in cases:
+        directional = kind == capi.RH_LIGHT_DIRECTIONAL
         flags = np.zeros(n, dtype=np.uint8)
-        capi.check(capi.lib().rh_lit_triangles((C.c_double * 3)(*L), tris_ptr, n, flags.ctypes.data))
+        capi.check(capi.lib().rh_lit_triangles(kind, (C.c_double * 3)(*L), tris_ptr, n, flags.ctypes.data))
         lit = np.flatnonzero(flags)
         total_lit += len(lit)
         if not len(lit):
@@ -182,7 +192,14 @@ def test_points_of_lit_triangles_see_the_light(name):
         a = np.where((snap == 2) | (snap == 3), 0.0, a) - np.where(snap == 3, 1e-12, 0.0)
         b = np.where((snap == 1) | (snap == 3), 0.0, b) - np.where(snap == 1, 1e-12, 0.0)
         p = p0[k] + a[:, None] * e1[k] + b[:, None] * e2[k]
-        occ = occluded(p, L, p0, e1, e2)
-        assert not occ.any(), (name, L, int(occ.sum()), k[occ][:5])
+        occ = occluded(p, L, p0, e1, e2, directional=directional)
+        assert not occ.any(), (name, kind, L, int(occ.sum()), k[occ][:5])
     assert total_lit > 0.1 * n, (total_lit, n)
-    print(name, "lit (triangle, light) pairs:", total_lit, "of", n * len(lights))
+    print(name, "lit (triangle, light) pairs:", total_lit, "of", n * len(cases))
+
+
+def test_lit_triangles_bad_arguments():
+    L = (C.c_double * 3)(0, 1, 0)
+    assert capi.lib().rh_lit_triangles(7, L, None, 0, None) == capi.RH_ERR_ARG
+    assert capi.lib().rh_lit_triangles(capi.RH_LIGHT_POINT, L, None, 1, None) == capi.RH_ERR_ARG
+    capi.check(capi.lib().rh_lit_triangles(capi.RH_LIGHT_POINT, L, None, 0, None))

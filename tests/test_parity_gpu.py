@@ -87,11 +87,11 @@ def test_float_cull_equals_exact_boxes(name):
 
 
 @pytest.mark.parametrize("shadow", ["pooled", "split"])
-@pytest.mark.parametrize("name", ["cornellBox", "texture", "dragon_full"])
+@pytest.mark.parametrize("name", ["cornellBox", "texture", "transform", "dragon_full"])
 def test_light_maps_change_no_byte_and_save_walks(name, shadow):
-    """The per-light cube maps of nearest possible occluder distance (light_maps.cpp) only skip tree walks that could
-    not find an occluder in front of the light: same bytes, same ray counts with RH_FLAG_NO_LIGHT_MAPS, under either
-    shadow schedule — and on the dragon a third of the shadow rays' node visits are gone."""
+    """The per-light cube maps of nearest possible occluder distance and the lit-triangle flags (light_maps.cpp; the
+    flags also for directional lights: transform.json has no other kind) only skip tree walks that could not find an
+    occluder in front of the light: same bytes, same ray counts with RH_FLAG_NO_LIGHT_MAPS, under either shadow schedule — and on the dragon a third of the shadow rays' node visits are gone."""
     sc = load_scene(name)
     w, h = 960, 540
     job = rh.renderingFromScene(sc, w, h)
