@@ -179,7 +179,7 @@ namespace {
 // Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
 constexpr int kLightMapRes = 512;                       // cells per edge of a cube-map face (6.3 MB per map)
 constexpr size_t kLightMapBudget = (size_t)256 << 20;   // all maps of a scene; the resolution halves until they fit
-constexpr size_t kLitMaxTris = 400000;                  // meshes beyond this get no lit-triangle flags (host time: ~10 us per triangle and light)
+constexpr size_t kLitMaxQueries = 1200000;              // (triangles x lights) of a mesh beyond which it gets no lit-triangle flags (host time: ~10 us per query)
 constexpr double kLightMapMinEmpty = 0.02;              // a map with fewer empty cells than this is not worth its lookups
 constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
 constexpr uint32_t kSphereLeaf = 4;
@@ -793,34 +793,60 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
             }
           }
           // lit triangles: per triangle and light, can another triangle of this mesh shadow it at all?
-          if (slots.size() <= kLitMaxTris && !(env_lit && env_lit[0] == '0')) {
+          if (slots.size() * (size_t)d->n_lights <= kLitMaxQueries && !(env_lit && env_lit[0] == '0')) {
             if (lit.empty()) lit.assign(dtris.size(), 0);
-            std::vector<uint32_t> walk;
-            for (uint32_t s0 : slots) {
-              uint32_t bits = 0;
-              for (uint32_t li = 0; li < d->n_lights && li < 12; li++) {
-                rh::LitQuery q;
-                if (!rh::lit_query_make(dtris[s0], d->lights[li].vec, d->lights[li].kind == RH_LIGHT_DIRECTIONAL, &q)) continue;
-                bool blocked = false;
-                walk.assign(1, occ_meshes[m]);
-                while (!walk.empty() && !blocked) {
-                  const WideNode& w = cull[walk.back()];
-                  walk.pop_back();
-                  for (int c = 0; c < 2 && !blocked; c++) {
-                    if (w.child[c] == kEmpty || rh::lit_query_box_outside(q, w.box + 6 * c, w.box + 6 * c + 3)) continue;
-                    if (w.child[c] & kLeafBit) {
-                      for (uint32_t k = 0; k < (w.child[c] & kCountMask) && !blocked; k++)
-                        blocked = (w.first[c] + k != s0) && rh::lit_query_tri_meets(q, dtris[w.first[c] + k]);
-                    } else {
-                      walk.push_back(w.child[c]);
+            // one query per (triangle, light), independent of each other: a few host threads share the triangles
+            std::atomic<size_t> next{0}, flagged{0};
+            std::atomic<bool> failed{false};
+            auto work = [&]() {
+              std::vector<uint32_t> walk;
+              size_t mine = 0;
+              try {
+              for (;;) {
+                const size_t begin = next.fetch_add(256);
+                if (begin >= slots.size()) break;
+                for (size_t at = begin; at < std::min(begin + 256, slots.size()); at++) {
+                  const uint32_t s0 = slots[at];
+                  uint32_t bits = 0;
+                  for (uint32_t li = 0; li < d->n_lights && li < 12; li++) {
+                    rh::LitQuery q;
+                    if (!rh::lit_query_make(dtris[s0], d->lights[li].vec, d->lights[li].kind == RH_LIGHT_DIRECTIONAL, &q)) continue;
+                    bool blocked = false;
+                    walk.assign(1, occ_meshes[m]);
+                    while (!walk.empty() && !blocked) {
+                      const WideNode& w = cull[walk.back()];
+                      walk.pop_back();
+                      for (int c = 0; c < 2 && !blocked; c++) {
+                        if (w.child[c] == kEmpty || rh::lit_query_box_outside(q, w.box + 6 * c, w.box + 6 * c + 3)) continue;
+                        if (w.child[c] & kLeafBit) {
+                          for (uint32_t k = 0; k < (w.child[c] & kCountMask) && !blocked; k++)
+                            blocked = (w.first[c] + k != s0) && rh::lit_query_tri_meets(q, dtris[w.first[c] + k]);
+                        } else {
+                          walk.push_back(w.child[c]);
+                        }
+                      }
                     }
+                    if (!blocked) bits |= 1u << li;
                   }
+                  lit[s0] = (uint16_t)(bits | ((uint32_t)m << 12));
+                  mine += bits != 0;
                 }
-                if (!blocked) bits |= 1u << li;
               }
-              lit[s0] = (uint16_t)(bits | ((uint32_t)m << 12));
-              n_lit += bits != 0;
+              } catch (const std::bad_alloc&) {
+                failed = true;  // (no exception may leave a thread)
+              }
+              flagged += mine;
+            };
+            const unsigned n_threads = slots.size() < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (n_threads == 1) {
+              work();
+            } else {
+              std::vector<std::thread> pool;
+              for (unsigned t = 0; t < n_threads; t++) pool.emplace_back(work);
+              for (std::thread& t : pool) t.join();
             }
+            if (failed) throw std::bad_alloc();
+            n_lit += flagged.load();
           }
           for (uint32_t li = 0; li < d->n_lights; li++) {
             if (d->lights[li].kind != RH_LIGHT_POINT) continue;
