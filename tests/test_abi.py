@@ -85,3 +85,22 @@ def test_shard_row_arithmetic():
             assert len(rows) == L.rh_shard_rows(H, G, bh)
             seen += [r for r in rows if r >= 0]
         assert sorted(seen) == list(range(H))
+
+
+def test_struct_offsets_the_haskell_shim_pokes():
+    """INTEGRATION.md's B200FFI.hs fills rh_scene_desc and rh_render_opts with pokeByteOff at fixed offsets; they must be
+    the offsets of the C structs (ctypes lays the mirrored structs out like the C compiler does)."""
+    import ctypes as C
+
+    from rayhs_b200 import capi
+
+    d = capi.rh_scene_desc
+    assert [getattr(d, f).offset for f in ("n_objects", "n_materials", "n_lights", "n_textures", "n_nodes", "n_tris")] == [0, 4, 8, 12, 16, 20]
+    assert [getattr(d, f).offset for f in ("objects", "materials", "lights", "textures", "texels", "n_texels", "nodes", "tris", "tri_shade")] == \
+        [24, 32, 40, 48, 56, 64, 72, 80, 88]
+    assert C.sizeof(d) == 96
+    o = capi.rh_render_opts
+    assert [getattr(o, f).offset for f in ("width", "height", "max_depth", "spp", "offset_mode", "offset_tile")] == [0, 4, 8, 12, 16, 20]
+    assert o.offsets.offset == 24 and o.shard_index.offset == 32 and o.shard_count.offset == 36 and o.flags.offset == 48
+    assert o.peer_frames.offset == 56 and C.sizeof(o) == 64
+    assert C.sizeof(capi.rh_camera) == 112
