@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RH_ABI_VERSION 1
+#define RH_ABI_VERSION 2
 
 /* ---- error classes -------------------------------------------------- */
 enum {
@@ -237,14 +237,14 @@ enum {
   RH_FLAG_PROFILE = 16,      /* bracket every launch with CUDA events: fills ms_trace / ms_shadow / ms_resolve */
   RH_FLAG_EXACT_BOXES = 32,  /* validation: the reference's double slab test at every box instead of the
                                 conservative float cull (same image) */
-  /* Shadow-ray schedule (same image either way; DESIGN.md "Kernels").  Default: the library times both on the
-   * first three large frames of a scene (warm-up, pooled, split) and keeps the faster one for that scene. */
-  RH_FLAG_SHADOW_POOLED = 64, /* one kernel per pass, tree walks in warp-local rounds of 32 (coherent rays)   */
-  RH_FLAG_SHADOW_SPLIT = 128, /* classify -> walk (per-lane refill from a global queue) -> fold (incoherent rays) */
+  /* Shadow-walk schedule (same image either way; DESIGN.md "Kernels").  Default: the library times both on the
+   * first large frames of a scene (warm-up, pooled, refill) and keeps the faster one for that scene. */
+  RH_FLAG_SHADOW_POOLED = 64, /* tree walks of the queued hits in warp-local rounds of 32, pooled per light (coherent rays) */
+  RH_FLAG_SHADOW_SPLIT = 128, /* one queued hit per lane, per-lane refill when a ray ends (incoherent rays: triangle soups) */
   RH_FLAG_PEER_FRAMES = 256,  /* store the finished rows into rh_render_opts.peer_frames (see there) */
-  /* Closest-hit schedule, chosen and timed per scene like the shadow schedule (same image either way). */
-  RH_FLAG_TRACE_FUSED = 512,  /* one kernel per pass: closest hit + shade, 32 items per warp in lock step (coherent rays) */
-  RH_FLAG_TRACE_SPLIT = 1024, /* intersect (per-lane refill) -> shade from hit records (incoherent rays)           */
+  /* 512 and 1024 selected the closest-hit schedule in ABI version 1; ignored since (one closest-hit kernel). */
+  RH_FLAG_SHARD_OFFSETS = 4096, /* RH_OFFSETS_F64 / F32 with shard_count > 1: `offsets` holds only THIS shard's rows, in
+                                   shard-compact order ([rh_shard_rows][width][spp][2]), instead of the full frame   */
   RH_FLAG_NO_LIGHT_MAPS = 2048 /* validation / A-B: shadow rays ignore the per-light cube maps of nearest possible
                                   occluder distance that rh_scene_create builds (same image; DESIGN.md "Light maps") */
 };
@@ -260,6 +260,9 @@ typedef struct rh_stats {
   uint64_t rays_shadow_culled; /* of rays_shadow: light at or below the shading horizon (l.n <= 0), Lambert term
                                   exactly 0, occlusion query skipped                                   */
   uint64_t shadow_tasks;  /* shaded Diffuse/Plastic hits (each folds over all lights) */
+  uint64_t shadow_tasks_queued; /* of those: hits with a light whose shadow ray had to walk a tree (the others fold in the trace kernel) */
+  uint64_t shadow_walk_pairs;   /* (hit, light) pairs that walked a tree                                  */
+  uint64_t deep_stack_pushes;   /* RH_FLAG_COUNT only: traversal-stack entries beyond the shared-memory short stack */
   uint64_t queued_rays;   /* ray-queue entries written and read back (reflect + probe + exit) */
   /* RH_FLAG_COUNT only; the first six are the closest-hit (trace) kernel's */
   uint64_t box_tests;     /* child boxes tested                                  */
@@ -283,8 +286,8 @@ typedef struct rh_stats {
   uint32_t chunks;
   uint32_t negative_channels; /* pixels with a channel whose toIntC is < 0 before the RGB8 clamp (App. A-Q2) */
   uint32_t queue_factor;      /* ray-queue capacity / chunk samples that was needed */
-  uint32_t shadow_split;      /* 1: this frame used the split shadow schedule (RH_FLAG_SHADOW_SPLIT or auto)  */
-  uint32_t trace_split;       /* 1: ... the split closest-hit schedule (RH_FLAG_TRACE_SPLIT or auto)          */
+  uint32_t shadow_split;      /* 1: this frame used the per-lane-refill shadow kernel (RH_FLAG_SHADOW_SPLIT or auto) */
+  uint32_t reserved_;
 } rh_stats;
 
 typedef struct rh_scene rh_scene; /* opaque; owns device copies */
@@ -350,6 +353,9 @@ int rh_peer_free(void* dev_ptr);
 /* Micro-benchmarks used by bench.py for the roofline denominators:
  * random 32-byte-aligned 64-byte gathers over `bytes` of device memory; returns GB/s. */
 int rh_bench_gather(uint64_t bytes, int iters, double* gbs_out);
+/* Coalesced 16-byte loads sweeping `bytes` of device memory `iters` times; with bytes below the L2 size this is the
+ * L2 -> SM streaming rate (the denominator for the traversal kernels' lts__t_bytes); returns GB/s. */
+int rh_bench_stream(uint64_t bytes, int iters, double* gbs_out);
 /* Dependent DFMA chains on all SMs; returns TFLOP/s (2 flop per DFMA). */
 int rh_bench_dfma(int iters, double* tflops_out);
 
@@ -377,6 +383,9 @@ void rh_loaded_destroy(rh_loaded* l);
  * fills out[n_pixels][spp][2] with (x-0.5, y-0.5), x drawn before y. */
 void rh_sample_offsets_f64(uint64_t seed, uint64_t n_pixels, int spp, double* out);
 void rh_sample_offsets_f32(uint64_t seed, uint64_t n_pixels, int spp, float* out);
+/* The same stream from pixel `first_pixel` on (SplitMix64 is counter-based): what a shard needs of a frame whose full
+ * stream does not fit the host (configs[4]: 34 GB). */
+void rh_sample_offsets_f64_at(uint64_t seed, uint64_t first_pixel, uint64_t n_pixels, int spp, double* out);
 
 /* P3 writer byte-identical to Image.hs:60-75. */
 int rh_write_ppm(const char* path, const uint8_t* rgb, int width, int height);

@@ -647,20 +647,38 @@ double orc_mod1(double n, double d) { return hs_mod1(n, d); }
 // 1-sample path.  Outputs (any may be NULL) are indexed by the FULL frame:
 //   rgb_f64[w*h*3] raw colour, rgb_u8[w*h*3] clamped toIntC, rgb_int[w*h*3] raw toIntC,
 //   hit_ids[w*h*spp*2] (object, tri).
-int orc_render(void* s, const rh_camera* cam, int w, int h, int maxDepth, int spp, const double* offsets, int row_begin,
-               int row_end, int row_step, int n_threads, double* rgb_f64, uint8_t* rgb_u8, int32_t* rgb_int,
-               int32_t* hit_ids, orc_result_counts* counts) {
+// Value k (0-based) of the SplitMix64 stream rh_sample_offsets_f64(seed, ...) writes, as a double in [0, 1): the
+// generator's state after k + 1 steps is seed + (k + 1) * gamma, so any value can be produced on its own.
+static double splitmix01_at(uint64_t seed, uint64_t k) {
+  uint64_t z = seed + (k + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// rayTrace (RayHs.hs:161-166) / distributedRayTrace (RayHs.hs:190-195) over the pixels (row, col) with
+// row in row_begin:row_end:row_step and col in col_begin:col_end:col_step.  Sample offsets: `offsets` (full-frame array,
+// pixel-major) or, when it is null and spp_seeded != 0, the SplitMix64 stream of `seed` evaluated in place — the frames
+// of configs[4] have 34 GB of offsets.  Output arrays are full-frame; only the selected pixels are written.
+int orc_render2(void* s, const rh_camera* cam, int w, int h, int maxDepth, int spp, const double* offsets, int spp_seeded,
+                uint64_t seed, int row_begin, int row_end, int row_step, int col_begin, int col_end, int col_step, int compact_out, int n_threads,
+                double* rgb_f64, uint8_t* rgb_u8, int32_t* rgb_int, int32_t* hit_ids, orc_result_counts* counts) {
   Scene& sc = ((OracleScene*)s)->sc;
   if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
   if (n_threads <= 0) n_threads = 1;
   if (row_step <= 0) row_step = 1;
-  std::vector<int> rows;
+  if (col_step <= 0) col_step = 1;
+  std::vector<int> rows, cols;
   for (int y = row_begin; y < row_end && y < h; y += row_step) rows.push_back(y);
-  const long long npix = (long long)rows.size() * w;
+  for (int x = col_begin; x < col_end && x < w; x += col_step) cols.push_back(x);
+  const long long nc = (long long)cols.size();
+  const long long npix = (long long)rows.size() * nc;
   const long long nchunks = (npix + 9) / 10;  // parListChunk 10, Image.hs:36
   std::atomic<long long> next{0};
   std::vector<Counters> tc(n_threads);
   const double dw = (double)w, dh = (double)h;
+  const bool sampled = offsets != nullptr || spp_seeded != 0;
   auto t_begin = std::chrono::steady_clock::now();
   auto worker = [&](int tid) {
     Counters& c = tc[tid];
@@ -668,30 +686,39 @@ int orc_render(void* s, const rh_camera* cam, int w, int h, int maxDepth, int sp
       long long ch = next.fetch_add(1);
       if (ch >= nchunks) break;
       for (long long k = ch * 10; k < std::min(npix, ch * 10 + 10); k++) {
-        int y = rows[k / w], x = (int)(k % w);
-        long long i = (long long)y * w + x;  // pixelCoord, Image.hs:31-32
+        int y = rows[k / nc], x = cols[k % nc];
+        const long long i = (long long)y * w + x;  // pixelCoord, Image.hs:31-32
+        const long long io = compact_out ? k : i;     // where the pixel's results go
         double pi_ = (double)x, pj = (double)y;
         Color col;
-        if (!offsets) {
+        if (!sampled) {
           int ho, ht;
           col = traceRay(sc, 0, maxDepth, rayFromPixel(dw, dh, *cam, pi_, pj), c, 0, &ho, &ht);  // tracePixel, RayHs.hs:156-159
-          if (hit_ids) { hit_ids[2 * i] = ho; hit_ids[2 * i + 1] = ht; }
+          if (hit_ids) { hit_ids[2 * io] = ho; hit_ids[2 * io + 1] = ht; }
         } else {
           Color sumc = black;  // average, RayHs.hs:169-171
           for (int sidx = 0; sidx < spp; sidx++) {
-            const double* of = offsets + ((size_t)i * spp + sidx) * 2;
+            double of[2];
+            const uint64_t g = (uint64_t)i * (uint64_t)spp + (uint64_t)sidx;
+            if (offsets) {
+              of[0] = offsets[2 * g];
+              of[1] = offsets[2 * g + 1];
+            } else {  // (x - 0.5, y - 0.5), x drawn before y (RayHs.hs:185-188)
+              of[0] = splitmix01_at(seed, 2 * g) - 0.5;
+              of[1] = splitmix01_at(seed, 2 * g + 1) - 0.5;
+            }
             int ho, ht;
             Color cs = traceRay(sc, 0, maxDepth, rayFromPixel(dw, dh, *cam, pi_ + of[0], pj + of[1]), c, 0, &ho, &ht);
-            if (hit_ids) { hit_ids[2 * (i * spp + sidx)] = ho; hit_ids[2 * (i * spp + sidx) + 1] = ht; }
+            if (hit_ids) { hit_ids[2 * (io * spp + sidx)] = ho; hit_ids[2 * (io * spp + sidx) + 1] = ht; }
             sumc = sumc + cs;
           }
           col = mul(1.0 / (double)spp, sumc);
         }
-        if (rgb_f64) { rgb_f64[3 * i] = col.r; rgb_f64[3 * i + 1] = col.g; rgb_f64[3 * i + 2] = col.b; }
+        if (rgb_f64) { rgb_f64[3 * io] = col.r; rgb_f64[3 * io + 1] = col.g; rgb_f64[3 * io + 2] = col.b; }
         long long q[3] = {toIntC(col.r), toIntC(col.g), toIntC(col.b)};
         for (int k2 = 0; k2 < 3; k2++) {
-          if (rgb_int) rgb_int[3 * i + k2] = (int32_t)std::max<long long>(INT32_MIN, std::min<long long>(INT32_MAX, q[k2]));
-          if (rgb_u8) rgb_u8[3 * i + k2] = (uint8_t)std::max<long long>(0, std::min<long long>(255, q[k2]));
+          if (rgb_int) rgb_int[3 * io + k2] = (int32_t)std::max<long long>(INT32_MIN, std::min<long long>(INT32_MAX, q[k2]));
+          if (rgb_u8) rgb_u8[3 * io + k2] = (uint8_t)std::max<long long>(0, std::min<long long>(255, q[k2]));
         }
       }
     }
@@ -713,6 +740,13 @@ int orc_render(void* s, const rh_camera* cam, int w, int h, int maxDepth, int sp
     counts->threads = n_threads;
   }
   return 0;
+}
+
+int orc_render(void* s, const rh_camera* cam, int w, int h, int maxDepth, int spp, const double* offsets, int row_begin,
+               int row_end, int row_step, int n_threads, double* rgb_f64, uint8_t* rgb_u8, int32_t* rgb_int,
+               int32_t* hit_ids, orc_result_counts* counts) {
+  return orc_render2(s, cam, w, h, maxDepth, spp, offsets, 0, 0, row_begin, row_end, row_step, 0, w, 1, 0, n_threads, rgb_f64, rgb_u8,
+                     rgb_int, hit_ids, counts);
 }
 
 }  // extern "C"

@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
         L.orc_mod1.argtypes = [C.c_double, C.c_double]
         L.orc_render.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                  vp, C.POINTER(orc_result_counts)]
+        L.orc_render2.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(orc_result_counts)]
         _lib = L
     return _lib
 
@@ -109,6 +111,30 @@ class OracleScene:
         return dict(rgb_f64=rgb_f64, rgb_u8=rgb_u8, rgb_int=rgb_int, hit_ids=ids,
                     rays={n: int(cnt.rays[i]) for i, n in enumerate(names)}, rays_total=int(sum(cnt.rays)),
                     box_tests=int(cnt.box_tests), tri_tests=int(cnt.tri_tests), prim_tests=int(cnt.prim_tests),
+                    seconds=cnt.seconds, threads=cnt.threads)
+
+
+    def render_sample(self, camera, w, h, max_depth, spp=1, seed=None, rows=(0, None, 1), cols=(0, None, 1), threads=0,
+                      want_ids=True):
+        """The same for the pixels rows x cols only, with COMPACT outputs [n_rows, n_cols, ...] and the sample offsets
+        taken from the SplitMix64 stream of `seed` in place (rh_sample_offsets_f64's stream; None: one sample at the
+        pixel corner).  For frames whose full-size arrays do not fit the host (configs[4]: 8K x 64 spp)."""
+        r0, r1, rs = rows
+        c0, c1, cs = cols
+        r1 = h if r1 is None else r1
+        c1 = w if c1 is None else c1
+        ys, xs = np.arange(r0, min(r1, h), rs), np.arange(c0, min(c1, w), cs)
+        rgb_f64 = np.zeros((len(ys), len(xs), 3), dtype=np.float64)
+        rgb_u8 = np.zeros((len(ys), len(xs), 3), dtype=np.uint8)
+        ids = np.full((len(ys), len(xs), spp, 2), -2, dtype=np.int32) if want_ids else None
+        cnt = orc_result_counts()
+        rc = lib().orc_render2(self._h, C.cast(C.pointer(camera), C.c_void_p), w, h, max_depth, spp, None, 0 if seed is None else 1,
+                               0 if seed is None else int(seed), r0, r1, rs, c0, c1, cs, 1, threads, rgb_f64.ctypes.data,
+                               rgb_u8.ctypes.data, None, ids.ctypes.data if ids is not None else None, C.byref(cnt))
+        assert rc == 0
+        names = ["primary", "reflect", "probe", "exit", "shadow"]
+        return dict(rows=ys, cols=xs, rgb_f64=rgb_f64, rgb_u8=rgb_u8, hit_ids=ids,
+                    rays={n: int(cnt.rays[i]) for i, n in enumerate(names)}, rays_total=int(sum(cnt.rays)),
                     seconds=cnt.seconds, threads=cnt.threads)
 
 

@@ -22,8 +22,9 @@ RH_LIGHT_DIRECTIONAL, RH_LIGHT_POINT = 0, 1
 RH_PROJ_ORTHOGRAPHIC, RH_PROJ_PERSPECTIVE = 0, 1
 RH_OFFSETS_NONE, RH_OFFSETS_F64, RH_OFFSETS_F32, RH_OFFSETS_TILED_F64, RH_OFFSETS_SPLITMIX64 = 0, 1, 2, 3, 4
 RH_FLAG_HIT_IDS, RH_FLAG_DEVICE_OUT, RH_FLAG_DEVICE_OFFSETS, RH_FLAG_COUNT, RH_FLAG_PROFILE, RH_FLAG_EXACT_BOXES = 1, 2, 4, 8, 16, 32
-RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES, RH_FLAG_TRACE_FUSED, RH_FLAG_TRACE_SPLIT = 64, 128, 256, 512, 1024
+RH_FLAG_SHADOW_POOLED, RH_FLAG_SHADOW_SPLIT, RH_FLAG_PEER_FRAMES = 64, 128, 256
 RH_FLAG_NO_LIGHT_MAPS = 2048
+RH_FLAG_SHARD_OFFSETS = 4096
 RH_NO_NODE = 0xFFFFFFFF
 
 d3 = C.c_double * 3
@@ -95,7 +96,8 @@ class rh_render_opts(C.Structure):
 
 class rh_stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_probe", C.c_uint64),
-                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_shadow_culled", C.c_uint64), ("shadow_tasks", C.c_uint64), ("queued_rays", C.c_uint64),
+                ("rays_exit", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_shadow_culled", C.c_uint64), ("shadow_tasks", C.c_uint64),
+                ("shadow_tasks_queued", C.c_uint64), ("shadow_walk_pairs", C.c_uint64), ("deep_stack_pushes", C.c_uint64), ("queued_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("shade_fetches", C.c_uint64), ("texel_fetches", C.c_uint64), ("node_visits", C.c_uint64),
                 ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
@@ -103,7 +105,7 @@ class rh_stats(C.Structure):
                 ("upload_bytes", C.c_uint64), ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_resolve", C.c_double), ("trace_launches", C.c_uint32), ("shadow_launches", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("negative_channels", C.c_uint32),
-                ("queue_factor", C.c_uint32), ("shadow_split", C.c_uint32), ("trace_split", C.c_uint32)]
+                ("queue_factor", C.c_uint32), ("shadow_split", C.c_uint32), ("reserved_", C.c_uint32)]
 
     def rays_total(self) -> int:
         return self.rays_primary + self.rays_reflect + self.rays_probe + self.rays_exit + self.rays_shadow
@@ -142,6 +144,7 @@ SIGNATURES = {
     "rh_peer_close": (C.c_int, [vp]),
     "rh_peer_free": (C.c_int, [vp]),
     "rh_bench_gather": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "rh_bench_stream": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "rh_bench_dfma": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "rh_flatten": (C.c_int, [C.POINTER(rh_raw_scene), C.POINTER(vp)]),
     "rh_flat_desc": (C.POINTER(rh_scene_desc), [vp]),
@@ -156,6 +159,7 @@ SIGNATURES = {
     "rh_loaded_destroy": (None, [vp]),
     "rh_sample_offsets_f64": (None, [C.c_uint64, C.c_uint64, C.c_int, vp]),
     "rh_sample_offsets_f32": (None, [C.c_uint64, C.c_uint64, C.c_int, vp]),
+    "rh_sample_offsets_f64_at": (None, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, vp]),
     "rh_write_ppm": (C.c_int, [C.c_char_p, vp, C.c_int, C.c_int]),
     "rh_light_map_build": (C.c_int, [C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, C.c_int, vp, C.POINTER(C.c_int),
                                      C.POINTER(C.c_double)]),

@@ -8,12 +8,25 @@
 namespace rhd {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;    // KDTree.hs:61 `Empty`
-constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf: low 30 bits = triangle (or sphere) count
-constexpr uint32_t kSphereLeafBit = 0x40000000u;  // ... a leaf of the sphere tree: `first` indexes sphere_refs
-constexpr uint32_t kCountMask = 0x3FFFFFFFu;
+constexpr uint32_t kLeafBit = 0x80000000u;  // child reference is a leaf
+constexpr uint32_t kSphereLeafBit = 0x40000000u;  // ... a leaf of the sphere tree: its slots index sphere_refs
+constexpr uint32_t kCountMask = 0x3FFFFFFFu;      // exact (double) tree: low 30 bits of a leaf reference = triangle count
+// Leaf reference of the float path's cull tree (WideNode32::child), self-contained so that a stacked subtree is ONE
+// 32-bit word: kLeafBit | kSphereLeafBit? | (count - 1) << 27 | first slot.  Cull-tree leaves hold at most kSubLeaf
+// triangles and sphere-tree leaves at most 4 spheres, so 3 bits of count and 27 bits of slot (134 M triangles) do.
+constexpr uint32_t kLeafCountShift = 27, kLeafFirstMask = 0x07FFFFFFu, kLeafMaxCount = 8;
 constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by rh_render (reference scenes use 3)
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
-constexpr int kStack = 112;                 // tree depth is <= 100 by construction (KDTree.hs:76-77, 82) + leaf refinement levels
+constexpr int kStack = 112;                 // deepest stack a walk may need: tree depth <= 100 (KDTree.hs:76-77, 82) + roots
+#ifndef RH_SHORT_STACK
+#define RH_SHORT_STACK 12
+#endif
+// Traversal stack entries per thread held in SHARED memory (8 bytes each: subtree reference + float entry distance).
+// Deeper entries — and the whole stack of the rare exact (double box) walk — go to the thread's column of a scratch
+// area in global memory that the runtime sizes from the scene's tree depth.  No stack lives in local memory.
+constexpr int kShortStack = RH_SHORT_STACK;
+// Queue entries per slab: the unit a warp reserves (producer) or claims (consumer) with ONE global atomic.
+constexpr uint32_t kSlab = 128;
 #ifndef RH_SMEM_NODES
 #define RH_SMEM_NODES 448
 #endif
@@ -23,51 +36,35 @@ constexpr int kSmemLights = 16;
 constexpr int kBlock = 128;                // resolve kernel
 constexpr int kMaxPeers = 16;
 #ifndef RH_TRACE_BLOCK
-#define RH_TRACE_BLOCK 1024
-#define RH_TRACE_MINB 1
+#define RH_TRACE_BLOCK 768
+#endif
+#ifndef RH_SHADOW_BLOCK
 #define RH_SHADOW_BLOCK 768
-#define RH_SHADOW_MINB 1
-#endif
-#ifndef RH_SHADOW_PAIRS
-#define RH_SHADOW_PAIRS 9  // (hit, light) pairs per lane whose terms the pooled fast shadow kernel keeps in shared memory: 3 hits per lane per batch with 3 lights (measured: 3 pairs 37.3 ms, 6 33.9, 9 33.7, 12 34.7 ms of shadow work per bench frame)
-#endif
-#ifndef RH_SHADOW_T
-#define RH_SHADOW_T 4   // shaded hits per lane per warp batch in the pooled shadow kernel
-#endif
-#ifndef RH_SHADOW_POOL
-#define RH_SHADOW_POOL 1
 #endif
 #ifndef RH_WALK_BLOCK
-#define RH_WALK_BLOCK 640  // threads per block of the shadow walk kernel (one block per SM): 640 -> up to 102 registers (measured best of 512, 640, 768)
+#define RH_WALK_BLOCK 640  // threads per block of the per-lane-refill shadow kernel (one block per SM)
 #endif
 #ifndef RH_WALK_UNROLL
 #define RH_WALK_UNROLL 2
 #endif
-#ifndef RH_ISECT_BLOCK
-#define RH_ISECT_BLOCK 1024  // threads per block of intersect_kernel (one block per SM; measured on the synthetic scene: 512 84 ms, 640 74 ms, 768 71 ms, 1024 69 ms)
-#endif
 #ifndef RH_REFILL_MIN
 #define RH_REFILL_MIN 16
 #endif
-#ifndef RH_SHADOW_SPLIT
-#define RH_SHADOW_SPLIT 1  // 0: one pooled shadow kernel per pass instead of classify -> walk -> fold
+#ifndef RH_TMA_STAGE
+#define RH_TMA_STAGE 1  // trace kernel: the next batch of queued rays / sample offsets arrives by a bulk async copy (cp.async.bulk + mbarrier) while the current batch is traced
 #endif
-#ifndef RH_SHADOW_FAST
-#define RH_SHADOW_FAST 1  // 0: always use the general pooled kernel (A/B and validation builds)
-#endif
-constexpr int kTraceBlock = RH_TRACE_BLOCK, kTraceMinBlocks = RH_TRACE_MINB;      // one block per SM, tables staged once per SM.  trace: 1024 threads at 64 registers (bench frame: equal to 768 at 80; incoherent synthetic scene: 57 vs 64 ms); shadow: 768 (measured best)
-constexpr int kShadowBlock = RH_SHADOW_BLOCK, kShadowMinBlocks = RH_SHADOW_MINB;
+constexpr int kTraceBlock = RH_TRACE_BLOCK;    // one block per SM, tables staged once per SM
+constexpr int kShadowBlock = RH_SHADOW_BLOCK;
+constexpr int kWalkBlock = RH_WALK_BLOCK;
 
-// 128-byte "wide" node: one record per inner tree node holding BOTH child boxes, so a
-// visit is one 128-byte line (4 sectors) and every box is still tested exactly once,
-// as in KDTree.hs:96-107 (box test at every Node and Leaf).  A synthetic super-root per
-// mesh carries the root's own box in slot 0.  Wide nodes are stored in level order over
-// all meshes, so the first kSmemNodes records are the top levels of every tree.
+// 128-byte "wide" node of the EXACT walk: one record per inner node of the reference's own tree (KDTree.hs:59-61)
+// holding BOTH child boxes in double, so every box is tested exactly once, as in KDTree.hs:96-107 (box test at every
+// Node and Leaf).  A synthetic super-root per mesh carries the root's own box in slot 0.  Level order over all meshes.
 struct __align__(16) WideNode {
   double box[12];     // child0 lo.xyz hi.xyz, child1 lo.xyz hi.xyz
   uint32_t child[2];  // kEmpty | kLeafBit|count | wide-node index
   uint32_t first[2];  // leaf child: first triangle slot
-  uint32_t refine;    // bit c: child c's box is a culling refinement inside a reference leaf (not a reference box)
+  uint32_t refine;    // bit c: child c's box is not a box the reference tests (sphere tree): the exact walk passes it
   uint32_t pad_[3];
 };
 #ifndef RH_STREAM_CHUNK_MI
@@ -81,15 +78,17 @@ struct __align__(16) WideNode {
 #define RH_SUBLEAF 4  // triangles per leaf of the float path's cull tree (measured: 3-4 best of 2, 3, 4, 6, 8)
 #endif
 constexpr uint32_t kSubLeaf = RH_SUBLEAF;
+static_assert(kSubLeaf <= kLeafMaxCount, "cull-tree leaf count must fit the packed leaf reference");
 static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
 
-// 64-byte culling copy of a WideNode: the same two child boxes rounded OUTWARD to float.  The fp32
-// slab test on it is conservative (never rejects a box the double test of KDTree.hs:39-56 accepts,
-// see kernels.cu), so it only decides which triangles get the exact double test.
+// 64-byte node of the float path's cull tree: two child boxes rounded OUTWARD to float, relative to SceneView::center.
+// The fp32 slab test on it is conservative (never rejects a box the double test of KDTree.hs:39-56 accepts, see
+// kernels.cu), so it only decides which triangles get the exact double test.  child: kEmpty | packed leaf reference
+// (see kLeafCountShift) | node index.
 struct __align__(16) WideNode32 {
   float box[12];
   uint32_t child[2];
-  uint32_t first[2];
+  uint32_t pad_[2];
 };
 static_assert(sizeof(WideNode32) == 64, "WideNode32 must be 64 bytes");
 
@@ -103,12 +102,12 @@ struct __align__(16) DObject {
 };
 static_assert(sizeof(DObject) == 96, "DObject must be 96 bytes");
 
-// Occluder tables of the fast shadow kernel (shadowIntersection, RayHs.hs:74-82): the non-emitter planes and the
-// non-emitter spheres that are not in the sphere tree, as compact records staged in shared memory, and the
-// super-roots of the non-emitter, non-empty meshes.
+// Occluder tables (shadowIntersection, RayHs.hs:74-82): the non-emitter planes and the non-emitter spheres that are
+// not in the sphere tree, as compact records, and the super-roots of the non-emitter, non-empty meshes.
 struct OccPlane { double p[3], n[3]; };   // Geometry.hs:62
 struct OccSphere { double c[3], r; };     // Geometry.hs:63
 constexpr int kOccPlanes = 16, kOccSpheres = 16, kOccMeshes = 8, kFastLights = 12;
+constexpr int kMaskLights = 32;  // lights whose per-hit state fits the 32-bit walk / settled masks of a shadow task
 
 struct SceneView {
   const WideNode* wide;      // exact double boxes: rays with a zero direction component, RH_FLAG_EXACT_BOXES
@@ -129,7 +128,7 @@ struct SceneView {
   const OccSphere* occ_spheres;
   const uint32_t* occ_meshes;
   uint32_t n_occ_planes, n_occ_spheres, n_occ_meshes;
-  uint32_t shadow_fast;         // the occluder tables and the lights fit the fast shadow kernel's shared-memory tables
+  uint32_t shadow_fast;         // the occluder tables and the lights fit the shared-memory tables (root boxes, light sides, cube maps usable)
   uint32_t n_wide, n_tris, n_objects, n_materials, n_lights, n_textures;
   uint32_t n_smem_nodes;    // min(n_wide, kSmemNodes)
   uint32_t tables_in_smem;  // objects/materials/lights fit the staged tables
@@ -159,14 +158,15 @@ struct CameraParams {
 
 // Per-chunk control block in device memory (zeroed before each chunk).
 struct ChunkCtl {
-  uint32_t ray_count[kMaxPasses + 2];     // entries in the ray queue consumed by pass k
-  uint32_t shadow_count[kMaxPasses + 2];  // shadow tasks produced by pass k
-  uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors
+  uint32_t ray_slabs[kMaxPasses + 2];     // slabs reserved in the ray queue that pass k consumes
+  uint32_t hit_slabs[kMaxPasses + 2];     // slabs of shaded Diffuse / Plastic hits produced by pass k (hit queue)
+  uint32_t shadow_slabs[kMaxPasses + 2];  // slabs of hits whose shadow rays have to walk a tree (walk queue)
+  uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors, in slabs
+  uint32_t hit_cursor[kMaxPasses + 2];
   uint32_t shadow_cursor[kMaxPasses + 2];
-  // split shadow pipeline: low word = deferred hits, high word = (hit, light) pairs queued for a tree walk
-  unsigned long long deferred_walk_count[kMaxPasses + 2];
-  uint32_t walk_cursor[kMaxPasses + 2];
-  uint32_t isect_cursor[kMaxPasses + 2];  // split trace schedule: intersect_kernel's work cursor
+  uint32_t ray_items[kMaxPasses + 2];     // entries in those slabs (statistics; one atomic per warp per launch)
+  uint32_t hit_items[kMaxPasses + 2];
+  uint32_t shadow_items[kMaxPasses + 2];
   uint32_t overflow;
   uint32_t pad_[3];
 };
@@ -177,26 +177,35 @@ struct KernelCounters {  // RH_FLAG_COUNT only
 };
 struct FrameCounters {
   unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;
+  unsigned long long shaded_hits;    // Diffuse / Plastic hits: each is one accumDiffuse fold over all lights (RayHs.hs:89-97)
   unsigned long long shadow_culled;  // (hit, light) pairs with l.n <= 0: Lambert term is exactly 0, query skipped
+  unsigned long long shadow_walk_pairs;  // (hit, light) pairs that went to a tree walk
   unsigned long long exact_walks;    // RH_FLAG_COUNT: shadow rays that took the exact (double box) walk
   unsigned long long max_walk_nodes; // RH_FLAG_COUNT: most node records one shadow ray visited
   unsigned long long exact_closest;  // RH_FLAG_COUNT: closest-hit rays that took the exact walk
   unsigned long long max_closest_nodes;
-  KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow_kernel
+  unsigned long long deep_pushes;    // RH_FLAG_COUNT: stack entries that went beyond the shared-memory short stack
+  KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow kernels
 };
 
+// Queues are arrays of slabs of kSlab entries; slab s holds fill[s] <= kSlab valid entries at [s * kSlab ..).  A warp
+// reserves a slab with one atomic and fills it privately; the consumer claims whole slabs.
 // SoA-of-16-byte planes so that a warp's compacted pushes are fully coalesced.
 // Ray queue: 4 planes (ox,oy) (oz,dx) (dy,dz) (weight, bits).
 // bits = sample | depth << 32 | kind << 40 | material << 48.
 struct RayQueue {
   double2* plane;  // plane k at plane + k*capacity
-  uint32_t capacity;
+  uint32_t* fill;  // entries per slab
+  uint32_t capacity;  // entries (a multiple of kSlab)
 };
-// Shadow queue: 5 planes (px,py) (pz,nx) (ny,nz) (cr,cg) (cb,w) + sample ids (bit 31 = ambient term) + lit flags.
+// Hit queue (every shaded Diffuse / Plastic hit of a pass) and walk queue (the hits with a light whose shadow ray has
+// to walk a tree): 5 planes (px,py) (pz,nx) (ny,nz) (cr,cg) (cb,w) + sample ids (bit 31 = ambient term) + two words.
 struct ShadowQueue {
   double2* plane;
   uint32_t* sample;
-  uint32_t* lit;  // lit_flags of the hit triangle, 0 for other hits
+  uint32_t* walk;     // walk queue: bit l = the shadow ray towards light l has to walk a tree; hit queue: the lit-triangle flags of the hit triangle
+  uint32_t* settled;  // walk queue: bit l = light l adds nothing (l.n <= 0, or a plane / sphere occludes)
+  uint32_t* fill;
   uint32_t capacity;
 };
 
@@ -218,10 +227,14 @@ struct ChunkParams {
   int32_t exact_boxes;    // RH_FLAG_EXACT_BOXES: double slab test for every ray (validation)
   int32_t no_light_maps;  // RH_FLAG_NO_LIGHT_MAPS: shadow rays ignore the lights' cube maps (validation, A/B)
   const void* offsets;    // device
+  uint32_t offset_linear; // f64 pairs in work-item order: pair of item i at offsets[offset_base + i] (bulk-copy staging)
+  uint32_t pad5_;
+  unsigned long long offset_base;
   unsigned long long offset_seed;  // RH_OFFSETS_SPLITMIX64
   double* accum;          // 3 planes of accum_stride (r,g,b), chunk-local sample order
   uint32_t accum_stride;
-  uint32_t pad_;
+  uint32_t deep_stride;   // threads the deep-stack scratch has a column for (>= grid * block of every launch)
+  uint2* deep_stack;      // [entry][thread]: stack entries beyond the short stack, and the exact walk's whole stack
   int2* hit_ids;          // shard-compact [pixel][spp] (object, tri) or null
   uint8_t* rgb;           // shard-compact framebuffer (or null with peer frames)
   uint8_t* peer[kMaxPeers];  // RH_FLAG_PEER_FRAMES: full frames of all shards
@@ -230,31 +243,23 @@ struct ChunkParams {
   ChunkCtl* ctl;
   FrameCounters* counters;
   RayQueue q_in, q_out;
-  ShadowQueue q_shadow;
-  // split shadow pipeline (classify -> walk -> fold)
-  uint2* walk_q;          // (shadow-queue item, light) pairs whose ray enters a tree's root box
-  uint32_t* deferred_q;   // shadow-queue items with at least one queued pair
-  uint8_t* pair_flags;    // [item * n_lights + light]: 1 = the pair adds nothing (l.n <= 0 or occluded)
-  uint32_t walk_capacity;
-  uint32_t pad3_;
-  double4* hits;          // split trace schedule: (t, u, v, slot | obj << 32) per work item of the pass
+  ShadowQueue q_hits, q_shadow;
 };
 
 // Launchers (kernels.cu).  `count` selects the instrumented instantiation (box/tri counters).
-// split: intersect_kernel (closest hits with per-lane refill -> P.hits) then trace_kernel<.., true> (shade from the records)
-void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, bool split, int grid, void* stream);
-// split: classify -> walk -> fold (3 launches) instead of one pooled kernel; only when shadow_split_possible(S)
-void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream);
-bool shadow_split_possible(const SceneView& S);
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
+// classify_kernel, then the walks of the hits it queued — refill: the per-lane-refill kernel (incoherent rays) instead of
+// the pooled one (coherent rays).  Returns the number of launches.
+int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream);
 void launch_resolve(const ChunkParams& P, void* stream);
 void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
                          void* stream);
 int configure_kernels();  // opt in to > 48 KB dynamic shared memory; returns a cudaError_t
-int trace_blocks_per_sm(bool count);
-int shadow_blocks_per_sm(bool count);
+int max_threads_per_launch(int n_sms);  // largest grid * block of the trace / shadow kernels (sizes the deep-stack scratch)
 // micro-benchmarks
 void launch_gather_bench(const double2* buf, uint64_t n_records, uint32_t loads_per_thread, double2* sink, int grid, int block,
                          void* stream);
+void launch_stream_bench(const double2* buf, uint64_t n_elems, double2* sink, int grid, int block, void* stream);
 void launch_dfma_bench(double* sink, int iters, int grid, int block, void* stream);
 
 }  // namespace rhd

@@ -18,6 +18,7 @@
 #include <string>
 #include <tuple>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -515,6 +516,24 @@ struct SplitMix64 {
   double uniform(double a, double b) { return a + (b - a) * uniform01(); }
 };
 
+// SplitMix64 is counter-based (state after k steps = seed + k * gamma), so any stretch of the stream can be produced on
+// its own: the generators below fill [first_pixel, first_pixel + n_pixels) of the full-frame stream, on several threads.
+template <class T>
+void sample_offsets_at(uint64_t seed, uint64_t first_pixel, uint64_t n_pixels, int spp, T* out) {
+  const uint64_t n = n_pixels * (uint64_t)spp * 2, first = first_pixel * (uint64_t)spp * 2;
+  const unsigned threads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min(32u, std::max(1u, std::thread::hardware_concurrency())), n >> 20));
+  auto work = [=](uint64_t b, uint64_t e) {
+    SplitMix64 rng(seed + (first + b) * 0x9E3779B97F4A7C15ull);
+    for (uint64_t i = b; i < e; i++) out[i] = (T)(rng.uniform01() - 0.5);
+  };
+  if (threads == 1) {
+    work(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, n * t / threads, n * (t + 1) / threads);
+  for (std::thread& t : pool) t.join();
+}
 // ------------------------------------------------------------------ pack I/O
 const char kPackMagic[8] = {'R', 'H', 'P', 'K', '0', '0', '0', '1'};
 template <class T> void wr(FILE* f, const T* p, size_t n) { if (n && fwrite(p, sizeof(T), n, f) != n) bad("pack write failed"); }
@@ -768,15 +787,10 @@ void rh_loaded_destroy(rh_loaded* l) { delete l; }
 // RayHs.hs:173-188: per pixel 2*spp uniform [0,1) draws, x before y, pair = (x-0.5, y-0.5).
 // The reference's StdGen algorithm is un-pinned (rayhs.cabal: random -any);
 // offsets are INPUTS to the render call, so any host stream of this shape is valid.
-void rh_sample_offsets_f64(uint64_t seed, uint64_t n_pixels, int spp, double* out) {
-  SplitMix64 rng(seed);
-  uint64_t n = n_pixels * (uint64_t)spp * 2;
-  for (uint64_t i = 0; i < n; i++) out[i] = rng.uniform01() - 0.5;
-}
-void rh_sample_offsets_f32(uint64_t seed, uint64_t n_pixels, int spp, float* out) {
-  SplitMix64 rng(seed);
-  uint64_t n = n_pixels * (uint64_t)spp * 2;
-  for (uint64_t i = 0; i < n; i++) out[i] = (float)(rng.uniform01() - 0.5);
+void rh_sample_offsets_f64(uint64_t seed, uint64_t n_pixels, int spp, double* out) { sample_offsets_at(seed, 0, n_pixels, spp, out); }
+void rh_sample_offsets_f32(uint64_t seed, uint64_t n_pixels, int spp, float* out) { sample_offsets_at(seed, 0, n_pixels, spp, out); }
+void rh_sample_offsets_f64_at(uint64_t seed, uint64_t first_pixel, uint64_t n_pixels, int spp, double* out) {
+  sample_offsets_at(seed, first_pixel, n_pixels, spp, out);
 }
 
 // Image.hs:60-75: "P3\nW H\n255\n", rows joined by "\n", each pixel "R G B" + two spaces, no trailing newline.

@@ -1,18 +1,27 @@
 // kernels.cu — sm_100a kernels of the RayHs ray-casting path.
 //
-//   trace_kernel   K1/K4: camera-ray generation (pass 0) or queued secondary rays (pass >= 1),
-//                  closest hit through the object list + wide-BVH traversal, shading, and
-//                  warp-ballot compaction of the shadow tasks and child rays it emits (K2, K5).
-//   shadow_kernel  K3: per shaded hit, fold over the lights with an any-hit query each.
-//   resolve_kernel K6: average the samples of a pixel, toIntC, coalesced RGB8 store.
-//   deinterleave   K7: band re-assembly after the all-gather.
+//   trace_kernel          K1/K2/K4/K5: camera-ray generation (pass 0) or queued secondary rays (pass >= 1), closest hit
+//                         through the object list + wide-BVH traversal, shading.  A Diffuse / Plastic hit folds its
+//                         lights on the spot (accumDiffuse, RayHs.hs:89-97) unless some light's shadow ray has to walk
+//                         a tree: only those hits are queued, with the lights to walk and the lights already settled.
+//   shadow_pooled_kernel  K3 for coherent rays: the queued hits of a slab, their tree walks pooled per light into
+//                         warp-local rounds of 32, then the fold.
+//   shadow_refill_kernel  K3 for incoherent rays (triangle soups): one queued hit per lane, a lane whose ray has ended
+//                         takes its next light or the next hit while its neighbours keep walking.
+//   shadow_simple_kernel  K3 for scenes with more than 32 lights.
+//   resolve_kernel        K6: average the samples of a pixel, toIntC, coalesced RGB8 store (or peer stores).
+//   deinterleave          K7: band re-assembly after the all-gather.
 //
-// All arithmetic is IEEE double in the reference's operation order and this file is compiled
-// with -fmad=false (GHC emits no fused multiply-adds), so every value the reference defines
-// (t, u, v, hit point, normal, colour) is computed bit-identically; only atan/acos (sphere
-// uv, Geometry.hs:96) go through CUDA's libm instead of the host's.  No tensor cores: the
-// path is branchy gather-bound traversal.  Each device function cites the reference lines
-// it restates; nothing here is shared with oracle/.
+// All arithmetic is IEEE double in the reference's operation order and this file is compiled with -fmad=false (GHC
+// emits no fused multiply-adds), so every value the reference defines (t, u, v, hit point, normal, colour) is computed
+// bit-identically; only atan/acos (sphere uv, Geometry.hs:96) go through CUDA's libm instead of the host's.  No tensor
+// cores: the path is branchy gather-bound traversal.  Each device function cites the reference lines it restates;
+// nothing here is shared with oracle/.
+//
+// B200 specifics: persistent warps (one block per SM); the traversal stack is a per-thread column of SHARED memory
+// (8-byte entries), never local memory; queues are arrays of 128-entry slabs that a warp reserves or claims with one
+// atomic; the trace kernel's next batch of queue entries / sample offsets arrives by bulk async copy
+// (cp.async.bulk.shared::cluster.global + mbarrier, SASS: UBLKCP / SYNCS) while the current batch is traced.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -67,21 +76,74 @@ struct Ray {
 __device__ __forceinline__ V3 rayAt(const Ray& r, double t) { return r.o + mul(t, r.d); }  // Geometry.hs:29
 __device__ __forceinline__ Ray rayEps(V3 p, V3 n) { return Ray{p + mul(kEps, n), n}; }      // Geometry.hs:36
 
+
 // ------------------------------------------------------------------ shared-memory staging
+// Top tree levels, object / material / light tables, and the occluder tables of shadowIntersection with what the
+// light fold needs per (light, tree root): which outer side of the root box the light lies on and the light's cube map.
 struct SmemTables {
   WideNode32 nodes[kSmemNodes];
   DObject objects[kSmemObjects];
   rh_material materials[kSmemObjects];
   rh_light lights[kSmemLights];
+  OccPlane planes[kOccPlanes];
+  OccSphere spheres[kOccSpheres];
+  // Root boxes (the float cull boxes of the mesh super-roots and of the sphere tree, padded by 2e-6 + 1e-12 |x|) and,
+  // per (light, root), on which outer side of each slab the light lies: bit a = below lo[a], bit 3 + a = above hi[a].
+  double rootbox[kOccMeshes + 1][6];
+  uint32_t mesh_roots[kOccMeshes + 1];  // the sphere tree's super-root follows the meshes'
+  uint32_t light_map[kFastLights][kOccMeshes + 1];  // number of the pair's cube map in SceneView::light_maps, or kEmpty
+  uint8_t light_side[kFastLights][kOccMeshes + 1];
+  uint8_t pad_[4];
+  // Plane sides (see fold_lights): per plane the margin terms m0 + m1 * |p|_1 a point needs to count as strictly on one
+  // side, and per point light the planes it lies strictly in front of (pn.(L - pp) > margin) / behind.
+  double plane_margin[kOccPlanes][2];
+  uint32_t light_front[kFastLights], light_behind[kFastLights];
+  uint8_t pad2_[32];
 };
 static_assert(sizeof(rh_material) == 96 && sizeof(rh_light) == 64, "table record sizes");
-static_assert(sizeof(SmemTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
-extern __shared__ __align__(16) unsigned char rh_smem[];  // SmemTables, then per-warp pools (shadow kernel)
+static_assert(sizeof(SmemTables) % 16 == 0, "per-warp regions follow the tables in dynamic shared memory");
+// What the shadow kernels stage: top tree levels, lights, tree roots.
+struct WalkTables {
+  WideNode32 nodes[kSmemNodes];
+  rh_light lights[kSmemLights];
+  uint32_t mesh_roots[kOccMeshes + 4];
+};
+static_assert(sizeof(WalkTables) % 16 == 0, "per-warp regions follow the tables in dynamic shared memory");
+extern __shared__ __align__(128) unsigned char rh_smem[];
 
 __device__ __forceinline__ void copy16(void* dst, const void* src, uint32_t bytes) {
   uint4* d = (uint4*)dst;
   const uint4* s = (const uint4*)src;
   for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// Traversal stack of one thread: entry k < kShortStack in the thread's column of shared memory, deeper entries in its
+// column of the global scratch area (ChunkParams::deep_stack).  Entry = (subtree reference, float entry distance).
+struct Stack {
+  uint2* col;    // &short_stack[0][threadIdx.x]; entry k at col[k * stride]
+  uint2* deep;   // &deep_stack[0][global thread]; entry k at deep[(k - kShortStack) * deep_stride]
+  uint32_t stride, deep_stride;
+  __device__ __forceinline__ void push(int& sp, uint32_t ref, float tmin) {
+    const uint2 e = make_uint2(ref, __float_as_uint(tmin));
+    if (sp < kShortStack) col[sp * stride] = e;
+    else deep[(size_t)(sp - kShortStack) * deep_stride] = e;
+    sp++;
+  }
+  __device__ __forceinline__ uint2 pop(int& sp) {
+    --sp;
+    return sp < kShortStack ? col[sp * stride] : deep[(size_t)(sp - kShortStack) * deep_stride];
+  }
+  // the exact walk keeps its whole stack in the global column ((reference, first slot) pairs)
+  __device__ __forceinline__ void push_deep(int& sp, uint32_t ref, uint32_t first) { deep[(size_t)(sp++) * deep_stride] = make_uint2(ref, first); }
+  __device__ __forceinline__ uint2 pop_deep(int& sp) { return deep[(size_t)(--sp) * deep_stride]; }
+};
+__device__ __forceinline__ Stack make_stack(void* smem_columns, uint32_t block_threads, const ChunkParams& P) {
+  Stack s;
+  s.col = reinterpret_cast<uint2*>(smem_columns) + threadIdx.x;
+  s.stride = block_threads;
+  s.deep = P.deep_stack + (size_t)blockIdx.x * block_threads + threadIdx.x;
+  s.deep_stride = P.deep_stride;
+  return s;
 }
 
 struct Ctx {
@@ -92,6 +154,58 @@ struct Ctx {
   const rh_light* lights;
 };
 
+// Root boxes and light sides of the staged occluder tables (threads 0 .. n_roots * n_lights of the block).
+__device__ __forceinline__ void stage_roots(SmemTables& sm, const SceneView& S) {
+  const uint32_t n_meshes = S.n_occ_meshes, n_lights = S.n_lights;
+  const uint32_t n_roots = n_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  if (threadIdx.x < n_roots) {
+    const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : S.sphere_root;
+    sm.mesh_roots[threadIdx.x] = root;
+    const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
+    for (int a = 0; a < 3; a++) {
+      const double lo = (double)fb[a] + S.center[a], hi = (double)fb[3 + a] + S.center[a];  // world coordinates
+      sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
+      sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_roots * n_lights) {
+    const uint32_t li = threadIdx.x / n_roots, m = threadIdx.x % n_roots;
+    uint32_t side = 0;
+    if (sm.lights[li].kind != RH_LIGHT_DIRECTIONAL)
+      for (int a = 0; a < 3; a++) {
+        if (sm.lights[li].vec[a] < sm.rootbox[m][a]) side |= 1u << a;
+        if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
+      }
+    sm.light_side[li][m] = (uint8_t)side;
+    sm.light_map[li][m] = (S.light_map_index && m < n_meshes) ? S.light_map_index[li * kOccMeshes + m] : kEmpty;
+  }
+  // plane sides: |pn.v| <= |pn|_1 |v|_1 bounds both the 1e-6 step from a hit to its shadow-ray origin and every rounding
+  if (threadIdx.x < S.n_occ_planes) {
+    const OccPlane& pl = sm.planes[threadIdx.x];
+    const double n1 = fabs(pl.n[0]) + fabs(pl.n[1]) + fabs(pl.n[2]), p1 = fabs(pl.p[0]) + fabs(pl.p[1]) + fabs(pl.p[2]);
+    sm.plane_margin[threadIdx.x][0] = n1 * (1e-5 + 1e-12 * p1);
+    sm.plane_margin[threadIdx.x][1] = n1 * 1e-12;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_lights) {
+    const rh_light& L = sm.lights[threadIdx.x];
+    uint32_t front = 0, behind = 0;
+    if (L.kind != RH_LIGHT_DIRECTIONAL) {
+      const V3 lp = ld3(L.vec);
+      const double l1 = fabs(lp.x) + fabs(lp.y) + fabs(lp.z);
+      for (uint32_t k = 0; k < S.n_occ_planes; k++) {
+        const double f = dot(ld3(sm.planes[k].n), lp - ld3(sm.planes[k].p));
+        const double m = sm.plane_margin[k][0] + sm.plane_margin[k][1] * l1;
+        if (f > m) front |= 1u << k;
+        if (f < -m) behind |= 1u << k;
+      }
+    }
+    sm.light_front[threadIdx.x] = front;
+    sm.light_behind[threadIdx.x] = behind;
+  }
+}
+
 __device__ __forceinline__ void stage_tables(SmemTables& sm, const SceneView& S, Ctx& cx) {
   copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
   if (S.tables_in_smem) {
@@ -99,19 +213,40 @@ __device__ __forceinline__ void stage_tables(SmemTables& sm, const SceneView& S,
     copy16(sm.materials, S.materials, S.n_materials * (uint32_t)sizeof(rh_material));
     copy16(sm.lights, S.lights, S.n_lights * (uint32_t)sizeof(rh_light));
   }
+  if (S.shadow_fast) {
+    copy16(sm.planes, S.occ_planes, S.n_occ_planes * (uint32_t)sizeof(OccPlane));
+    copy16(sm.spheres, S.occ_spheres, S.n_occ_spheres * (uint32_t)sizeof(OccSphere));
+    if (!S.tables_in_smem) copy16(sm.lights, S.lights, S.n_lights * (uint32_t)sizeof(rh_light));
+  }
+  __syncthreads();
+  if (S.shadow_fast) stage_roots(sm, S);
   __syncthreads();
   cx.S = &S;
   cx.sm_nodes = sm.nodes;
   cx.objects = S.tables_in_smem ? sm.objects : S.objects;
   cx.materials = S.tables_in_smem ? sm.materials : S.materials;
-  cx.lights = S.tables_in_smem ? sm.lights : S.lights;
+  cx.lights = (S.tables_in_smem || S.shadow_fast) ? sm.lights : S.lights;
+}
+
+// Shadow kernels: top tree levels, lights (when they fit) and the roots of the occluding trees.
+__device__ __forceinline__ void stage_walk_tables(WalkTables& sm, const SceneView& S, Ctx& cx) {
+  copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
+  const bool lights_fit = S.n_lights <= (uint32_t)kSmemLights;
+  if (lights_fit) copy16(sm.lights, S.lights, S.n_lights * (uint32_t)sizeof(rh_light));
+  if (S.n_occ_meshes <= (uint32_t)kOccMeshes && threadIdx.x < S.n_occ_meshes) sm.mesh_roots[threadIdx.x] = S.occ_meshes[threadIdx.x];
+  __syncthreads();
+  cx.S = &S;
+  cx.sm_nodes = sm.nodes;
+  cx.objects = S.objects;  // sphere-tree leaves only
+  cx.materials = S.materials;
+  cx.lights = lights_fit ? sm.lights : S.lights;
 }
 
 // ------------------------------------------------------------------ counters
 template <bool COUNT>
 struct Cnt {
-  unsigned long long box, tri, prim, nodes, shade, texel;
-  __device__ __forceinline__ void zero() { box = tri = prim = nodes = shade = texel = 0; }
+  unsigned long long box, tri, prim, nodes, shade, texel, deep;
+  __device__ __forceinline__ void zero() { box = tri = prim = nodes = shade = texel = deep = 0; }
 };
 template <>
 struct Cnt<false> {
@@ -132,6 +267,9 @@ __device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* f
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
       if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst[k], v);
     }
+    unsigned long long v = cnt.deep;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&fc->deep_pushes, v);
   }
 }
 
@@ -371,6 +509,49 @@ __device__ __forceinline__ bool test_sphere_leaf(const Ctx& cx, uint32_t first, 
   return false;
 }
 
+// One inner node of the cull tree: both child boxes against the float ray; the nearer surviving child becomes `ref`,
+// the farther one is stacked with its entry distance.  False when neither survives (the caller pops).
+template <bool COUNT>
+__device__ __forceinline__ bool node_step(const Ctx& cx, uint32_t& ref, const RayF& f, float fb, Stack& st, int& sp,
+                                          Cnt<COUNT>& cnt) {
+  const float4* np = ref < cx.S->n_smem_nodes ? (const float4*)&cx.sm_nodes[ref] : (const float4*)&cx.S->wide32[ref];
+  const float4 b0 = np[0], b1 = np[1], b2 = np[2];
+  const uint2 cw = *(const uint2*)(np + 3);  // child0, child1
+  RH_CNT(nodes, 1);
+  bool h0 = false, h1 = false;
+  float tm0 = 0, tm1 = 0;
+  if (cw.x != kEmpty) {
+    RH_CNT(box, 1);
+    h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > fb);
+  }
+  if (cw.y != kEmpty) {
+    RH_CNT(box, 1);
+    h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > fb);
+  }
+  if (h0 && h1) {
+    if constexpr (COUNT) {
+      if (sp >= kShortStack) cnt.deep += 1;
+    }
+    if (tm1 < tm0) {
+      st.push(sp, cw.x, tm0);
+      ref = cw.y;
+    } else {
+      st.push(sp, cw.y, tm1);
+      ref = cw.x;
+    }
+    return true;
+  }
+  if (h0) {
+    ref = cw.x;
+    return true;
+  }
+  if (h1) {
+    ref = cw.y;
+    return true;
+  }
+  return false;
+}
+
 // KDTree.hs:96-107 rayInter, ordered and pruned, culling with the conservative float boxes.
 // Subtrees are skipped only when their entry distance exceeds `bound` (the best t so far times
 // 1 + 1e-7, or the light distance), both when they are first met and again when they are popped.
@@ -380,75 +561,42 @@ __device__ __forceinline__ bool test_sphere_leaf(const Ctx& cx, uint32_t first, 
 // SPHERES: the tree is the top-level sphere tree (leaves hold object indices) instead of a mesh tree.
 template <bool COUNT, class Sink, bool SPHERES = false>
 __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray& r, const RayF& f, double& bound, Sink& sink,
-                                         uint4* stack, Cnt<COUNT>& cnt, bool skip_emitters = false) {
+                                         Stack& st, Cnt<COUNT>& cnt, bool skip_emitters = false) {
   int sp = 0;
-  uint32_t ref = root, first = 0;
+  uint32_t ref = root;
   const rh_tri* tris = cx.S->tris;
-  const uint32_t n_smem = cx.S->n_smem_nodes;
   for (;;) {
     while (!(ref & kLeafBit)) {
-      const float4* np = ref < n_smem ? (const float4*)&cx.sm_nodes[ref] : (const float4*)&cx.S->wide32[ref];
-      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
-      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
-      RH_CNT(nodes, 1);
       const float fb = __double2float_ru(bound);
-      bool h0 = false, h1 = false;
-      float tm0 = 0, tm1 = 0;
-      if (cw.x != kEmpty) {
-        RH_CNT(box, 1);
-        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > fb);
-      }
-      if (cw.y != kEmpty) {
-        RH_CNT(box, 1);
-        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > fb);
-      }
-      if (h0 && h1) {
-        if (tm1 < tm0) {
-          stack[sp++] = make_uint4(cw.x, cw.z, __float_as_uint(tm0), 0);
-          ref = cw.y;
-          first = cw.w;
-        } else {
-          stack[sp++] = make_uint4(cw.y, cw.w, __float_as_uint(tm1), 0);
-          ref = cw.x;
-          first = cw.z;
-        }
-      } else if (h0) {
-        ref = cw.x;
-        first = cw.z;
-      } else if (h1) {
-        ref = cw.y;
-        first = cw.w;
-      } else {
-        uint4 e;
-        do {
-          if (sp == 0) return false;
-          e = stack[--sp];
-        } while (__uint_as_float(e.z) > fb);
-        ref = e.x;
-        first = e.y;
-      }
+      if (node_step<COUNT>(cx, ref, f, fb, st, sp, cnt)) continue;
+      uint2 e;
+      do {
+        if (sp == 0) return false;
+        e = st.pop(sp);
+      } while (__uint_as_float(e.y) > fb);
+      ref = e.x;
     }
+    const uint32_t first = ref & kLeafFirstMask, count = ((ref >> kLeafCountShift) & (kLeafMaxCount - 1)) + 1;
     if constexpr (SPHERES) {
-      if (test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, skip_emitters, cnt)) return true;
+      if (test_sphere_leaf<COUNT>(cx, first, count, r, sink, bound, skip_emitters, cnt)) return true;
     } else {
-      if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt)) return true;
+      if (test_leaf<COUNT>(tris, first, count, r, sink, bound, cnt)) return true;
     }
     const float fb = __double2float_ru(bound);
-    uint4 e;
+    uint2 e;
     do {
       if (sp == 0) return false;
-      e = stack[--sp];
-    } while (__uint_as_float(e.z) > fb);
+      e = st.pop(sp);
+    } while (__uint_as_float(e.y) > fb);
     ref = e.x;
-    first = e.y;
   }
 }
 
-// The same walk with the reference's own double slab test (GHC min/max NaN semantics included):
-// rays with a zero direction component (centre row/column of the image) and
-// RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line.
+// The same walk over the reference's own tree with the reference's own double slab test (GHC min/max NaN semantics
+// included): rays with a zero direction component (centre row/column of the image), far origins, and
+// RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line; its stack is the thread's global column.
 template <bool COUNT, class Sink, bool SPHERES = false>
-__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, uint4* stack,
+__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, Stack& st,
                                             Cnt<COUNT>& cnt, bool skip_emitters = false) {
   const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
   int sp = 0;
@@ -459,8 +607,8 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       const double2* np = (const double2*)&cx.S->wide[ref];
       const double2 b0 = np[0], b1 = np[1], b2 = np[2], b3 = np[3], b4 = np[4], b5 = np[5];
       const uint4 cw = *(const uint4*)(np + 6);
-      const uint32_t refine = *(const uint32_t*)(np + 7);  // bit c: child c's box is a culling refinement inside a reference
-                                                           // leaf, not a box the reference tests: it always passes here
+      const uint32_t refine = *(const uint32_t*)(np + 7);  // bit c: child c's box is not a box the reference tests
+                                                           // (sphere tree): it always passes here
       RH_CNT(nodes, 2);  // a 128-byte record = two 64-byte units
       bool h0 = false, h1 = false;
       double tm0 = 0, tm1 = 0;
@@ -474,11 +622,11 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       }
       if (h0 && h1) {
         if (tm1 < tm0) {
-          stack[sp++] = make_uint4(cw.x, cw.z, 0, 0);
+          st.push_deep(sp, cw.x, cw.z);
           ref = cw.y;
           first = cw.w;
         } else {
-          stack[sp++] = make_uint4(cw.y, cw.w, 0, 0);
+          st.push_deep(sp, cw.y, cw.w);
           ref = cw.x;
           first = cw.z;
         }
@@ -500,7 +648,7 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       if (test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt, cx.S->exact_index)) return true;
     }
     if (sp == 0) return false;
-    const uint4 e = stack[--sp];
+    const uint2 e = st.pop_deep(sp);
     ref = e.x;
     first = e.y;
   }
@@ -543,8 +691,7 @@ __device__ __forceinline__ bool sphere_time(const Ray& r, const DObject& ob, dou
 
 // RayHs.hs:58-71 closestIntersection over the object list.
 template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, uint4* stack,
-                                            Cnt<COUNT>& cnt) {
+__device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool exact, Closest& best, Stack& st, Cnt<COUNT>& cnt) {
   const RayF f = make_rayf(r, *cx.S);
   best.t = __longlong_as_double(0x7ff0000000000000LL);
   best.u = best.v = 0;
@@ -563,9 +710,9 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
       best.cur_obj = (int)i;
       double bound = best.t * kPruneSlack;
       if (exact)
-        traverse_exact<COUNT>(cx, root, r, bound, best, stack, cnt);
+        traverse_exact<COUNT>(cx, root, r, bound, best, st, cnt);
       else
-        traverse<COUNT>(cx, root, r, f, bound, best, stack, cnt);
+        traverse<COUNT>(cx, root, r, f, bound, best, st, cnt);
     } else {
       double time;
       RH_CNT(prim, 1);
@@ -579,16 +726,16 @@ __device__ __forceinline__ void closest_hit(const Ctx& cx, const Ray& r, bool ex
   if (sphere_root != kEmpty) {
     double bound = best.t * kPruneSlack;
     if (exact)
-      traverse_exact<COUNT, Closest, true>(cx, sphere_root, r, bound, best, stack, cnt);
+      traverse_exact<COUNT, Closest, true>(cx, sphere_root, r, bound, best, st, cnt);
     else
-      traverse<COUNT, Closest, true>(cx, sphere_root, r, f, bound, best, stack, cnt);
+      traverse<COUNT, Closest, true>(cx, sphere_root, r, f, bound, best, st, cnt);
   }
 }
 
 // RayHs.hs:74-87 shadowIntersection: true when some non-emitter object has a hit in front of the light.
+// (General form over the object list; the kernels for <= 32 lights use the compact occluder tables instead.)
 template <bool COUNT>
-__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, uint4* stack,
-                                         Cnt<COUNT>& cnt) {
+__device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact, const rh_light& L, Stack& st, Cnt<COUNT>& cnt) {
   const RayF f = make_rayf(r, *cx.S);
   AnyHit sink;
   sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
@@ -608,8 +755,8 @@ __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact
       const uint32_t root = ob.root;
       if (root == kEmpty) continue;
       double bound = far;
-      const bool hit = exact ? traverse_exact<COUNT>(cx, root, r, bound, sink, stack, cnt)
-                             : traverse<COUNT>(cx, root, r, f, bound, sink, stack, cnt);
+      const bool hit = exact ? traverse_exact<COUNT>(cx, root, r, bound, sink, st, cnt)
+                             : traverse<COUNT>(cx, root, r, f, bound, sink, st, cnt);
       if (hit) return true;
     } else {
       double time;
@@ -620,8 +767,8 @@ __device__ __forceinline__ bool occluded(const Ctx& cx, const Ray& r, bool exact
   }
   if (sphere_root != kEmpty) {
     double bound = far;
-    return exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, stack, cnt, true)
-                 : traverse<COUNT, AnyHit, true>(cx, sphere_root, r, f, bound, sink, stack, cnt, true);
+    return exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, st, cnt, true)
+                 : traverse<COUNT, AnyHit, true>(cx, sphere_root, r, f, bound, sink, st, cnt, true);
   }
   return false;
 }
@@ -687,29 +834,71 @@ __device__ __noinline__ V3 color_at(const Ctx& cx, const rh_material& m, double 
   return mul(ly, cx1) + mul(1 - ly, cx0);
 }
 
-// ------------------------------------------------------------------ queues (warp-aggregated compaction)
+// ------------------------------------------------------------------ queues: slabs, warp-aggregated compaction
 __device__ __forceinline__ uint64_t pack_bits(uint32_t sample, int depth, int kind, uint32_t mat) {
   return (uint64_t)sample | ((uint64_t)(depth & 0xff) << 32) | ((uint64_t)(kind & 0xff) << 40) | ((uint64_t)(mat & 0xffff) << 48);
 }
 
-__device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint64_t bits, const RayQueue& q, uint32_t* counter,
-                                         uint32_t* overflow, uint32_t lane) {
+// A warp's open slab of an output queue: entries [base, base + used) are written.  One per warp, in shared memory.
+struct SlabWriter {
+  uint32_t base, used, pushed;
+  __device__ __forceinline__ void init() { base = kEmpty; used = 0; pushed = 0; }
+};
+
+// Slots for the lanes of ballot `m` (all 32 lanes call this, converged, with m != 0): the open slab first, then a new
+// one reserved with ONE atomic on the queue's slab counter — one global atomic per kSlab entries instead of one per
+// push.  The slab a push completes gets its fill count here; the last, partly filled one at slab_close.  Returns
+// kEmpty for an entry that does not fit the queue (overflow is flagged; the host re-renders with larger queues).
+__device__ __forceinline__ uint32_t slab_reserve(SlabWriter& w, unsigned m, uint32_t lane, uint32_t* slab_counter, uint32_t* fill,
+                                                 uint32_t capacity, uint32_t* overflow) {
+  // `w` lives in the warp's shared memory: every lane reads it, then lane 0 writes the new state
+  const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane) - 1));
+  __syncwarp();  // lane 0's update of the previous push is visible
+  const uint32_t base = w.base, used = w.used;
+  const uint32_t room = (base == kEmpty) ? 0u : kSlab - used;
+  __syncwarp();  // every lane has read the state before lane 0 replaces it
+  if (n <= room) {
+    if (lane == 0) {
+      w.used = used + n;
+      w.pushed += n;
+    }
+    return base + used + rank;
+  }
+  uint32_t ns = 0;
+  if (lane == 0) {
+    if (base != kEmpty) fill[base / kSlab] = kSlab;  // this push fills the open slab to the brim
+    ns = atomicAdd(slab_counter, 1u);
+  }
+  ns = __shfl_sync(kFull, ns, 0);
+  const bool full = ns >= capacity / kSlab;
+  if (lane == 0) {
+    if (full) *overflow = 1;
+    w.base = full ? kEmpty : ns * kSlab;
+    w.used = full ? 0u : n - room;
+    w.pushed += n;
+  }
+  if (rank < room) return base + used + rank;
+  return full ? kEmpty : ns * kSlab + (rank - room);
+}
+__device__ __forceinline__ void slab_close(const SlabWriter& w, uint32_t lane, uint32_t* fill, uint32_t* items) {
+  __syncwarp();
+  if (lane == 0) {
+    if (w.base != kEmpty) fill[w.base / kSlab] = w.used;
+    if (w.pushed) atomicAdd(items, w.pushed);
+  }
+}
+
+__device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint64_t bits, const RayQueue& q, SlabWriter& sw,
+                                         uint32_t* slab_counter, uint32_t* overflow, uint32_t lane) {
   const unsigned m = __ballot_sync(kFull, has);
   if (!m) return;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(kFull, base, 0);
-  if (has) {
-    const uint32_t idx = base + __popc(m & ((1u << lane) - 1));
-    if (idx < q.capacity) {
-      const size_t cap = q.capacity;
-      q.plane[idx] = make_double2(r.o.x, r.o.y);
-      q.plane[cap + idx] = make_double2(r.o.z, r.d.x);
-      q.plane[2 * cap + idx] = make_double2(r.d.y, r.d.z);
-      q.plane[3 * cap + idx] = make_double2(w, __longlong_as_double((long long)bits));
-    } else {
-      *overflow = 1;
-    }
+  const uint32_t idx = slab_reserve(sw, m, lane, slab_counter, q.fill, q.capacity, overflow);
+  if (has && idx != kEmpty) {
+    const size_t cap = q.capacity;
+    q.plane[idx] = make_double2(r.o.x, r.o.y);
+    q.plane[cap + idx] = make_double2(r.o.z, r.d.x);
+    q.plane[2 * cap + idx] = make_double2(r.d.y, r.d.z);
+    q.plane[3 * cap + idx] = make_double2(w, __longlong_as_double((long long)bits));
   }
 }
 
@@ -717,30 +906,24 @@ struct ShadowTask {
   V3 p, n, cd;
   double w;
   uint32_t sample;  // bit 31: add the 0.2*cd ambient term (Diffuse, RayHs.hs:111-114)
-  uint32_t lit;     // SceneView::lit_flags of the hit triangle (mesh hits), else 0
+  uint32_t walk, settled;
 };
 
-__device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const ShadowQueue& q, uint32_t* counter,
-                                            uint32_t* overflow, uint32_t lane) {
+__device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const ShadowQueue& q, SlabWriter& sw,
+                                            uint32_t* slab_counter, uint32_t* overflow, uint32_t lane) {
   const unsigned m = __ballot_sync(kFull, has);
   if (!m) return;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(kFull, base, 0);
-  if (has) {
-    const uint32_t idx = base + __popc(m & ((1u << lane) - 1));
-    if (idx < q.capacity) {
-      const size_t cap = q.capacity;
-      q.plane[idx] = make_double2(t.p.x, t.p.y);
-      q.plane[cap + idx] = make_double2(t.p.z, t.n.x);
-      q.plane[2 * cap + idx] = make_double2(t.n.y, t.n.z);
-      q.plane[3 * cap + idx] = make_double2(t.cd.x, t.cd.y);
-      q.plane[4 * cap + idx] = make_double2(t.cd.z, t.w);
-      q.sample[idx] = t.sample;
-      q.lit[idx] = t.lit;
-    } else {
-      *overflow = 1;
-    }
+  const uint32_t idx = slab_reserve(sw, m, lane, slab_counter, q.fill, q.capacity, overflow);
+  if (has && idx != kEmpty) {
+    const size_t cap = q.capacity;
+    q.plane[idx] = make_double2(t.p.x, t.p.y);
+    q.plane[cap + idx] = make_double2(t.p.z, t.n.x);
+    q.plane[2 * cap + idx] = make_double2(t.n.y, t.n.z);
+    q.plane[3 * cap + idx] = make_double2(t.cd.x, t.cd.y);
+    q.plane[4 * cap + idx] = make_double2(t.cd.z, t.w);
+    q.sample[idx] = t.sample;
+    q.walk[idx] = t.walk;
+    q.settled[idx] = t.settled;
   }
 }
 
@@ -751,129 +934,31 @@ __device__ __forceinline__ void accumulate(const ChunkParams& P, uint32_t sample
   atomicAdd(a + 2 * (size_t)P.accum_stride, w * c.z);
 }
 
-// What one shaded hit emits.  Kept in registers until the warp reconverges, then pushed
-// with one ballot + one atomic per queue (north_star requirement 3).
-struct Emit {
-  bool has_a, has_b, has_s;
-  Ray ra, rb;
-  double wa, wb;
-  uint64_t bits_a, bits_b;
-  ShadowTask s;
-};
-
-// Rebuild the Hit (Geometry.hs:39) of the winning primitive and run `irradiance`
-// (RayHs.hs:107-147) with the recursion unrolled into weighted child rays: every combine in
-// the reference is `mul scalar colour` + add, so a child carries the scalar product `w`.
-template <bool COUNT>
-__device__ __forceinline__ void shade(const Ctx& cx, const ChunkParams& P, const Ray& r, const Closest& best, double w,
-                                      int depth, int kind, uint32_t probe_mat, uint32_t sample, Emit& em, Cnt<COUNT>& cnt,
-                                      FrameCounters* fc_unused) {
-  const DObject& ob = cx.objects[best.obj];
-  V3 p, n;
-  double tu = 0, tv = 0;
-  const rh_material& mat = cx.materials[ob.material];
-  const int mkind = mat.kind;
-  const bool need_uv = (kind == kRayNormal) && (mkind == RH_MAT_SHOWUV || ((mkind == RH_MAT_DIFFUSE || mkind == RH_MAT_PLASTIC) &&
-                                                                            mat.cmap_kind != RH_CMAP_FLAT));
-  if (ob.kind == RH_OBJ_MESH) {
-    p = rayAt(r, best.t);
-    const double* sh = (const double*)(cx.S->shade + best.slot);
-    RH_CNT(shade, 1);
-    const double wu = best.u, wv = best.v, ww = 1 - best.u - best.v;
-    // barycentricInterp u n1 v n2 (1-u-v) n0 = mul a p + mul b q + mul c r   (Mesh.hs:57, 81)
-    n = mul(wu, ld3(sh + 3)) + mul(wv, ld3(sh + 6)) + mul(ww, ld3(sh));
-    if (need_uv) {
-      tu = wu * sh[11] + wv * sh[13] + ww * sh[9];
-      tv = wu * sh[12] + wv * sh[14] + ww * sh[10];
-    }
-  } else if (ob.kind == RH_OBJ_PLANE) {  // Geometry.hs:70-79
-    p = rayAt(r, best.t);
-    n = ld3(ob.b);
-    if (need_uv) {
-      const V3 tg = ld3(ob.c);
-      const V3 b = cross(tg, n);
-      const V3 rel = p - ld3(ob.a);
-      tu = dot(tg, rel);
-      tv = dot(b, rel);
-    }
-  } else {  // Geometry.hs:83-96
-    p = rayAt(r, best.t);
-    n = normalize(p - ld3(ob.a));
-    if (need_uv) {
-      tu = kPiInv * atan(n.z / n.x);
-      tv = kPiInv * acos(n.y);
-    }
-  }
-
-  if (kind == kRayProbe) {
-    // interior probe of a Transparent hit (RayHs.hs:140-143): leave through the far interface
-    const double ior = cx.materials[probe_mat].ior;
-    V3 outDir;
-    if (refract(r.d, neg(n), ior, 1.0, outDir)) {
-      em.has_a = true;
-      em.ra = rayEps(p, outDir);
-      em.wa = w;
-      em.bits_a = pack_bits(sample, depth, kRayNormal, 0) | (1ull << 63);  // bit 63: counts as an exit ray
-    }
-    return;
-  }
-
-  const V3 v = r.d;
-  switch (mkind) {
-    case RH_MAT_DIFFUSE:
-    case RH_MAT_PLASTIC: {
-      em.has_s = true;
-      em.s.p = p;
-      em.s.n = n;
-      em.s.cd = color_at<COUNT>(cx, mat, tu, tv, cnt);
-      em.s.w = w;
-      em.s.sample = sample | (mkind == RH_MAT_DIFFUSE ? 0x80000000u : 0u);
-      em.s.lit = (ob.kind == RH_OBJ_MESH && cx.S->lit_flags) ? (uint32_t)__ldg(cx.S->lit_flags + best.slot) : 0u;
-      if (mkind == RH_MAT_DIFFUSE) break;
-    }
-    // fallthrough: Plastic adds the Fresnel-weighted mirror term
-    case RH_MAT_MIRROR: {
-      if (depth < P.max_depth) {  // specular, RayHs.hs:99-104
-        const V3 rd = reflect(v, n);
-        const double f = fresnel(mat.ior, dot(n, neg(v)));
-        em.has_a = true;
-        em.ra = rayEps(p, rd);
-        em.wa = w * (f * dot(rd, n));
-        em.bits_a = pack_bits(sample, depth + 1, kRayNormal, 0);
-      }
-      break;
-    }
-    case RH_MAT_EMMIT:
-      accumulate(P, sample, w, ld3(mat.color1));
-      break;
-    case RH_MAT_TRANSPARENT: {
-      if (depth != P.max_depth) {  // RayHs.hs:136-139
-        V3 refDir;
-        if (refract(v, n, 1.0, mat.ior, refDir)) {
-          em.has_b = true;
-          em.rb = rayEps(p, refDir);
-          em.wb = w * (1 - r0f(mat.ior, 1.0));
-          em.bits_b = pack_bits(sample, depth + 1, kRayProbe, (uint32_t)ob.material);
-        }
-      }
-      if (depth < P.max_depth) {
-        const V3 rd = reflect(v, n);
-        const double f = fresnel(mat.ior, dot(n, neg(v)));
-        em.has_a = true;
-        em.ra = rayEps(p, rd);
-        em.wa = w * (f * dot(rd, n));
-        em.bits_a = pack_bits(sample, depth + 1, kRayNormal, 0);
-      }
-      break;
-    }
-    case RH_MAT_SHOWNORMAL:
-      accumulate(P, sample, w, n);
-      break;
-    case RH_MAT_SHOWUV:
-      accumulate(P, sample, w, mk(tu, tv, 0));
-      break;
-    default:
-      break;
+// ------------------------------------------------------------------ bulk async copies (TMA unit, 1-D form)
+// cp.async.bulk.shared::cluster.global with mbarrier completion: one elected lane starts the copy of a contiguous
+// tile, the data lands in shared memory without occupying registers or LSU slots, every lane waits on the mbarrier's
+// phase before reading.  SASS: UBLKCP, SYNCS.ARRIVE.TRANS64, SYNCS.PHASECHK.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_global, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
   }
 }
 
@@ -912,147 +997,7 @@ __device__ __forceinline__ double splitmix01(unsigned long long seed, unsigned l
   return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// Work item -> ray: the camera ray of a pixel sample (pass 0: pixelCoord, Image.hs:31-32, + sample offset,
-// RayHs.hs:178-181) or a queued secondary ray with its weight and tags.  False for a padding row of the last band.
-__device__ __forceinline__ bool load_item(const ChunkParams& P, const CameraParams& cam, uint32_t item, bool primary, Ray& r,
-                                          double& w, uint32_t& sample, int& depth, int& kind, uint32_t& probe_mat) {
-  r.o = r.d = mk(0, 0, 1);
-  if (primary) {
-    const uint32_t lp = item / P.spp, s = item - lp * P.spp;
-    const uint32_t lrow = lp / P.width, col = lp - lrow * P.width;
-    const uint32_t grow = global_row(P, P.first_row + lrow);
-    if (grow >= P.height) return false;
-    double ox = 0, oy = 0;
-    if (P.offset_mode == RH_OFFSETS_SPLITMIX64) {
-      // values 2g and 2g+1 of the stream rh_sample_offsets_f64(seed, ...) writes (x before y, RayHs.hs:185-188)
-      const unsigned long long g = ((unsigned long long)grow * P.width + col) * P.spp + s;
-      ox = splitmix01(P.offset_seed, 2 * g) - 0.5;
-      oy = splitmix01(P.offset_seed, 2 * g + 1) - 0.5;
-    } else if (P.offset_mode != RH_OFFSETS_NONE) {
-      size_t idx;
-      if (P.offset_mode == RH_OFFSETS_TILED_F64)
-        idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
-      else if (P.offset_index == kOffIndexGlobal)
-        idx = ((size_t)grow * P.width + col) * P.spp + s;
-      else
-        idx = item;
-      if (P.offset_mode == RH_OFFSETS_F32) {
-        const float2 o2 = __ldg((const float2*)P.offsets + idx);
-        ox = (double)o2.x;
-        oy = (double)o2.y;
-      } else {
-        const double2 o2 = __ldg((const double2*)P.offsets + idx);
-        ox = o2.x;
-        oy = o2.y;
-      }
-    }
-    r = camera_ray(cam, (double)col + ox, (double)grow + oy);
-    return true;
-  }
-  const size_t cap = P.q_in.capacity;
-  const double2 a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item], d = P.q_in.plane[3 * cap + item];
-  r.o = mk(a.x, a.y, b.x);
-  r.d = mk(b.y, c.x, c.y);
-  w = d.x;
-  const uint64_t bits = (uint64_t)__double_as_longlong(d.y);
-  sample = (uint32_t)bits;
-  depth = (int)((bits >> 32) & 0xff);
-  kind = (int)((bits >> 40) & 0xff);
-  probe_mat = (uint32_t)((bits >> 48) & 0x7fff);
-  return true;
-}
-
-// ------------------------------------------------------------------ K1/K2/K4/K5
-// HITS: the closest hits were found by intersect_kernel (split schedule) and are read from P.hits.
-template <bool COUNT, bool HITS = false>
-__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks) trace_kernel(const __grid_constant__ SceneView S,
-                                                       const __grid_constant__ CameraParams cam,
-                                                       const __grid_constant__ ChunkParams P) {
-  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
-  Ctx cx;
-  stage_tables(sm, S, cx);
-  uint4 stack[kStack];
-  Cnt<COUNT> cnt;
-  cnt.zero();
-  const uint32_t lane = threadIdx.x & 31;
-  const bool primary = (P.pass == 0);
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = primary ? P.n_samples : min(ctl->ray_count[P.pass], P.q_in.capacity);
-  unsigned long long n_reflect = 0, n_probe = 0, n_exit = 0;
-
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&ctl->trace_cursor[P.pass], 32u);
-    base = __shfl_sync(kFull, base, 0);
-    if (base >= n_items) break;
-    const uint32_t item = base + lane;
-    bool valid = item < n_items;
-    Ray r;
-    double w = 1;
-    uint32_t sample = item, probe_mat = 0;
-    int depth = 0, kind = kRayNormal;
-    if (valid) valid = load_item(P, cam, item, primary, r, w, sample, depth, kind, probe_mat);
-    else r.o = r.d = mk(0, 0, 1);
-
-    Closest best;
-    best.obj = -1;
-    if constexpr (HITS) {
-      if (valid) {
-        const double4 h = P.hits[item];  // (t, u, v, slot | obj)
-        const unsigned long long so = (unsigned long long)__double_as_longlong(h.w);
-        best.t = h.x;
-        best.u = h.y;
-        best.v = h.z;
-        best.slot = (uint32_t)so;
-        best.obj = (int)(uint32_t)(so >> 32);
-        best.tris = S.tris;
-      }
-    } else if (valid) {
-      const bool exact = P.exact_boxes || needs_exact_walk(r, S);
-      unsigned long long nodes_before = 0;
-      if constexpr (COUNT) nodes_before = cnt.nodes;
-      closest_hit<COUNT>(cx, r, exact, best, stack, cnt);
-      if constexpr (COUNT) {
-        if (exact) atomicAdd(&P.counters->exact_closest, 1ull);
-        atomicMax(&P.counters->max_closest_nodes, cnt.nodes - nodes_before);
-      }
-    }
-
-    if (primary && valid && P.hit_ids) {
-      int tri = -1;
-      if (best.obj >= 0 && cx.objects[best.obj].kind == RH_OBJ_MESH) tri = (int)S.tris[best.slot].tri_id;
-      P.hit_ids[(size_t)P.first_row * P.width * P.spp + item] = make_int2(best.obj, tri);
-    }
-
-    Emit em;
-    em.has_a = em.has_b = em.has_s = false;
-    if (valid && best.obj >= 0) shade<COUNT>(cx, P, r, best, w, depth, kind, probe_mat, sample, em, cnt, P.counters);
-
-    // RayHs.hs:149-154: a miss contributes black — nothing to do.
-    if (em.has_a) {
-      if (em.bits_a >> 63) n_exit++; else n_reflect++;
-    }
-    if (em.has_b) n_probe++;
-    push_ray(em.has_a, em.ra, em.wa, em.bits_a & ~(1ull << 63), P.q_out, &ctl->ray_count[P.pass + 1], &ctl->overflow, lane);
-    push_ray(em.has_b, em.rb, em.wb, em.bits_b, P.q_out, &ctl->ray_count[P.pass + 1], &ctl->overflow, lane);
-    push_shadow(em.has_s, em.s, P.q_shadow, &ctl->shadow_count[P.pass], &ctl->overflow, lane);
-  }
-
-  // ray-class statistics (one ray per closestIntersection call, SURVEY 8d)
-  for (int o = 16; o > 0; o >>= 1) {
-    n_reflect += __shfl_xor_sync(kFull, n_reflect, o);
-    n_probe += __shfl_xor_sync(kFull, n_probe, o);
-    n_exit += __shfl_xor_sync(kFull, n_exit, o);
-  }
-  if (lane == 0) {
-    if (n_reflect) atomicAdd(&P.counters->rays_reflect, n_reflect);
-    if (n_probe) atomicAdd(&P.counters->rays_probe, n_probe);
-    if (n_exit) atomicAdd(&P.counters->rays_exit, n_exit);
-  }
-  flush_counters<COUNT>(cnt, P.counters, 0);
-}
-
-// ------------------------------------------------------------------ K3: accumDiffuse (RayHs.hs:89-97)
+// ------------------------------------------------------------------ accumDiffuse (RayHs.hs:89-97): the light fold
 // Light.hs:12-17
 __device__ __forceinline__ void light_at(const rh_light& L, const V3& p, V3& ld, V3& lc) {
   if (L.kind == RH_LIGHT_DIRECTIONAL) {  // Light.hs:14
@@ -1066,664 +1011,6 @@ __device__ __forceinline__ void light_at(const rh_light& L, const V3& p, V3& ld,
     ld = mul(1 / dd, lp - p);
     lc = mul(falloff, ld3(L.color));
   }
-}
-__device__ __forceinline__ V3 light_dir(const rh_light& L, const V3& p) {
-  if (L.kind == RH_LIGHT_DIRECTIONAL) return ld3(L.vec);
-  const V3 lp = ld3(L.vec);
-  const double dd = sqrt(sqrDist(lp, p));  // dist, Vec.hs:122
-  return mul(1 / dd, lp - p);
-}
-
-// Shadow-ray setup shared by the phases below: the same arithmetic every time, so the same ray.
-struct ShadowRay {
-  Ray r;
-  AnyHit sink;
-  double far;
-};
-__device__ __forceinline__ ShadowRay make_shadow_ray(const rh_light& L, const V3& p, const V3& ld) {
-  ShadowRay s;
-  s.r = rayEps(p, ld);  // RayHs.hs:93
-  s.sink.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
-  s.sink.lpos = ld3(L.vec);
-  s.sink.dl2 = s.sink.directional ? 0.0 : sqrDist(s.r.o, s.sink.lpos);
-  // Hits farther than the light cannot be in front of it.  A point light's direction is unit to
-  // 1e-15 and the origin sits 1e-6 along it, so the light is at t = |L - o| (1 +- 1e-15) < sqrt(dl2) * 1.000001.
-  s.far = s.sink.directional ? __longlong_as_double(0x7ff0000000000000LL) : sqrt(s.sink.dl2) * 1.000001;
-  return s;
-}
-
-// Simple form: one shaded hit per lane, lights in sequence, each query run to completion.
-// Used when the scene has more than 32 lights (the pooled kernel keeps one visibility bit per light).
-template <bool COUNT>
-__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_simple(const __grid_constant__ SceneView S,
-                                                                                       const __grid_constant__ ChunkParams P) {
-  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
-  Ctx cx;
-  stage_tables(sm, S, cx);
-  uint4 stack[kStack];
-  Cnt<COUNT> cnt;
-  cnt.zero();
-  const uint32_t lane = threadIdx.x & 31;
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
-  const size_t cap = P.q_shadow.capacity;
-  unsigned long long n_culled = 0;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&ctl->shadow_cursor[P.pass], 32u);
-    base = __shfl_sync(kFull, base, 0);
-    if (base >= n_items) break;
-    const uint32_t item = base + lane;
-    if (item >= n_items) continue;
-    const double2 a = P.q_shadow.plane[item], b = P.q_shadow.plane[cap + item], c = P.q_shadow.plane[2 * cap + item],
-                  d = P.q_shadow.plane[3 * cap + item], e = P.q_shadow.plane[4 * cap + item];
-    const uint32_t sbits = P.q_shadow.sample[item];
-    const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
-    const double w = e.y;
-    V3 acc = mk(0, 0, 0);  // foldl ... black lts
-    for (uint32_t li = 0; li < S.n_lights; li++) {
-      const rh_light& L = cx.lights[li];
-      V3 ld, lc;
-      light_at(L, p, ld, lc);
-      // diffuse (Material.hs:31-33) = (max (l.n) 0 / pi) * (cd (*) lc): exactly zero when l.n <= 0, whether
-      // or not the point is shadowed, so the occlusion query cannot change the sum and is skipped.
-      const double ldn = dot(ld, n);
-      if (ldn <= 0) {
-        n_culled++;
-        continue;
-      }
-      const Ray sr = rayEps(p, ld);
-      const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || needs_exact_walk(sr, S), L, stack, cnt);
-      if (!shadowed) acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));
-    }
-    const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
-    accumulate(P, sbits & 0x7fffffffu, w, total);
-  }
-  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
-  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
-  flush_counters<COUNT>(cnt, P.counters, 1);
-}
-
-// Pooled form.  Most shadow rays never reach a triangle: the light is below the horizon, a
-// wall plane answers, or the ray misses every mesh's root box.  Running those in the same loop
-// as the rays that do walk a tree leaves most lanes of a warp idle (ncu: 16.6 active threads per
-// instruction in the dragon region).  So each warp takes kShadowT*32 shaded hits at a time and,
-// light by light (rays towards one light from neighbouring samples stay coherent),
-//   phase 1  every lane settles the cheap cases of its own hits for that light and appends the
-//            hits that need a tree walk to a warp-local pool in shared memory
-//            (ballot + prefix-popcount compaction);
-//   phase 2  the pool is walked in full rounds of 32, every lane on a ray that needs it; what is
-//            left over (< 32) stays pooled and joins the next light's rays.  An occluded pair
-//            sets its bit in the hit's visibility word (shared-memory atomicOr);
-//   phase 3  every lane folds the lights of its own hits in order (accumDiffuse's foldl) with
-//            those bits and adds w * (ambient + sum) to the sample.
-constexpr int kShadowT = RH_SHADOW_T;
-struct ShadowWarpSmem {
-  uint32_t vis[32 * kShadowT];       // bit li: light li is occluded for this hit
-  uint16_t pool[32 * kShadowT + 32]; // hit-in-batch | light << 8
-};
-static_assert(sizeof(ShadowWarpSmem) % 16 == 0, "the pair terms follow the per-warp regions");
-static_assert(32 * kShadowT <= 256, "pool entries keep the hit index in 8 bits");
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel(const __grid_constant__ SceneView S,
-                                                                                const __grid_constant__ ChunkParams P) {
-  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
-  ShadowWarpSmem* wsm = reinterpret_cast<ShadowWarpSmem*>(rh_smem + sizeof(SmemTables));
-  Ctx cx;
-  stage_tables(sm, S, cx);
-  uint4 stack[kStack];
-  Cnt<COUNT> cnt;
-  cnt.zero();
-  const uint32_t lane = threadIdx.x & 31;
-  ShadowWarpSmem& ws = wsm[threadIdx.x >> 5];
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
-  const size_t cap = P.q_shadow.capacity;
-  const uint32_t n_lights = S.n_lights, n_lin = S.n_lin, sphere_root = S.sphere_root;
-  const double2* qp = P.q_shadow.plane;
-  unsigned long long n_culled = 0;
-
-  // phase 2 body: one pooled (hit, light) pair
-  auto walk = [&](uint32_t base, uint32_t e) {
-    const uint32_t j = e & 0xff, li = e >> 8;
-    const uint32_t item = base + j;
-    const double2 a = qp[item], b = qp[cap + item];
-    const V3 p = mk(a.x, a.y, b.x);
-    const rh_light& L = cx.lights[li];
-    const ShadowRay sr = make_shadow_ray(L, p, light_dir(L, p));
-    const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S);
-    const RayF f = make_rayf(sr.r, S);
-    bool hit = false;
-    for (uint32_t k = 0; k < n_lin && !hit; k++) {
-      const uint32_t oi = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
-      const DObject& ob = cx.objects[oi];
-      if (ob.kind != RH_OBJ_MESH || ob.is_emitter || ob.root == kEmpty) continue;
-      double bound = sr.far;
-      AnyHit sink = sr.sink;
-      hit = exact ? traverse_exact<COUNT>(cx, ob.root, sr.r, bound, sink, stack, cnt)
-                  : traverse<COUNT>(cx, ob.root, sr.r, f, bound, sink, stack, cnt);
-    }
-    if (!hit && sphere_root != kEmpty) {
-      double bound = sr.far;
-      AnyHit sink = sr.sink;
-      hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, sr.r, bound, sink, stack, cnt, true)
-                  : traverse<COUNT, AnyHit, true>(cx, sphere_root, sr.r, f, bound, sink, stack, cnt, true);
-    }
-    if (hit) atomicOr(&ws.vis[j], 1u << li);
-  };
-
-  const uint32_t total_warps = gridDim.x * (kShadowBlock / 32);
-  for (;;) {
-    // guided self-scheduling: large batches (fuller pool rounds) while plenty of work is left, single
-    // rows of 32 near the end of the queue and for small launches, so no warp ends up with a long tail
-    uint32_t base = 0, T = 1;
-    if (lane == 0) {
-      const uint32_t seen = *(volatile uint32_t*)&ctl->shadow_cursor[P.pass];
-      const uint32_t left = seen < n_items ? n_items - seen : 0;
-      T = min((uint32_t)kShadowT, max(1u, left / (total_warps * 32u * 2u)));
-      base = atomicAdd(&ctl->shadow_cursor[P.pass], 32u * T);
-    }
-    base = __shfl_sync(kFull, base, 0);
-    T = __shfl_sync(kFull, T, 0);
-    if (base >= n_items) break;
-    const uint32_t n_here = min(32u * T, n_items - base);
-    for (uint32_t t = 0; t < T; t++) ws.vis[t * 32 + lane] = 0;
-    uint32_t pool_n = 0;
-    for (uint32_t li = 0; li < n_lights; li++) {
-      const rh_light& L = cx.lights[li];
-      // ---- phase 1: cheap cases, pool the rest
-      for (uint32_t t = 0; t < T; t++) {
-        const uint32_t j = t * 32 + lane;
-        bool need_walk = false;
-        if (j < n_here) {
-          const uint32_t item = base + j;
-          const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
-          const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
-          const V3 ld = light_dir(L, p);
-          if (dot(ld, n) <= 0) {
-            n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
-          } else {
-            const ShadowRay sr = make_shadow_ray(L, p, ld);
-            const bool exact = P.exact_boxes || needs_exact_walk(sr.r, S);
-            const RayF f = make_rayf(sr.r, S);
-            const float ffar = __double2float_ru(sr.far);
-            bool shadowed = false;
-            for (uint32_t k = 0; k < n_lin && !shadowed; k++) {
-              const uint32_t oi = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
-              const DObject& ob = cx.objects[oi];
-              if (ob.is_emitter) continue;  // isOccluder, RayHs.hs:81-82
-              const int kind = ob.kind;
-              if (kind == RH_OBJ_MESH) {
-                const uint32_t root = ob.root;
-                if (root == kEmpty || need_walk) continue;
-                if (exact) {
-                  need_walk = true;
-                } else {  // the mesh's own box (slot 0 of its super-root)
-                  const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
-                  const float4 b0 = np[0], b1 = np[1];
-                  float tm;
-                  RH_CNT(nodes, 1);
-                  RH_CNT(box, 1);
-                  need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
-                }
-              } else {
-                double time;
-                RH_CNT(prim, 1);
-                const bool hit = (kind == RH_OBJ_PLANE) ? plane_time(sr.r, ob, sr.far, time) : sphere_time(sr.r, ob, time);
-                shadowed = hit && sr.sink.in_front(sr.r, time);
-              }
-            }
-            if (!shadowed && !need_walk && sphere_root != kEmpty) {  // the sphere tree's own box
-              if (exact) {
-                need_walk = true;
-              } else {
-                const float4* np =
-                    sphere_root < S.n_smem_nodes ? (const float4*)&sm.nodes[sphere_root] : (const float4*)&S.wide32[sphere_root];
-                const float4 b0 = np[0], b1 = np[1];
-                float tm;
-                RH_CNT(nodes, 1);
-                RH_CNT(box, 1);
-                need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
-              }
-            }
-            if (shadowed) {
-              ws.vis[j] |= 1u << li;  // only this lane touches vis[j] during phase 1
-              need_walk = false;
-            }
-          }
-        }
-        const unsigned m = __ballot_sync(kFull, need_walk);
-        if (need_walk) ws.pool[pool_n + __popc(m & ((1u << lane) - 1))] = (uint16_t)(j | (li << 8));
-        pool_n += __popc(m);
-      }
-      __syncwarp();
-      // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
-      const bool last = (li + 1 == n_lights);
-      const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
-      for (uint32_t i = lane; i < n_full; i += 32) walk(base, ws.pool[i]);
-      __syncwarp();
-      const uint32_t rem = pool_n - n_full;
-      uint16_t keep = 0;
-      if (lane < rem) keep = ws.pool[n_full + lane];
-      __syncwarp();
-      if (lane < rem) ws.pool[lane] = keep;
-      pool_n = rem;
-      __syncwarp();
-    }
-    // ---- phase 3: accumDiffuse's fold over the lights, in order
-    for (uint32_t t = 0; t < T; t++) {
-      const uint32_t j = t * 32 + lane;
-      if (j >= n_here) continue;
-      const uint32_t item = base + j;
-      const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
-      const uint32_t sbits = P.q_shadow.sample[item];
-      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
-      const double w = e.y;
-      const uint32_t vis = ws.vis[j];
-      V3 acc = mk(0, 0, 0);  // foldl ... black lts
-      for (uint32_t li = 0; li < n_lights; li++) {
-        if ((vis >> li) & 1u) continue;  // Just _ -> black
-        V3 ld, lc;
-        light_at(cx.lights[li], p, ld, lc);
-        const double ldn = dot(ld, n);
-        if (ldn <= 0) continue;
-        acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
-      }
-      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
-      accumulate(P, sbits & 0x7fffffffu, w, total);
-    }
-    __syncwarp();
-  }
-  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
-  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
-  flush_counters<COUNT>(cnt, P.counters, 1);
-}
-
-// Fast form of the pooled kernel, for the common scene shape: at most kOccPlanes occluding planes, kOccSpheres
-// occluding spheres outside the sphere tree, kOccMeshes meshes and kFastLights lights (SceneView::shadow_fast).
-// Same three phases and the same arithmetic per (hit, light) pair, restructured around what ncu showed on the wall-only
-// chunks of the bench frame (profiles/r1e_*): fp64 math was a quarter of the issued instructions, the rest control
-// flow, generic loads and recomputation.  So
-//   * the occluder and light tables are compact shared-memory records read with LDS, without the per-object kind
-//     dispatch and emitter test;
-//   * the plane tests of a pair are straight-line: every plane gets the reference's two dot products
-//     (Geometry.hs:70-79), and a plane is dropped when `abs (d.n) > 0 && time > 0` is certain to fail or time is
-//     certain to lie beyond the light (the same three rejections as plane_time).  Planes that survive — none in a
-//     closed room — get the exact quotient and inFrontOfLight (RayHs.hs:84-87) in a cold loop;
-//   * phase 1 leaves the pair's Lambert factor and light falloff in shared memory, so phase 3 folds the lights
-//     (accumDiffuse's foldl, RayHs.hs:89-97) without recomputing lightAt (Light.hs:12-17).
-struct __align__(16) ShadowTables {
-  WideNode32 nodes[kSmemNodes];
-  OccPlane planes[kOccPlanes];
-  OccSphere spheres[kOccSpheres];
-  rh_light lights[kFastLights];
-  // Root boxes (the float cull boxes of the mesh super-roots and of the sphere tree, padded by 2e-6 + 1e-12 |x|) and,
-  // per (light, root), on which outer side of each slab the light lies: bit a = below lo[a], bit 3 + a = above hi[a].
-  double rootbox[kOccMeshes + 1][6];
-  uint32_t mesh_roots[kOccMeshes + 1];  // the sphere tree's super-root follows the meshes'
-  uint8_t light_side[kFastLights][kOccMeshes + 1];
-  // per (light, mesh root): number of its cube map in SceneView::light_maps, or kEmpty (light_maps.cpp)
-  uint32_t light_map[kFastLights][kOccMeshes + 1];
-};
-static_assert(sizeof(ShadowTables) % 16 == 0, "warp pools follow the tables in dynamic shared memory");
-
-constexpr int kPairSlots = RH_SHADOW_PAIRS > kFastLights ? RH_SHADOW_PAIRS : kFastLights;  // one hit per lane always fits
-__device__ __forceinline__ int fast_shadow_T(uint32_t n_lights) {  // hits per lane per batch: 6 KB of pair terms per warp
-  const int t = RH_SHADOW_PAIRS / (int)(n_lights ? n_lights : 1);
-  return t < 1 ? 1 : (t > kShadowT ? kShadowT : t);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kShadowBlock, kShadowMinBlocks) shadow_kernel_fast(const __grid_constant__ SceneView S,
-                                                                                     const __grid_constant__ ChunkParams P) {
-  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
-  const uint32_t n_lights = S.n_lights, n_planes = S.n_occ_planes, n_spheres = S.n_occ_spheres, n_meshes = S.n_occ_meshes;
-  const uint32_t sphere_root = S.sphere_root;
-  const uint32_t Tmax = (uint32_t)fast_shadow_T(n_lights);
-  // per-warp regions after the tables: vis + pool (ShadowWarpSmem), then the pair terms
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kShadowBlock / 32;
-  ShadowWarpSmem& ws = reinterpret_cast<ShadowWarpSmem*>(rh_smem + sizeof(ShadowTables))[warp];
-  const uint32_t pairs_per_warp = 32u * Tmax * n_lights;
-  double2* terms = reinterpret_cast<double2*>(rh_smem + sizeof(ShadowTables) + n_warps * sizeof(ShadowWarpSmem)) +
-                   (size_t)warp * pairs_per_warp;  // [light][hit in batch] = (Lambert factor / pi, falloff)
-  copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
-  copy16(sm.planes, S.occ_planes, n_planes * (uint32_t)sizeof(OccPlane));
-  copy16(sm.spheres, S.occ_spheres, n_spheres * (uint32_t)sizeof(OccSphere));
-  copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
-  const uint32_t n_roots = n_meshes + (sphere_root != kEmpty ? 1u : 0u);
-  const bool use_maps = S.light_map_index != nullptr && !P.no_light_maps;
-  const bool use_lit = S.lit_flags != nullptr && !P.no_light_maps;
-  if (threadIdx.x < n_roots) {
-    const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : sphere_root;
-    sm.mesh_roots[threadIdx.x] = root;
-    const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
-    for (int a = 0; a < 3; a++) {
-      const double lo = (double)fb[a] + S.center[a], hi = (double)fb[3 + a] + S.center[a];  // world coordinates
-      sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
-      sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < n_roots * n_lights) {
-    const uint32_t li = threadIdx.x / n_roots, m = threadIdx.x % n_roots;
-    uint32_t side = 0;
-    if (sm.lights[li].kind != RH_LIGHT_DIRECTIONAL)
-      for (int a = 0; a < 3; a++) {
-        if (sm.lights[li].vec[a] < sm.rootbox[m][a]) side |= 1u << a;
-        if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
-      }
-    sm.light_side[li][m] = (uint8_t)side;
-    sm.light_map[li][m] = (S.light_map_index && m < n_meshes) ? S.light_map_index[li * kOccMeshes + m] : kEmpty;
-  }
-  __syncthreads();
-  Ctx cx;
-  cx.S = &S;
-  cx.sm_nodes = sm.nodes;
-  cx.objects = S.objects;  // sphere-tree leaves only
-  cx.materials = S.materials;
-  cx.lights = sm.lights;
-
-  uint4 stack[kStack];
-  Cnt<COUNT> cnt;
-  cnt.zero();
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
-  const size_t cap = P.q_shadow.capacity;
-  const double2* qp = P.q_shadow.plane;
-  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-  unsigned long long n_culled = 0;
-
-  // The pair's light direction and shadow ray (Light.hs:12-17, RayHs.hs:93).  `far` bounds the distance from the
-  // ray origin to the light from above (|o - L| <= |o - p| + |p - L| = 1e-6 |ld| + dd); it only prunes — whether a
-  // hit is in front of the light is always decided by inFrontOfLight's own comparison.
-  struct Pair {
-    V3 ld, o, lp;
-    double dd, far;
-    bool directional;
-  };
-  auto make_pair = [&](const rh_light& L, const V3& p) {
-    Pair q;
-    q.directional = (L.kind == RH_LIGHT_DIRECTIONAL);
-    q.lp = ld3(L.vec);
-    if (q.directional) {
-      q.ld = q.lp;
-      q.dd = 0;
-      q.far = kInf;
-    } else {
-      const V3 dv = q.lp - p;
-      q.dd = sqrt(sqrLen(dv));  // dist lightPos p = sqrt (sqrDist ..), Vec.hs:118-122: (lp - p).(lp - p)
-      q.ld = mul(1 / q.dd, dv);
-      q.far = (q.dd + kEps) * 1.000001;
-    }
-    q.o = p + mul(kEps, q.ld);  // rayEps, Geometry.hs:36
-    return q;
-  };
-
-  // phase 2 body: one pooled (hit, light) pair walks the mesh trees and the sphere tree
-  auto walk = [&](uint32_t base, uint32_t e) {
-    const uint32_t j = e & 0xff, li = e >> 8;
-    const uint32_t item = base + j;
-    const double2 a = qp[item], b = qp[cap + item];
-    const V3 p = mk(a.x, a.y, b.x);
-    const Pair q = make_pair(sm.lights[li], p);
-    Ray r;
-    r.o = q.o;
-    r.d = q.ld;
-    AnyHit sink;
-    sink.directional = q.directional;
-    sink.lpos = q.lp;
-    sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
-    const bool exact = P.exact_boxes || needs_exact_walk(r, S);
-    const RayF f = make_rayf(r, S);
-    bool hit = false;
-    unsigned long long nodes_before = 0;
-    if constexpr (COUNT) {
-      nodes_before = cnt.nodes;
-      if (exact) atomicAdd(&P.counters->exact_walks, 1ull);
-    }
-    for (uint32_t m = 0; m < n_meshes && !hit; m++) {
-      double bound = q.far;
-      hit = exact ? traverse_exact<COUNT>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt)
-                  : traverse<COUNT>(cx, sm.mesh_roots[m], r, f, bound, sink, stack, cnt);
-    }
-    if constexpr (COUNT) atomicMax(&P.counters->max_walk_nodes, cnt.nodes - nodes_before);
-    if (!hit && sphere_root != kEmpty) {
-      double bound = q.far;
-      hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, sphere_root, r, bound, sink, stack, cnt, true)
-                  : traverse<COUNT, AnyHit, true>(cx, sphere_root, r, f, bound, sink, stack, cnt, true);
-    }
-    if (hit) atomicOr(&ws.vis[j], 1u << li);
-  };
-
-  const uint32_t total_warps = gridDim.x * n_warps;
-  // Guided self-scheduling, as in shadow_kernel.  (Claiming the next batch early, to overlap the cursor round trip
-  // with work, was measured 5 % slower: every warp then finishes one batch after the queue has run dry.)
-  auto claim = [&]() {
-    uint2 c = make_uint2(0, 1);
-    if (lane == 0) {
-      const uint32_t seen = *(volatile uint32_t*)&ctl->shadow_cursor[P.pass];
-      const uint32_t left = seen < n_items ? n_items - seen : 0;
-      c.y = min(Tmax, max(1u, left / (total_warps * 32u * 2u)));
-      c.x = atomicAdd(&ctl->shadow_cursor[P.pass], 32u * c.y);
-    }
-    return c;
-  };
-  for (;;) {
-    const uint2 now = claim();
-    const uint32_t base = __shfl_sync(kFull, now.x, 0), T = __shfl_sync(kFull, now.y, 0);
-    if (base >= n_items) break;
-    const uint32_t n_here = min(32u * T, n_items - base);
-    for (uint32_t t = 0; t < T; t++) ws.vis[t * 32 + lane] = 0;
-    uint32_t pool_n = 0;
-    for (uint32_t li = 0; li < n_lights; li++) {
-      const rh_light& L = sm.lights[li];
-      // ---- phase 1
-      for (uint32_t t = 0; t < T; t++) {
-        const uint32_t j = t * 32 + lane;
-        bool need_walk = false;
-        if (j < n_here) {
-          const uint32_t item = base + j;
-          const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
-          const uint32_t lit = use_lit ? P.q_shadow.lit[item] : 0u;  // (asked for here, needed far below)
-          const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
-          const Pair q = make_pair(L, p);
-          const double ldn = dot(q.ld, n);
-          if (ldn <= 0) {
-            n_culled++;  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
-            ws.vis[j] |= 1u << li;  // (only this lane touches vis[j] during phase 1)
-          } else {
-            // lightAt's colour factor (Light.hs:16-17) and diffuse's scalar (Material.hs:31-33), for phase 3
-            double falloff = 1.0;
-            if (!q.directional) {
-              const double s = 1.0 + q.dd / L.radius;
-              falloff = 1.0 / (s * s);
-            }
-            terms[li * (32u * Tmax) + j] = make_double2(hs_max(ldn, 0) * kPiInv, falloff);
-            // planes, straight-line
-            uint32_t maybe = 0;
-            for (uint32_t k = 0; k < n_planes; k++) {
-              const double2* pl = (const double2*)&sm.planes[k];
-              const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
-              const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
-              RH_CNT(prim, 1);
-              const double den = dot(q.ld, pn);
-              const double num = dot(pn, pp - q.o);
-              const bool miss = !(fabs(den) > 0) | (((num > 0) != (den > 0)) & (num == num)) |
-                                (fabs(num) > q.far * fabs(den) * 1.000000000001);
-              maybe |= (miss ? 0u : 1u) << k;
-            }
-            bool shadowed = false;
-            Ray r;
-            r.o = q.o;
-            r.d = q.ld;
-            AnyHit sink;
-            sink.directional = q.directional;
-            sink.lpos = q.lp;
-            sink.dl2 = 0.0;
-            if (maybe | n_spheres) sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
-            while (maybe) {  // cold: exact quotient and inFrontOfLight for the surviving planes
-              const uint32_t k = __ffs(maybe) - 1;
-              maybe &= maybe - 1;
-              const V3 pp = ld3(sm.planes[k].p), pn = ld3(sm.planes[k].n);
-              const double time = dot(pn, pp - r.o) / dot(r.d, pn);
-              if (time > 0 && sink.in_front(r, time)) shadowed = true;
-            }
-            for (uint32_t k = 0; k < n_spheres && !shadowed; k++) {  // Geometry.hs:81-95
-              const V3 ct = ld3(sm.spheres[k].c);
-              const double rad = sm.spheres[k].r;
-              RH_CNT(prim, 1);
-              const double qa = dot(r.d, r.d);
-              const double qb = 2.0 * dot(r.d, r.o - ct);
-              const double qc = sqrLen(r.o - ct) - rad * rad;
-              const double delta = qb * qb - 4.0 * qa * qc;
-              if (delta < 0.0) continue;
-              const double t0 = 0.5 * ((-qb) - sqrt(delta)) / qa;
-              double time;
-              if (t0 > 0) time = t0;
-              else {
-                const double t1 = 0.5 * ((-qb) + sqrt(delta)) / qa;
-                if (!(t1 > 0)) continue;
-                time = t1;
-              }
-              shadowed = sink.in_front(r, time);
-            }
-            if (shadowed) {
-              ws.vis[j] |= 1u << li;
-            } else if (n_roots) {
-              // Only the part of the ray between its origin and the light can hold an occluder (inFrontOfLight).  The
-              // origin is within 1.000001e-6 of p in every coordinate, so when p and the light lie beyond the same face
-              // of a (padded) root box, that part is outside the box: nothing to walk.
-              bool may = P.exact_boxes != 0;
-              // Lit triangles (light_maps.cpp): when the hit lies on a triangle that nothing of its own mesh can
-              // shadow from this light, that mesh is not walked for this pair.
-              uint32_t skip = 0;
-              if ((lit >> li) & 1u) skip = 1u << (lit >> 12);
-              for (uint32_t m = 0; m < n_roots; m++) {
-                if ((skip >> m) & 1u) continue;
-                const double* rb = sm.rootbox[m];
-                const uint32_t side = (p.x < rb[0] ? 1u : 0u) | (p.y < rb[1] ? 2u : 0u) | (p.z < rb[2] ? 4u : 0u) |
-                                      (p.x > rb[3] ? 8u : 0u) | (p.y > rb[4] ? 16u : 0u) | (p.z > rb[5] ? 32u : 0u);
-                may |= (side & sm.light_side[li][m]) == 0;
-              }
-              // the root boxes themselves (slot 0 of each super-root)
-              if (!may) {
-              } else if (P.exact_boxes || needs_exact_walk(r, S)) {
-                need_walk = true;
-              } else {
-                // the light's cube maps: a mesh none of whose triangles can lie between p and the light is not walked
-                if (use_maps && !q.directional) {
-                  const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
-                  const float dist_up = __double2float_ru(q.dd);
-                  if (cell != kEmpty)
-                    for (uint32_t m = 0; m < n_meshes; m++) {
-                      const uint32_t mi = sm.light_map[li][m];
-                      if (mi != kEmpty && light_map_clears(S, mi, cell, dist_up)) skip |= 1u << m;
-                    }
-                }
-                const RayF f = make_rayf(r, S);
-                const float ffar = __double2float_ru(q.far);
-                for (uint32_t m = 0; m < n_roots && !need_walk; m++) {
-                  if ((skip >> m) & 1u) continue;
-                  const uint32_t root = sm.mesh_roots[m];
-                  const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
-                  const float4 b0 = np[0], b1 = np[1];
-                  float tm;
-                  RH_CNT(nodes, 1);
-                  RH_CNT(box, 1);
-                  need_walk = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
-                }
-              }
-            }
-          }
-        }
-        const unsigned m = __ballot_sync(kFull, need_walk);
-        if (need_walk) ws.pool[pool_n + __popc(m & ((1u << lane) - 1))] = (uint16_t)(j | (li << 8));
-        pool_n += __popc(m);
-      }
-      __syncwarp();
-      // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
-      const bool last = (li + 1 == n_lights);
-      const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
-      for (uint32_t i = lane; i < n_full; i += 32) walk(base, ws.pool[i]);
-      __syncwarp();
-      const uint32_t rem = pool_n - n_full;
-      uint16_t keep = 0;
-      if (lane < rem) keep = ws.pool[n_full + lane];
-      __syncwarp();
-      if (lane < rem) ws.pool[lane] = keep;
-      pool_n = rem;
-      __syncwarp();
-    }
-    // ---- phase 3: accumDiffuse's fold over the lights, in order
-    for (uint32_t t = 0; t < T; t++) {
-      const uint32_t j = t * 32 + lane;
-      if (j >= n_here) continue;
-      const uint32_t item = base + j;
-      const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
-      const uint32_t sbits = P.q_shadow.sample[item];
-      const V3 cd = mk(d.x, d.y, e.x);
-      const double w = e.y;
-      const uint32_t vis = ws.vis[j];
-      V3 acc = mk(0, 0, 0);  // foldl ... black lts
-      for (uint32_t li = 0; li < n_lights; li++) {
-        if ((vis >> li) & 1u) continue;  // Just _ -> black (or l.n <= 0: the term is exactly 0)
-        const double2 tm = terms[li * (32u * Tmax) + j];
-        const V3 lc = mul(tm.y, ld3(sm.lights[li].color));   // Light.hs:14, 17
-        acc = acc + mul(tm.x, cmul(cd, lc));                  // diffuse, Material.hs:31-33
-      }
-      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
-      accumulate(P, sbits & 0x7fffffffu, w, total);
-    }
-    __syncwarp();
-  }
-  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
-  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
-  flush_counters<COUNT>(cnt, P.counters, 1);
-}
-
-// ------------------------------------------------------------------ K3 split: classify -> walk -> fold
-// The same work as shadow_kernel_fast, cut at the two places where its warps lose lanes:
-//   classify  one thread per shaded hit, all lights: everything that needs no tree (l.n <= 0, planes, linear spheres,
-//             root boxes).  A hit whose lights are all settled is folded and accumulated on the spot (accumDiffuse,
-//             RayHs.hs:89-97).  Otherwise the hit goes to the deferred list, its settled lights are flagged, and every
-//             (hit, light) pair whose ray enters a root box goes to the walk queue.  Warps never diverge on tree work.
-//   walk      persistent warps over the walk queue with PER-LANE refill: a lane whose ray has ended (occluder found or
-//             stack empty) takes the next queued pair while its neighbours keep walking, so the long unoccluded rays
-//             no longer hold 31 idle lanes (ncu, pooled kernel: 16-22 active threads per instruction in the dragon
-//             chunks, 1.7 on the synthetic triangle soup).  The loop is warp-uniform — votes decide between the refill,
-//             inner-node and leaf steps — so the lanes reconverge at every step by construction.
-//   fold      one thread per deferred hit: lightAt + diffuse for the lights still unflagged, in order, then accumulate.
-__device__ __forceinline__ void stage_shadow_tables(ShadowTables& sm, const SceneView& S, bool with_nodes) {
-  const uint32_t n_meshes = S.n_occ_meshes, n_lights = S.n_lights;
-  if (with_nodes) copy16(sm.nodes, S.wide32, S.n_smem_nodes * (uint32_t)sizeof(WideNode32));
-  copy16(sm.planes, S.occ_planes, S.n_occ_planes * (uint32_t)sizeof(OccPlane));
-  copy16(sm.spheres, S.occ_spheres, S.n_occ_spheres * (uint32_t)sizeof(OccSphere));
-  copy16(sm.lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
-  const uint32_t n_roots = n_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
-  if (threadIdx.x < n_roots) {
-    const uint32_t root = threadIdx.x < n_meshes ? S.occ_meshes[threadIdx.x] : S.sphere_root;
-    sm.mesh_roots[threadIdx.x] = root;
-    const float* fb = S.wide32[root].box;  // slot 0 of a super-root = the tree's own box
-    for (int a = 0; a < 3; a++) {
-      const double lo = (double)fb[a] + S.center[a], hi = (double)fb[3 + a] + S.center[a];  // world coordinates
-      sm.rootbox[threadIdx.x][a] = lo - (2e-6 + 1e-12 * fabs(lo));
-      sm.rootbox[threadIdx.x][3 + a] = hi + (2e-6 + 1e-12 * fabs(hi));
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < n_roots * n_lights) {
-    const uint32_t li = threadIdx.x / n_roots, m = threadIdx.x % n_roots;
-    uint32_t side = 0;
-    if (sm.lights[li].kind != RH_LIGHT_DIRECTIONAL)
-      for (int a = 0; a < 3; a++) {
-        if (sm.lights[li].vec[a] < sm.rootbox[m][a]) side |= 1u << a;
-        if (sm.lights[li].vec[a] > sm.rootbox[m][3 + a]) side |= 8u << a;
-      }
-    sm.light_side[li][m] = (uint8_t)side;
-    sm.light_map[li][m] = (S.light_map_index && m < n_meshes) ? S.light_map_index[li * kOccMeshes + m] : kEmpty;
-  }
-  __syncthreads();
 }
 
 // Light direction and shadow ray of a (hit, light) pair (Light.hs:12-17, RayHs.hs:93).  `far` bounds the distance from
@@ -1744,49 +1031,75 @@ __device__ __forceinline__ LightPair make_light_pair(const rh_light& L, const V3
     q.far = __longlong_as_double(0x7ff0000000000000LL);
   } else {
     const V3 dv = q.lp - p;
-    q.dd = sqrt(sqrLen(dv));  // dist lightPos p, Vec.hs:118-122
+    q.dd = sqrt(sqrLen(dv));  // dist lightPos p = sqrt (sqrDist ..), Vec.hs:118-122: (lp - p).(lp - p)
     q.ld = mul(1 / q.dd, dv);
     q.far = (q.dd + kEps) * 1.000001;
   }
   q.o = p + mul(kEps, q.ld);  // rayEps, Geometry.hs:36
   return q;
 }
-
-// Planes and linear spheres of shadowIntersection (RayHs.hs:74-87) for one pair; true = occluded.
-template <bool COUNT>
-__device__ __forceinline__ bool primitives_occlude(const ShadowTables& sm, uint32_t n_planes, uint32_t n_spheres,
-                                                   const LightPair& q, Cnt<COUNT>& cnt) {
-  uint32_t maybe = 0;
-  for (uint32_t k = 0; k < n_planes; k++) {  // straight-line: see shadow_kernel_fast
-    const double2* pl = (const double2*)&sm.planes[k];
-    const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
-    const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
-    RH_CNT(prim, 1);
-    const double den = dot(q.ld, pn);
-    const double num = dot(pn, pp - q.o);
-    const bool miss = !(fabs(den) > 0) | (((num > 0) != (den > 0)) & (num == num)) |
-                      (fabs(num) > q.far * fabs(den) * 1.000000000001);
-    maybe |= (miss ? 0u : 1u) << k;
-  }
-  if (!(maybe | n_spheres)) return false;
-  Ray r;
-  r.o = q.o;
-  r.d = q.ld;
+__device__ __forceinline__ AnyHit make_any_hit(const LightPair& q) {
   AnyHit sink;
   sink.directional = q.directional;
   sink.lpos = q.lp;
-  sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
+  sink.dl2 = q.directional ? 0.0 : sqrDist(q.o, q.lp);
+  return sink;
+}
+
+// Is the Lambert cull exact for this light?  diffuse (Material.hs:31-33) = (max (l.n) 0 / pi) * (cd (*) lc) is +-0 for
+// l.n <= 0 only while cd (*) lc is finite: 0 * inf = NaN in the reference, which prints as channel 255.
+__device__ __forceinline__ bool light_is_tame(const rh_light& L) {
+  const bool colour = isfinite(L.color[0]) && isfinite(L.color[1]) && isfinite(L.color[2]);
+  return colour && (L.kind == RH_LIGHT_DIRECTIONAL || L.radius >= 0);  // radius < 0 can make the falloff 1 / 0
+}
+
+// Planes and linear spheres of shadowIntersection (RayHs.hs:74-87) for one pair; true = occluded.
+// The plane tests are straight-line: every plane gets the reference's two dot products (Geometry.hs:70-79), and a plane
+// is dropped when `abs (d.n) > 0 && time > 0` is certain to fail or time is certain to lie beyond the light (the same
+// three rejections as plane_time).  Planes that survive — none in a closed room — get the exact quotient and
+// inFrontOfLight (RayHs.hs:84-87) in a cold loop.
+// `skip`: planes (of the first 32) that the caller knows cannot lie between the hit and the light.
+template <bool COUNT>
+__device__ __forceinline__ bool primitives_occlude(const OccPlane* planes, uint32_t n_planes, const OccSphere* spheres,
+                                                   uint32_t n_spheres, const LightPair& q, uint32_t skip, Cnt<COUNT>& cnt) {
   bool shadowed = false;
-  while (maybe) {  // cold: exact quotient and inFrontOfLight for the surviving planes (Geometry.hs:70-79)
-    const uint32_t k = __ffs(maybe) - 1;
-    maybe &= maybe - 1;
-    const V3 pp = ld3(sm.planes[k].p), pn = ld3(sm.planes[k].n);
-    const double time = dot(pn, pp - r.o) / dot(r.d, pn);
-    if (time > 0 && sink.in_front(r, time)) shadowed = true;
+  for (uint32_t k0 = 0; k0 < n_planes && !shadowed; k0 += 32) {
+    uint32_t maybe = 0;
+    const uint32_t kn = min(32u, n_planes - k0);
+    for (uint32_t k = 0; k < kn; k++) {
+      if (k0 == 0 && ((skip >> k) & 1u)) continue;
+      const double2* pl = (const double2*)&planes[k0 + k];
+      const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
+      const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
+      RH_CNT(prim, 1);
+      const double den = dot(q.ld, pn);
+      const double num = dot(pn, pp - q.o);
+      const bool miss = !(fabs(den) > 0) | (((num > 0) != (den > 0)) & (num == num)) |
+                        (fabs(num) > q.far * fabs(den) * 1.000000000001);
+      maybe |= (miss ? 0u : 1u) << k;
+    }
+    if (maybe) {
+      Ray r;
+      r.o = q.o;
+      r.d = q.ld;
+      const AnyHit sink = make_any_hit(q);
+      while (maybe) {  // cold: exact quotient and inFrontOfLight for the surviving planes
+        const uint32_t k = k0 + __ffs(maybe) - 1;
+        maybe &= maybe - 1;
+        const V3 pp = ld3(planes[k].p), pn = ld3(planes[k].n);
+        const double time = dot(pn, pp - r.o) / dot(r.d, pn);
+        if (time > 0 && sink.in_front(r, time)) shadowed = true;
+      }
+    }
   }
+  if (shadowed || !n_spheres) return shadowed;
+  Ray r;
+  r.o = q.o;
+  r.d = q.ld;
+  const AnyHit sink = make_any_hit(q);
   for (uint32_t k = 0; k < n_spheres && !shadowed; k++) {  // Geometry.hs:81-95
-    const V3 ct = ld3(sm.spheres[k].c);
-    const double rad = sm.spheres[k].r;
+    const V3 ct = ld3(spheres[k].c);
+    const double rad = spheres[k].r;
     RH_CNT(prim, 1);
     const double qa = dot(r.d, r.d);
     const double qb = 2.0 * dot(r.d, r.o - ct);
@@ -1808,14 +1121,16 @@ __device__ __forceinline__ bool primitives_occlude(const ShadowTables& sm, uint3
 
 // Does the pair's ray have to walk a tree?  Only the part of the ray between its origin and the light can hold an
 // occluder (inFrontOfLight).  The origin is within 1.000001e-6 of p in every coordinate, so when p and the light lie
-// beyond the same face of a (padded) root box, that part is outside the box; otherwise the root boxes get the float
-// slab test (slot 0 of each super-root).
+// beyond the same face of a (padded) root box, that part is outside the box.  A mesh is not walked either when the hit
+// lies on a triangle that nothing of its own mesh can shadow from this light (lit triangles, light_maps.cpp), or when
+// the light's cube map says no triangle of the mesh can lie between p and the light.  What is left gets the float slab
+// test of its root box (slot 0 of the super-root).
 template <bool COUNT>
-__device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const SceneView& S, bool exact_boxes, bool use_maps,
+__device__ __forceinline__ bool roots_need_walk(const SmemTables& sm, const SceneView& S, bool exact_boxes, bool use_maps,
                                                 uint32_t lit, uint32_t n_roots, uint32_t li, const V3& p, const LightPair& q,
                                                 Cnt<COUNT>& cnt) {
   bool may = exact_boxes;
-  uint32_t skip = 0;  // meshes that need no walk: lit triangle (see shadow_kernel_fast), then the light's cube maps
+  uint32_t skip = 0;
   if ((lit >> li) & 1u) skip = 1u << (lit >> 12);  // (lit is 0 when the flags are switched off)
   for (uint32_t m = 0; m < n_roots; m++) {
     if ((skip >> m) & 1u) continue;
@@ -1843,8 +1158,9 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
   bool need = false;
   for (uint32_t m = 0; m < n_roots && !need; m++) {
     if ((skip >> m) & 1u) continue;
-    const float4* np = (const float4*)&S.wide32[sm.mesh_roots[m]];
-    const float4 b0 = __ldg(np), b1 = __ldg(np + 1);
+    const uint32_t root = sm.mesh_roots[m];
+    const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
+    const float4 b0 = np[0], b1 = np[1];
     float tm;
     RH_CNT(nodes, 1);
     RH_CNT(box, 1);
@@ -1853,270 +1169,793 @@ __device__ __forceinline__ bool roots_need_walk(const ShadowTables& sm, const Sc
   return need;
 }
 
-constexpr int kClassifyBlock = 256;
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kClassifyBlock, 3) shadow_classify_kernel(const __grid_constant__ SceneView S,
-                                                                         const __grid_constant__ ChunkParams P) {
-  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
-  stage_shadow_tables(sm, S, false);
-  const uint32_t n_lights = S.n_lights, n_planes = S.n_occ_planes, n_spheres = S.n_occ_spheres;
+// The lights of one Diffuse / Plastic hit, everything that needs no tree walk: which lights add nothing (`settled`:
+// l.n <= 0 — the Lambert term (Material.hs:31-33) is then exactly 0 whatever the query returns — or a plane / sphere
+// occludes), which need a walk (`walk`), and, when none does, the fold itself (accumDiffuse's foldl in light order).
+struct LightFold {
+  uint32_t walk, settled, culled;
+  V3 acc;
+};
+// FAST: the occluder tables are the staged shared-memory ones (SceneView::shadow_fast), read with LDS.
+template <bool COUNT, bool FAST>
+__device__ __forceinline__ LightFold fold_lights(const SmemTables& sm, const Ctx& cx, const ChunkParams& P, const V3& p, const V3& n,
+                                                const V3& cd, uint32_t lit, Cnt<COUNT>& cnt) {
+  const SceneView& S = *cx.S;
+  LightFold F;
+  F.walk = F.settled = F.culled = 0;
+  F.acc = mk(0, 0, 0);  // foldl ... black lts
+  const uint32_t n_lights = S.n_lights;
+  constexpr bool fast = FAST;
+  const OccPlane* planes = fast ? sm.planes : S.occ_planes;
+  const OccSphere* spheres = fast ? sm.spheres : S.occ_spheres;
+  const rh_light* lights = fast ? sm.lights : cx.lights;
   const uint32_t n_roots = S.n_occ_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
   const bool use_maps = S.light_map_index != nullptr && !P.no_light_maps;
-  Cnt<COUNT> cnt;
-  cnt.zero();
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t n_items = min(ctl->shadow_count[P.pass], P.q_shadow.capacity);
-  const size_t cap = P.q_shadow.capacity;
-  const double2* qp = P.q_shadow.plane;
-  unsigned long long n_culled = 0;
-  const uint32_t stride = gridDim.x * kClassifyBlock;
-  const uint32_t n_rounds = (n_items + stride - 1) / stride;  // every warp runs the same number of rounds (ballots below)
-  for (uint32_t round = 0; round < n_rounds; round++) {
-    const uint32_t item = round * stride + blockIdx.x * kClassifyBlock + threadIdx.x;
-    uint32_t pending = 0, settled = 0;  // per light: queued for a walk / adds nothing
-    if (item < n_items) {
-      const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item];
-      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y);
-      const uint32_t lit = (S.lit_flags != nullptr && !P.no_light_maps) ? P.q_shadow.lit[item] : 0u;
-      V3 acc = mk(0, 0, 0), cd = mk(0, 0, 0);  // foldl ... black lts
-      bool have_cd = false;
-      for (uint32_t li = 0; li < n_lights; li++) {
-        const rh_light& L = sm.lights[li];
-        const LightPair q = make_light_pair(L, p);
-        const double ldn = dot(q.ld, n);
-        if (ldn <= 0) {  // Lambert term exactly 0: the query cannot change the sum (Material.hs:31-33)
-          n_culled++;
-          settled |= 1u << li;
-          continue;
-        }
-        if (primitives_occlude<COUNT>(sm, n_planes, n_spheres, q, cnt)) {
-          settled |= 1u << li;  // Just _ -> black
-          continue;
-        }
-        if (n_roots && roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, use_maps, lit, n_roots, li, p, q, cnt)) {
-          pending |= 1u << li;
-          continue;
-        }
-        if (pending) continue;  // the fold kernel redoes this hit: no point in the term
-        if (!have_cd) {
-          const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
-          cd = mk(d.x, d.y, e.x);
-          have_cd = true;
-        }
-        V3 lc = ld3(L.color);  // lightAt, Light.hs:14-17
-        if (!q.directional) {
-          const double s = 1.0 + q.dd / L.radius;
-          lc = mul(1.0 / (s * s), lc);
-        }
-        acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
-      }
-      if (!pending) {
-        const double2 d = qp[3 * cap + item], e = qp[4 * cap + item];
-        const uint32_t sbits = P.q_shadow.sample[item];
-        cd = mk(d.x, d.y, e.x);
-        const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;  // Diffuse adds the ambient term, RayHs.hs:111-114
-        accumulate(P, sbits & 0x7fffffffu, e.y, total);
-      } else {
-        for (uint32_t li = 0; li < n_lights; li++) P.pair_flags[(size_t)item * n_lights + li] = (uint8_t)((settled >> li) & 1u);
+  const bool cd_finite = isfinite(cd.x) && isfinite(cd.y) && isfinite(cd.z);
+  // Plane sides, once per hit instead of once per (hit, light).  f(x) = pn.(x - pp) is affine, so a plane can only hold a
+  // point of the shadow ray between its origin o and a point light L when f(o) and f(L) differ in sign.  o is within
+  // 1e-6 |ld| of the hit p, so |f(o) - f(p)| <= 1e-6 |pn|_1; with |f(p)| and |f(L)| both above the margin
+  // |pn|_1 (1e-5 + 1e-12 (|x|_1 + |pp|_1)) — which also covers the roundings of f — and equal in sign, the reference's
+  // own quotient n.(p-o)/(d.n) (Geometry.hs:70-79) is either negative (`time > 0` fails) or exceeds the distance to
+  // the light by >= 1e-5, far beyond the roundings of inFrontOfLight's comparison (RayHs.hs:84-87) for lights nearer
+  // than 1e9: the plane cannot occlude, and its two dot products are skipped.  The hit's own wall (f(p) ~ 0) and
+  // everything near a plane still get the reference's test.
+  uint32_t hit_front = 0, hit_behind = 0;
+  if constexpr (FAST) {
+    const double p1 = fabs(p.x) + fabs(p.y) + fabs(p.z);
+    for (uint32_t k = 0; k < S.n_occ_planes; k++) {
+      const double2* pl = (const double2*)&sm.planes[k];
+      const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
+      const double f = dot(mk(u1.y, u2.x, u2.y), p - mk(u0.x, u0.y, u1.x));
+      const double m = sm.plane_margin[k][0] + sm.plane_margin[k][1] * p1;
+      hit_front |= (f > m ? 1u : 0u) << k;
+      hit_behind |= (f < -m ? 1u : 0u) << k;
+    }
+  }
+  for (uint32_t li = 0; li < n_lights; li++) {
+    const rh_light& L = lights[li];
+    const LightPair q = make_light_pair(L, p);
+    const double ldn = dot(q.ld, n);
+    if (ldn <= 0 && cd_finite && light_is_tame(L)) {
+      F.culled++;
+      F.settled |= 1u << li;
+      continue;
+    }
+    uint32_t skip = 0;
+    if constexpr (FAST) {
+      if (q.dd < 1e9) skip = (hit_front & sm.light_front[li]) | (hit_behind & sm.light_behind[li]);
+    }
+    if (primitives_occlude<COUNT>(planes, S.n_occ_planes, spheres, S.n_occ_spheres, q, skip, cnt)) {
+      F.settled |= 1u << li;  // Just _ -> black
+      continue;
+    }
+    if (n_roots) {
+      // scenes beyond the staged tables (more than kOccMeshes meshes, kFastLights lights, ...) walk whenever there is a tree
+      const bool need = fast ? roots_need_walk<COUNT>(sm, S, P.exact_boxes != 0, use_maps, lit, n_roots, li, p, q, cnt) : true;
+      if (need) {
+        F.walk |= 1u << li;
+        continue;
       }
     }
-    // warp-aggregated append: one 64-bit atomic reserves the deferred slots (low word) and the walk slots (high word).
-    // The warp's pairs go in light-major order — all its pairs for light 0, then light 1, ... — so that consecutive
-    // queue entries are rays from neighbouring hits towards the same light, as coherent as the hits themselves.
-    const unsigned has = __ballot_sync(kFull, pending != 0);
-    if (has) {
-      uint32_t total_walks = 0, my_at = 0;  // my_at: offset of this lane's entry for the light being counted
-      uint32_t offs[kFastLights];
+    if (F.walk) continue;  // the shadow kernel redoes this hit's fold: no point in the term
+    V3 lc = ld3(L.color);  // lightAt, Light.hs:14-17
+    if (!q.directional) {
+      const double s = 1.0 + q.dd / L.radius;
+      lc = mul(1.0 / (s * s), lc);
+    }
+    F.acc = F.acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+  }
+  return F;
+}
+
+// The fold of a queued hit once its walks are done: `vis` bit l = light l adds nothing.
+__device__ __forceinline__ V3 fold_visible(const Ctx& cx, uint32_t n_lights, uint32_t vis, const V3& p, const V3& n, const V3& cd) {
+  V3 acc = mk(0, 0, 0);  // foldl ... black lts
+  for (uint32_t li = 0; li < n_lights; li++) {
+    if ((vis >> li) & 1u) continue;  // Just _ -> black (or l.n <= 0: the term is exactly 0)
+    V3 ld, lc;
+    light_at(cx.lights[li], p, ld, lc);
+    acc = acc + mul(hs_max(dot(ld, n), 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
+  }
+  return acc;
+}
+
+// Index of a pixel sample's offset pair in the offset array, or false when the mode has no array.
+__device__ __forceinline__ bool offset_slot(const ChunkParams& P, uint32_t item, size_t& idx, uint32_t& grow, uint32_t& col, uint32_t& s) {
+  const uint32_t lp = item / P.spp;
+  s = item - lp * P.spp;
+  const uint32_t lrow = lp / P.width;
+  col = lp - lrow * P.width;
+  grow = global_row(P, P.first_row + lrow);
+  if (P.offset_mode == RH_OFFSETS_TILED_F64)
+    idx = ((size_t)(grow % P.offset_tile) * P.offset_tile + (col % P.offset_tile)) * P.spp + s;
+  else if (P.offset_index == kOffIndexGlobal)
+    idx = ((size_t)grow * P.width + col) * P.spp + s;
+  else
+    idx = item;
+  return P.offset_mode == RH_OFFSETS_F64 || P.offset_mode == RH_OFFSETS_F32 || P.offset_mode == RH_OFFSETS_TILED_F64;
+}
+
+// One warp's staging tile for the NEXT batch of 32 work items: the four planes of a ray-queue batch (pass >= 1) or the
+// f64 offset pairs of 32 pixel samples (pass 0, plane 0 only), filled by bulk async copies.
+struct __align__(128) StageTile {
+  double2 plane[4][32];
+};
+struct Staged {
+  uint32_t first;   // first work item of the staged batch, kEmpty = nothing staged
+  uint32_t parity;  // phase of the warp's mbarrier the next wait uses
+};
+
+// Start the copy of the batch of `n` items beginning at `first` (lane 0 only calls this).  Pass 0: only when the
+// offsets are per-sample f64 pairs laid out in work-item order (P.offset_linear: chunk-local slices, or the full-frame
+// array of an unsharded frame), so that the batch's pairs are one contiguous run.
+// `dep`: a value derived from what this lane just read out of the tile; the copy's byte count is made to depend on
+// it, so the warp's shared-memory reads of the previous batch have returned before the copy engine may overwrite them.
+__device__ __forceinline__ bool stage_start(const ChunkParams& P, bool primary, uint32_t first, uint32_t n, StageTile* tile,
+                                            unsigned long long* bar, uint32_t dep) {
+  uint32_t zero;
+  asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(dep));
+  n += zero;
+  if (primary) {
+    if (!P.offset_linear) return false;
+    mbar_expect(bar, n * 16u);
+    bulk_g2s(tile->plane[0], (const double2*)P.offsets + P.offset_base + first, n * 16u, bar);
+    return true;
+  }
+  const size_t cap = P.q_in.capacity;
+  mbar_expect(bar, 4u * n * 16u);
 #pragma unroll
-      for (uint32_t li = 0; li < (uint32_t)kFastLights; li++) {
-        offs[li] = 0;
-        if (li < n_lights) {
-          const unsigned m = __ballot_sync(kFull, (pending >> li) & 1u);
-          offs[li] = total_walks + __popc(m & ((1u << lane) - 1));
-          total_walks += __popc(m);
+  for (int k = 0; k < 4; k++) bulk_g2s(tile->plane[k], P.q_in.plane + (size_t)k * cap + first, n * 16u, bar);
+  return true;
+}
+
+// Work item -> ray: the camera ray of a pixel sample (pass 0: pixelCoord, Image.hs:31-32, + sample offset,
+// RayHs.hs:178-181) or a queued secondary ray with its weight and tags.  False for a padding row of the last band.
+// `tile`: the item's batch was staged in shared memory (see stage_start), else it is read from global memory.
+__device__ __forceinline__ bool load_item(const ChunkParams& P, const CameraParams& cam, uint32_t item, bool primary,
+                                          const StageTile* tile, uint32_t lane, Ray& r, double& w, uint32_t& sample, int& depth,
+                                          int& kind, uint32_t& probe_mat) {
+  r.o = r.d = mk(0, 0, 1);
+  if (primary) {
+    size_t idx;
+    uint32_t grow, col, s;
+    const bool has_array = offset_slot(P, item, idx, grow, col, s);
+    if (grow >= P.height) return false;
+    double ox = 0, oy = 0;
+    if (P.offset_mode == RH_OFFSETS_SPLITMIX64) {
+      // values 2g and 2g+1 of the stream rh_sample_offsets_f64(seed, ...) writes (x before y, RayHs.hs:185-188)
+      const unsigned long long g = ((unsigned long long)grow * P.width + col) * P.spp + s;
+      ox = splitmix01(P.offset_seed, 2 * g) - 0.5;
+      oy = splitmix01(P.offset_seed, 2 * g + 1) - 0.5;
+    } else if (has_array) {
+      if (P.offset_mode == RH_OFFSETS_F32) {
+        const float2 o2 = __ldg((const float2*)P.offsets + idx);
+        ox = (double)o2.x;
+        oy = (double)o2.y;
+      } else {
+        const double2 o2 = tile ? tile->plane[0][lane] : __ldg((const double2*)P.offsets + idx);
+        ox = o2.x;
+        oy = o2.y;
+      }
+    }
+    r = camera_ray(cam, (double)col + ox, (double)grow + oy);
+    return true;
+  }
+  double2 a, b, c, d;
+  if (tile) {
+    a = tile->plane[0][lane], b = tile->plane[1][lane], c = tile->plane[2][lane], d = tile->plane[3][lane];
+  } else {
+    const size_t cap = P.q_in.capacity;
+    a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item], d = P.q_in.plane[3 * cap + item];
+  }
+  r.o = mk(a.x, a.y, b.x);
+  r.d = mk(b.y, c.x, c.y);
+  w = d.x;
+  const uint64_t bits = (uint64_t)__double_as_longlong(d.y);
+  sample = (uint32_t)bits;
+  depth = (int)((bits >> 32) & 0xff);
+  kind = (int)((bits >> 40) & 0xff);
+  probe_mat = (uint32_t)((bits >> 48) & 0x7fff);
+  return true;
+}
+
+// ------------------------------------------------------------------ K1/K2/K4/K5
+struct TraceWarpSmem {
+#if RH_TMA_STAGE
+  StageTile tile;
+#endif
+  unsigned long long bar;
+  SlabWriter out_rays, out_shadow;  // the warp's open slabs of the two output queues
+  unsigned long long pad_[12];
+};
+static_assert(sizeof(TraceWarpSmem) % 128 == 0, "staging tiles stay 128-byte aligned");
+constexpr size_t kTraceSmem = sizeof(SmemTables) + (size_t)kShortStack * kTraceBlock * sizeof(uint2) +
+                              (kTraceBlock / 32) * sizeof(TraceWarpSmem);
+static_assert(sizeof(SmemTables) % 128 == 0 || !RH_TMA_STAGE, "staging tiles need 128-byte alignment after the tables");
+static_assert(((size_t)kShortStack * kTraceBlock * sizeof(uint2)) % 128 == 0, "stack columns keep the alignment");
+static_assert(kTraceSmem <= 227 * 1024, "trace kernel shared memory");
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_constant__ SceneView S,
+                                                               const __grid_constant__ CameraParams cam,
+                                                               const __grid_constant__ ChunkParams P) {
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  Stack st = make_stack(rh_smem + sizeof(SmemTables), kTraceBlock, P);
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  const uint32_t lane = threadIdx.x & 31;
+  const bool primary = (P.pass == 0);
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_slabs = primary ? (P.n_samples + kSlab - 1) / kSlab : min(ctl->ray_slabs[P.pass], P.q_in.capacity / kSlab);
+  uint32_t n_reflect = 0, n_probe = 0, n_exit = 0, n_shaded = 0;  // (per thread: far below 2^32)
+  TraceWarpSmem& wsm = reinterpret_cast<TraceWarpSmem*>(rh_smem + sizeof(SmemTables) + (size_t)kShortStack * kTraceBlock * sizeof(uint2))[threadIdx.x >> 5];
+  SlabWriter& out_rays = wsm.out_rays;  // warp-uniform state, kept out of the register file
+  SlabWriter& out_shadow = wsm.out_shadow;
+  if (lane == 0) {
+    out_rays.init();
+    out_shadow.init();
+  }
+#if RH_TMA_STAGE
+  if (lane == 0) mbar_init(&wsm.bar);
+  Staged staged;
+  staged.first = kEmpty;
+  staged.parity = 0;
+#endif
+  __syncwarp();
+
+  for (;;) {
+    uint32_t slab = 0;
+    if (lane == 0) slab = atomicAdd(&ctl->trace_cursor[P.pass], 1u);  // one atomic per kSlab work items
+    slab = __shfl_sync(kFull, slab, 0);
+    if (slab >= n_slabs) break;
+    const uint32_t slab_first = slab * kSlab;
+    const uint32_t count = primary ? min(kSlab, P.n_samples - slab_first) : min(__ldg(P.q_in.fill + slab), kSlab);
+    for (uint32_t b = 0; b < count; b += 32) {
+      const uint32_t item = slab_first + b + lane;
+      bool valid = b + lane < count;
+      Ray r;
+      double w = 1;
+      uint32_t sample = item, probe_mat = 0;
+      int depth = 0, kind = kRayNormal;
+      const StageTile* tile = nullptr;
+#if RH_TMA_STAGE
+      if (staged.first == slab_first + b) {  // this batch was asked for while the previous one was traced
+        mbar_wait(&wsm.bar, staged.parity);
+        staged.parity ^= 1u;
+        tile = &wsm.tile;
+      }
+#endif
+      if (valid) valid = load_item(P, cam, item, primary, tile, lane, r, w, sample, depth, kind, probe_mat);
+      else r.o = r.d = mk(0, 0, 1);
+#if RH_TMA_STAGE
+      // the tile is in registers now: ask for the next batch of this slab; it lands while this one is traced
+      __syncwarp();
+      staged.first = kEmpty;
+      if (b + 32 < count) {
+        uint32_t ok = 0;
+        const uint32_t dep = (uint32_t)(__double2loint(r.o.x) ^ __double2loint(r.d.x) ^ __double2loint(w));
+        if (lane == 0) ok = stage_start(P, primary, slab_first + b + 32, min(32u, count - b - 32), &wsm.tile, &wsm.bar, dep) ? 1u : 0u;
+        if (__shfl_sync(kFull, ok, 0)) staged.first = slab_first + b + 32;
+      }
+#endif
+
+      Closest best;
+      best.obj = -1;
+      if (valid) {
+        const bool exact = P.exact_boxes || needs_exact_walk(r, S);
+        unsigned long long nodes_before = 0;
+        if constexpr (COUNT) nodes_before = cnt.nodes;
+        closest_hit<COUNT>(cx, r, exact, best, st, cnt);
+        if constexpr (COUNT) {
+          if (exact) atomicAdd(&P.counters->exact_closest, 1ull);
+          atomicMax(&P.counters->max_closest_nodes, cnt.nodes - nodes_before);
         }
       }
-      (void)my_at;
-      unsigned long long base = 0;
-      if (lane == 0)
-        base = atomicAdd(&ctl->deferred_walk_count[P.pass], ((unsigned long long)total_walks << 32) | (unsigned long long)__popc(has));
-      base = __shfl_sync(kFull, base, 0);
-      if (pending) {
-        const uint32_t dslot = (uint32_t)base + __popc(has & ((1u << lane) - 1));
-        P.deferred_q[dslot] = item;  // deferred hits <= shadow tasks <= capacity
-#pragma unroll
-        for (uint32_t li = 0; li < (uint32_t)kFastLights; li++) {
-          if (li < n_lights && ((pending >> li) & 1u)) {
-            const uint32_t w = (uint32_t)(base >> 32) + offs[li];
-            if (w < P.walk_capacity) P.walk_q[w] = make_uint2(item, li);
-            else ctl->overflow = 1;
+      if (primary && valid && P.hit_ids) {
+        int tri = -1;
+        if (best.obj >= 0 && cx.objects[best.obj].kind == RH_OBJ_MESH) tri = (int)S.tris[best.slot].tri_id;
+        P.hit_ids[(size_t)P.first_row * P.width * P.spp + item] = make_int2(best.obj, tri);
+      }
+      // RayHs.hs:149-154: a miss contributes black — nothing to do.
+      const bool hit = valid && best.obj >= 0;
+
+      // ---- shade (irradiance, RayHs.hs:107-147), in stages the whole warp walks through together so that every queue
+      // push is one ballot; the recursion is unrolled into weighted child rays: every combine in the reference is
+      // `mul scalar colour` + add, so a child carries the scalar product `w`.
+      V3 p = mk(0, 0, 0), n = mk(0, 0, 1);
+      double tu = 0, tv = 0;
+      int mkind = -1, okind = -1;
+      uint32_t mat_index = 0;
+      if (hit) {
+        // rebuild the Hit (Geometry.hs:39) of the winning primitive
+        const DObject& ob = cx.objects[best.obj];
+        mat_index = (uint32_t)ob.material;
+        const rh_material& mat = cx.materials[mat_index];
+        mkind = mat.kind;
+        okind = ob.kind;
+        const bool need_uv = (kind == kRayNormal) && (mkind == RH_MAT_SHOWUV ||
+                                                      ((mkind == RH_MAT_DIFFUSE || mkind == RH_MAT_PLASTIC) && mat.cmap_kind != RH_CMAP_FLAT));
+        p = rayAt(r, best.t);
+        if (okind == RH_OBJ_MESH) {
+          const double* sh = (const double*)(S.shade + best.slot);
+          RH_CNT(shade, 1);
+          const double wu = best.u, wv = best.v, ww = 1 - best.u - best.v;
+          // barycentricInterp u n1 v n2 (1-u-v) n0 = mul a p + mul b q + mul c r   (Mesh.hs:57, 81)
+          n = mul(wu, ld3(sh + 3)) + mul(wv, ld3(sh + 6)) + mul(ww, ld3(sh));
+          if (need_uv) {
+            tu = wu * sh[11] + wv * sh[13] + ww * sh[9];
+            tv = wu * sh[12] + wv * sh[14] + ww * sh[10];
+          }
+        } else if (okind == RH_OBJ_PLANE) {  // Geometry.hs:70-79
+          n = ld3(ob.b);
+          if (need_uv) {
+            const V3 tg = ld3(ob.c);
+            const V3 bt = cross(tg, n);
+            const V3 rel = p - ld3(ob.a);
+            tu = dot(tg, rel);
+            tv = dot(bt, rel);
+          }
+        } else {  // Geometry.hs:83-96
+          n = normalize(p - ld3(ob.a));
+          if (need_uv) {
+            tu = kPiInv * atan(n.z / n.x);
+            tv = kPiInv * acos(n.y);
           }
         }
+      }
+      const bool probe = hit && kind == kRayProbe;
+      const bool surface = hit && kind != kRayProbe;
+
+      // child ray A: the specular reflection (RayHs.hs:99-104) of Plastic / Mirror / Transparent, or — for the interior
+      // probe of a Transparent hit (RayHs.hs:140-143) — the ray that leaves through the far interface
+      {
+        bool has = false, is_exit = false;
+        Ray ra;
+        ra.o = ra.d = mk(0, 0, 1);
+        double wa = 0;
+        uint64_t bits = 0;
+        if (probe) {
+          const double ior = cx.materials[probe_mat].ior;
+          V3 outDir;
+          if (refract(r.d, neg(n), ior, 1.0, outDir)) {
+            has = is_exit = true;
+            ra = rayEps(p, outDir);
+            wa = w;
+            bits = pack_bits(sample, depth, kRayNormal, 0);
+          }
+        } else if (surface && (mkind == RH_MAT_PLASTIC || mkind == RH_MAT_MIRROR || mkind == RH_MAT_TRANSPARENT) && depth < P.max_depth) {
+          const double ior = cx.materials[mat_index].ior;
+          const V3 rd = reflect(r.d, n);
+          const double f = fresnel(ior, dot(n, neg(r.d)));
+          has = true;
+          ra = rayEps(p, rd);
+          wa = w * (f * dot(rd, n));
+          bits = pack_bits(sample, depth + 1, kRayNormal, 0);
+        }
+        if (has) {
+          if (is_exit) n_exit++;
+          else n_reflect++;
+        }
+        push_ray(has, ra, wa, bits, P.q_out, out_rays, &ctl->ray_slabs[P.pass + 1], &ctl->overflow, lane);
+      }
+      // child ray B: the interior probe of a Transparent hit (RayHs.hs:136-139)
+      if (__any_sync(kFull, surface && mkind == RH_MAT_TRANSPARENT)) {
+        bool has = false;
+        Ray rb;
+        rb.o = rb.d = mk(0, 0, 1);
+        double wb = 0;
+        uint64_t bits = 0;
+        if (surface && mkind == RH_MAT_TRANSPARENT && depth != P.max_depth) {
+          const double ior = cx.materials[mat_index].ior;
+          V3 refDir;
+          if (refract(r.d, n, 1.0, ior, refDir)) {
+            has = true;
+            rb = rayEps(p, refDir);
+            wb = w * (1 - r0f(ior, 1.0));
+            bits = pack_bits(sample, depth + 1, kRayProbe, mat_index);
+            n_probe++;
+          }
+        }
+        push_ray(has, rb, wb, bits, P.q_out, out_rays, &ctl->ray_slabs[P.pass + 1], &ctl->overflow, lane);
+      }
+      // local terms that need no light
+      if (surface) {
+        if (mkind == RH_MAT_EMMIT) accumulate(P, sample, w, ld3(cx.materials[mat_index].color1));
+        else if (mkind == RH_MAT_SHOWNORMAL) accumulate(P, sample, w, n);
+        else if (mkind == RH_MAT_SHOWUV) accumulate(P, sample, w, mk(tu, tv, 0));
+      }
+      // Diffuse / Plastic: ambient + accumDiffuse (RayHs.hs:111-119) — the hit goes to the hit queue with its colour;
+      // classify_kernel folds its lights
+      {
+        const bool lit_surface = surface && (mkind == RH_MAT_DIFFUSE || mkind == RH_MAT_PLASTIC);
+        ShadowTask task;
+        if (lit_surface) {
+          n_shaded++;
+          task.p = p;
+          task.n = n;
+          task.cd = color_at<COUNT>(cx, cx.materials[mat_index], tu, tv, cnt);
+          task.w = w;
+          task.sample = sample | (mkind == RH_MAT_DIFFUSE ? 0x80000000u : 0u);
+          // lit-triangle flags of the hit triangle (light_maps.cpp) travel in the `walk` word of the hit queue
+          task.walk = (okind == RH_OBJ_MESH && S.lit_flags && !P.no_light_maps) ? (uint32_t)__ldg(S.lit_flags + best.slot) : 0u;
+          task.settled = 0;
+        }
+        push_shadow(lit_surface, task, P.q_hits, out_shadow, &ctl->hit_slabs[P.pass], &ctl->overflow, lane);
       }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
-  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
+  slab_close(out_rays, lane, P.q_out.fill, &ctl->ray_items[P.pass + 1]);
+  slab_close(out_shadow, lane, P.q_hits.fill, &ctl->hit_items[P.pass]);
+
+  // ray-class statistics (one ray per closestIntersection call, SURVEY 8d)
+  const uint32_t per_thread[4] = {n_reflect, n_probe, n_exit, n_shaded};
+  unsigned long long* const totals[4] = {&P.counters->rays_reflect, &P.counters->rays_probe, &P.counters->rays_exit,
+                                         &P.counters->shaded_hits};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned long long v = per_thread[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if (lane == 0 && v) atomicAdd(totals[k], v);
+  }
+  flush_counters<COUNT>(cnt, P.counters, 0);
+}
+
+// ------------------------------------------------------------------ K3a: the light fold of every shaded hit
+// One thread per Diffuse / Plastic hit of the pass: all its lights, everything that needs no tree (Lambert cull, planes,
+// linear spheres, root boxes, lit triangles, cube maps).  A hit whose lights are all settled is folded and accumulated
+// on the spot (accumDiffuse, RayHs.hs:89-97); a hit with a light whose shadow ray has to walk a tree goes to the walk
+// queue with the two light masks.  Straight-line code, no stack, small enough for the instruction cache.
+#ifndef RH_CLASSIFY_BLOCK
+#define RH_CLASSIFY_BLOCK 256
+#define RH_CLASSIFY_MINB 3
+#endif
+constexpr int kClassifyBlock = RH_CLASSIFY_BLOCK;
+struct ClassifyWarpSmem {
+  SlabWriter out;
+  uint32_t pad_;
+};
+constexpr size_t kClassifySmem = sizeof(SmemTables) + (kClassifyBlock / 32) * sizeof(ClassifyWarpSmem);
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_kernel(const __grid_constant__ SceneView S,
+                                                                     const __grid_constant__ ChunkParams P) {
+  SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
+  Ctx cx;
+  stage_tables(sm, S, cx);
+  const uint32_t lane = threadIdx.x & 31;
+  SlabWriter& out = reinterpret_cast<ClassifyWarpSmem*>(rh_smem + sizeof(SmemTables))[threadIdx.x >> 5].out;
+  if (lane == 0) out.init();
+  __syncwarp();
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_slabs = min(ctl->hit_slabs[P.pass], P.q_hits.capacity / kSlab);
+  const size_t cap = P.q_hits.capacity;
+  const double2* qp = P.q_hits.plane;
+  uint32_t n_culled = 0, n_walk_pairs = 0;
+  for (;;) {
+    uint32_t slab = 0;
+    if (lane == 0) slab = atomicAdd(&ctl->hit_cursor[P.pass], 1u);
+    slab = __shfl_sync(kFull, slab, 0);
+    if (slab >= n_slabs) break;
+    const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
+    for (uint32_t b = 0; b < n_here; b += 32) {
+      const uint32_t item = slab * kSlab + b + lane;
+      const bool valid = b + lane < n_here;
+      ShadowTask task;
+      bool queue = false;
+      if (valid) {
+        const double2 a = qp[item], bq = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
+        task.sample = P.q_hits.sample[item];
+        const uint32_t lit = P.q_hits.walk[item];
+        task.p = mk(a.x, a.y, bq.x);
+        task.n = mk(bq.y, c.x, c.y);
+        task.cd = mk(d.x, d.y, e.x);
+        task.w = e.y;
+        const LightFold F = S.shadow_fast ? fold_lights<COUNT, true>(sm, cx, P, task.p, task.n, task.cd, lit, cnt)
+                                          : fold_lights<COUNT, false>(sm, cx, P, task.p, task.n, task.cd, lit, cnt);
+        n_culled += F.culled;
+        if (F.walk) {
+          queue = true;
+          n_walk_pairs += __popc(F.walk);
+          task.walk = F.walk;
+          task.settled = F.settled;
+        } else {
+          const V3 total = (task.sample & 0x80000000u) ? mul(0.2, task.cd) + F.acc : F.acc;  // Diffuse adds the ambient term, RayHs.hs:111-114
+          accumulate(P, task.sample & 0x7fffffffu, task.w, total);
+        }
+      }
+      push_shadow(queue, task, P.q_shadow, out, &ctl->shadow_slabs[P.pass], &ctl->overflow, lane);
+    }
+  }
+  slab_close(out, lane, P.q_shadow.fill, &ctl->shadow_items[P.pass]);
+  unsigned long long vc = n_culled, vw = n_walk_pairs;
+  for (int o = 16; o > 0; o >>= 1) {
+    vc += __shfl_xor_sync(kFull, vc, o);
+    vw += __shfl_xor_sync(kFull, vw, o);
+  }
+  if (lane == 0) {
+    if (vc) atomicAdd(&P.counters->shadow_culled, vc);
+    if (vw) atomicAdd(&P.counters->shadow_walk_pairs, vw);
+  }
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
-constexpr int kWalkBlock = RH_WALK_BLOCK;
-constexpr uint32_t kWalkChunk = 256;   // walk-queue entries a warp claims per atomic
-constexpr uint32_t kRefillMin = RH_REFILL_MIN;  // idle lanes that trigger a refill while other lanes are still walking
+// ------------------------------------------------------------------ K3: the tree walks of the queued hits
+// The (hit, light) pair's any-hit walk over the occluding trees (RayHs.hs:74-87 for the mesh objects and the sphere
+// tree; planes and linear spheres were settled by the trace kernel).  True = occluded.
+template <bool COUNT>
+__device__ __forceinline__ bool walk_pair(const Ctx& cx, const ChunkParams& P, const uint32_t* mesh_roots, uint32_t n_meshes,
+                                          const rh_light& L, const V3& p, Stack& st, Cnt<COUNT>& cnt) {
+  const SceneView& S = *cx.S;
+  const LightPair q = make_light_pair(L, p);
+  Ray r;
+  r.o = q.o;
+  r.d = q.ld;
+  AnyHit sink = make_any_hit(q);
+  const bool exact = P.exact_boxes || needs_exact_walk(r, S);
+  const RayF f = make_rayf(r, S);
+  bool hit = false;
+  unsigned long long nodes_before = 0;
+  if constexpr (COUNT) {
+    nodes_before = cnt.nodes;
+    if (exact) atomicAdd(&P.counters->exact_walks, 1ull);
+  }
+  for (uint32_t m = 0; m < n_meshes && !hit; m++) {
+    double bound = q.far;
+    hit = exact ? traverse_exact<COUNT>(cx, mesh_roots[m], r, bound, sink, st, cnt)
+                : traverse<COUNT>(cx, mesh_roots[m], r, f, bound, sink, st, cnt);
+  }
+  if (!hit && S.sphere_root != kEmpty) {
+    double bound = q.far;
+    hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, S.sphere_root, r, bound, sink, st, cnt, true)
+                : traverse<COUNT, AnyHit, true>(cx, S.sphere_root, r, f, bound, sink, st, cnt, true);
+  }
+  if constexpr (COUNT) atomicMax(&P.counters->max_walk_nodes, cnt.nodes - nodes_before);
+  return hit;
+}
+
+// Pooled form, for coherent rays.  Each warp takes one slab of queued hits (<= 128, 4 per lane) and, light by light
+// (rays towards one light from neighbouring samples stay coherent),
+//   phase 1  appends the hits whose mask asks for a walk towards that light to a warp-local pool in shared memory
+//            (ballot + prefix-popcount compaction);
+//   phase 2  walks the pool in full rounds of 32, every lane on a ray that needs it; what is left over (< 32) stays
+//            pooled and joins the next light's rays.  An occluded pair sets its bit in the hit's visibility word
+//            (shared-memory atomicOr);
+//   phase 3  every lane folds the lights of its own hits in order (accumDiffuse's foldl, RayHs.hs:89-97) with those
+//            bits and adds w * (ambient + sum) to the sample.
+constexpr int kShadowT = kSlab / 32;
+struct ShadowWarpSmem {
+  uint32_t vis[kSlab];        // bit li: light li adds nothing for this hit
+  uint16_t pool[kSlab + 32];  // hit-in-slab | light << 8
+};
+static_assert(sizeof(ShadowWarpSmem) % 16 == 0, "the stack columns follow the per-warp regions");
+static_assert(kSlab <= 256 && kMaskLights <= 256, "pool entries keep the hit index and the light in 8 bits each");
+constexpr size_t kShadowSmem = sizeof(WalkTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem) +
+                               (size_t)kShortStack * kShadowBlock * sizeof(uint2);
+static_assert(kShadowSmem <= 227 * 1024, "pooled shadow kernel shared memory");
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kWalkBlock, 1) shadow_walk_kernel(const __grid_constant__ SceneView S,
-                                                                                     const __grid_constant__ ChunkParams P) {
-  ShadowTables& sm = *reinterpret_cast<ShadowTables*>(rh_smem);
-  stage_shadow_tables(sm, S, true);
+__global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __grid_constant__ SceneView S,
+                                                                        const __grid_constant__ ChunkParams P) {
+  WalkTables& sm = *reinterpret_cast<WalkTables*>(rh_smem);
   Ctx cx;
-  cx.S = &S;
-  cx.sm_nodes = sm.nodes;
-  cx.objects = S.objects;  // sphere-tree leaves only
-  cx.materials = S.materials;
-  cx.lights = sm.lights;
-  const uint32_t n_lights = S.n_lights, n_roots = S.n_occ_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
-  const uint32_t n_smem = S.n_smem_nodes;
+  stage_walk_tables(sm, S, cx);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ShadowWarpSmem& ws = reinterpret_cast<ShadowWarpSmem*>(rh_smem + sizeof(WalkTables))[warp];
+  Stack st = make_stack(rh_smem + sizeof(WalkTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem), kShadowBlock, P);
+  const uint32_t n_lights = S.n_lights, n_meshes = S.n_occ_meshes;
+  const uint32_t* mesh_roots = n_meshes <= (uint32_t)kOccMeshes ? sm.mesh_roots : S.occ_meshes;
+  Cnt<COUNT> cnt;
+  cnt.zero();
+  ChunkCtl* ctl = P.ctl;
+  const uint32_t n_slabs = min(ctl->shadow_slabs[P.pass], P.q_shadow.capacity / kSlab);
+  const size_t cap = P.q_shadow.capacity;
+  const double2* qp = P.q_shadow.plane;
+
+  for (;;) {
+    uint32_t slab = 0;
+    if (lane == 0) slab = atomicAdd(&ctl->shadow_cursor[P.pass], 1u);
+    slab = __shfl_sync(kFull, slab, 0);
+    if (slab >= n_slabs) break;
+    const uint32_t base = slab * kSlab, n_here = min(__ldg(P.q_shadow.fill + slab), kSlab);
+    uint32_t wm[kShadowT];
+#pragma unroll
+    for (int t = 0; t < kShadowT; t++) {
+      const uint32_t j = t * 32 + lane;
+      wm[t] = 0;
+      if (j < n_here) {
+        wm[t] = P.q_shadow.walk[base + j];
+        ws.vis[j] = P.q_shadow.settled[base + j];
+      }
+    }
+    __syncwarp();
+    uint32_t pool_n = 0;
+    for (uint32_t li = 0; li < n_lights; li++) {
+      // ---- phase 1
+#pragma unroll
+      for (int t = 0; t < kShadowT; t++) {
+        const bool need = (wm[t] >> li) & 1u;
+        const unsigned m = __ballot_sync(kFull, need);
+        if (need) ws.pool[pool_n + __popc(m & ((1u << lane) - 1))] = (uint16_t)((t * 32 + lane) | (li << 8));
+        pool_n += __popc(m);
+      }
+      __syncwarp();
+      // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
+      const bool last = (li + 1 == n_lights);
+      const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
+      for (uint32_t i = lane; i < n_full; i += 32) {
+        const uint32_t e = ws.pool[i], j = e & 0xff, lw = e >> 8;
+        const double2 a = qp[base + j], b = qp[cap + base + j];
+        if (walk_pair<COUNT>(cx, P, mesh_roots, n_meshes, cx.lights[lw], mk(a.x, a.y, b.x), st, cnt)) atomicOr(&ws.vis[j], 1u << lw);
+      }
+      __syncwarp();
+      const uint32_t rem = pool_n - n_full;
+      uint16_t keep = 0;
+      if (lane < rem) keep = ws.pool[n_full + lane];
+      __syncwarp();
+      if (lane < rem) ws.pool[lane] = keep;
+      pool_n = rem;
+      __syncwarp();
+    }
+    // ---- phase 3: accumDiffuse's fold over the lights, in order
+#pragma unroll 1
+    for (int t = 0; t < kShadowT; t++) {
+      const uint32_t j = t * 32 + lane;
+      if (j >= n_here) continue;
+      const uint32_t item = base + j;
+      const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
+      const uint32_t sbits = P.q_shadow.sample[item];
+      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+      const V3 acc = fold_visible(cx, n_lights, ws.vis[j], p, n, cd);
+      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;  // Diffuse adds the ambient term, RayHs.hs:111-114
+      accumulate(P, sbits & 0x7fffffffu, e.y, total);
+    }
+    __syncwarp();
+  }
+  flush_counters<COUNT>(cnt, P.counters, 1);
+}
+
+// Per-lane refill form, for incoherent rays (triangle soups: unoccluded rays walk hundreds of nodes while occluded ones
+// stop after a few, and a pooled round lasts as long as its longest walk).  One queued hit per lane; a lane whose ray
+// has ended starts the walk towards its hit's next light, or — when the hit has none left — folds the hit and takes
+// the next one of the warp's slab, while its neighbours keep walking.  The loop is warp-uniform: votes decide between
+// the refill, inner-node and leaf steps, so the lanes reconverge at every step by construction.
+constexpr uint32_t kRefillMin = RH_REFILL_MIN;  // lanes without a ray in flight that trigger a refill step
+constexpr int kWalkColumns = 12;                // per-thread doubles in shared memory: ray origin, direction, far, dl2, hit point, (spare)
+constexpr size_t kWalkSmem = sizeof(WalkTables) + (size_t)kWalkColumns * kWalkBlock * sizeof(double) +
+                             (size_t)kShortStack * kWalkBlock * sizeof(uint2);
+static_assert(kWalkSmem <= 227 * 1024, "refill shadow kernel shared memory");
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWalkBlock, 1) shadow_refill_kernel(const __grid_constant__ SceneView S,
+                                                                      const __grid_constant__ ChunkParams P) {
+  WalkTables& sm = *reinterpret_cast<WalkTables*>(rh_smem);
+  Ctx cx;
+  stage_walk_tables(sm, S, cx);
+  const uint32_t n_lights = S.n_lights, n_meshes = S.n_occ_meshes;
+  const uint32_t n_roots = n_meshes + (S.sphere_root != kEmpty ? 1u : 0u);
+  const uint32_t* mesh_roots = n_meshes <= (uint32_t)kOccMeshes ? sm.mesh_roots : S.occ_meshes;
   const rh_tri* tris = S.tris;
-  uint4 stack[kStack];
+  // Lane state: what every inner-node step needs stays in registers (the float ray, the node reference, the stack
+  // pointer); what only a leaf or the fold needs lives in a per-thread column of shared memory.
+  double* lane_mem = reinterpret_cast<double*>(rh_smem + sizeof(WalkTables)) + threadIdx.x;
+  auto lane_slot = [&](int k) -> double& { return lane_mem[k * kWalkBlock]; };  // 0-2 o, 3-5 d, 6 far, 7 dl2, 8-10 hit point
+  Stack st = make_stack(rh_smem + sizeof(WalkTables) + (size_t)kWalkColumns * kWalkBlock * sizeof(double), kWalkBlock, P);
   Cnt<COUNT> cnt;
   cnt.zero();
   ChunkCtl* ctl = P.ctl;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t n_items = min((uint32_t)(ctl->deferred_walk_count[P.pass] >> 32), P.walk_capacity);
+  const uint32_t n_slabs = min(ctl->shadow_slabs[P.pass], P.q_shadow.capacity / kSlab);
   const size_t cap = P.q_shadow.capacity;
   const double2* qp = P.q_shadow.plane;
 
-  uint32_t pos = 0, end = 0;  // this warp's claimed range of the walk queue
+  uint32_t pos = 0, end = 0;  // this warp's claimed range of queued hits
   bool exhausted = false;
-  // Lane state: the ray in flight.  What every inner-node step needs stays in registers (the float ray, the node
-  // reference, the stack pointer); what only a leaf needs — the double ray, the light distance, where to report an
-  // occluder — lives in a per-thread column of shared memory, so that the node loop does not spill.
-  double* lane_mem = reinterpret_cast<double*>(rh_smem + sizeof(ShadowTables)) + threadIdx.x;
-  auto lane_slot = [&](int k) -> double& { return lane_mem[k * kWalkBlock]; };  // 0-2 o, 3-5 d, 6 far, 7 dl2, 8 flag index
-  bool active = false, directional = false;
+  bool walking = false, has_task = false, directional = false;
+  uint32_t item = 0, rest = 0, vis = 0, cur = 0;  // the lane's hit, its lights still to walk, lights that add nothing, light in flight
   RayF f;
   f.ix = f.iy = f.iz = f.pix = f.piy = f.piz = f.mix = f.miy = f.miz = 0.f;
   float ffar = 0;
-  uint32_t ref = 0, first = 0;
+  uint32_t ref = 0;
   int sp = 0;
 
   for (;;) {
-    // ---- refill: idle lanes take the next queued pairs
-    const unsigned idle = __ballot_sync(kFull, !active);
-    const uint32_t n_idle = __popc(idle);
-    if (n_idle >= kRefillMin) {
-      if (pos == end && !exhausted) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(&ctl->walk_cursor[P.pass], kWalkChunk);
-        b = __shfl_sync(kFull, b, 0);
-        if (b >= n_items) exhausted = true;
-        else {
-          pos = b;
-          end = min(b + kWalkChunk, n_items);
-        }
+    // ---- refill: lanes without a ray in flight fold a finished hit, take a new one, start the next light
+    const unsigned idle = __ballot_sync(kFull, !walking);
+    if (__popc(idle) >= kRefillMin) {
+      if (!walking && has_task && rest == 0) {  // all lights known: accumDiffuse's fold, in order
+        const double2 bq = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
+        const uint32_t sbits = P.q_shadow.sample[item];
+        const V3 p = mk(lane_slot(8), lane_slot(9), lane_slot(10)), n = mk(bq.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+        const V3 acc = fold_visible(cx, n_lights, vis, p, n, cd);
+        const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;  // Diffuse adds the ambient term, RayHs.hs:111-114
+        accumulate(P, sbits & 0x7fffffffu, e.y, total);
+        has_task = false;
       }
-      if (pos < end) {
-        const uint32_t take = min(n_idle, end - pos);
-        const uint32_t rank = __popc(idle & ((1u << lane) - 1));
-        if (!active && rank < take) {
-          const uint2 e = P.walk_q[pos + rank];
-          const uint32_t item = e.x, li = e.y;
-          const double2 a = qp[item], b = qp[cap + item];
-          const LightPair q = make_light_pair(sm.lights[li], mk(a.x, a.y, b.x));
-          Ray r;
-          r.o = q.o;
-          r.d = q.ld;
-          AnyHit sink;
-          sink.directional = q.directional;
-          sink.lpos = q.lp;
-          sink.dl2 = q.directional ? 0.0 : sqrDist(r.o, q.lp);
-          const size_t flag_at = (size_t)item * n_lights + li;
-          if (P.exact_boxes || needs_exact_walk(r, S)) {
-            // rare (far origins): the reference's own double boxes, run to the end right here
-            if constexpr (COUNT) atomicAdd(&P.counters->exact_walks, 1ull);
-            bool hit = false;
-            for (uint32_t m = 0; m < n_roots && !hit; m++) {
-              double bound = q.far;
-              if (m < S.n_occ_meshes) hit = traverse_exact<COUNT>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt);
-              else hit = traverse_exact<COUNT, AnyHit, true>(cx, sm.mesh_roots[m], r, bound, sink, stack, cnt, true);
-            }
-            if (hit) P.pair_flags[flag_at] = 1;
-          } else {
-            lane_slot(0) = r.o.x; lane_slot(1) = r.o.y; lane_slot(2) = r.o.z;
-            lane_slot(3) = r.d.x; lane_slot(4) = r.d.y; lane_slot(5) = r.d.z;
-            lane_slot(6) = q.far;
-            lane_slot(7) = sink.dl2;
-            lane_slot(8) = __longlong_as_double((long long)flag_at);
-            directional = q.directional;
-            f = make_rayf(r, S);
-            ffar = __double2float_ru(q.far);
-            sp = 0;
-            for (uint32_t m = 1; m < n_roots; m++) stack[sp++] = make_uint4(sm.mesh_roots[m], 0, 0, 0);  // entry distance 0
-            ref = sm.mesh_roots[0];
-            first = 0;
-            active = true;
+      const unsigned empty = __ballot_sync(kFull, !has_task);
+      if (empty) {
+        if (pos == end && !exhausted) {
+          uint32_t s = 0;
+          if (lane == 0) s = atomicAdd(&ctl->shadow_cursor[P.pass], 1u);
+          s = __shfl_sync(kFull, s, 0);
+          if (s >= n_slabs) exhausted = true;
+          else {
+            pos = s * kSlab;
+            end = pos + min(__ldg(P.q_shadow.fill + s), kSlab);
           }
         }
-        pos += take;
-      } else if (n_idle == 32) {
-        break;  // nothing in flight, nothing left to claim
+        if (pos < end) {
+          const uint32_t take = min((uint32_t)__popc(empty), end - pos);
+          const uint32_t rank = __popc(empty & ((1u << lane) - 1));
+          if (!has_task && rank < take) {
+            item = pos + rank;
+            rest = P.q_shadow.walk[item];
+            vis = P.q_shadow.settled[item];
+            const double2 a = qp[item], b = qp[cap + item];
+            lane_slot(8) = a.x; lane_slot(9) = a.y; lane_slot(10) = b.x;
+            has_task = true;
+          }
+          pos += take;
+        } else if (exhausted && empty == kFull) {
+          break;  // nothing in flight, nothing left to claim
+        }
+      }
+      if (!walking && has_task && rest != 0) {  // the walk towards the hit's next light
+        cur = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const LightPair q = make_light_pair(cx.lights[cur], mk(lane_slot(8), lane_slot(9), lane_slot(10)));
+        Ray r;
+        r.o = q.o;
+        r.d = q.ld;
+        AnyHit sink = make_any_hit(q);
+        if (P.exact_boxes || needs_exact_walk(r, S)) {
+          // rare (far origins): the reference's own double boxes, run to the end right here
+          if constexpr (COUNT) atomicAdd(&P.counters->exact_walks, 1ull);
+          bool hit = false;
+          for (uint32_t m = 0; m < n_roots && !hit; m++) {
+            double bound = q.far;
+            if (m < n_meshes) hit = traverse_exact<COUNT>(cx, mesh_roots[m], r, bound, sink, st, cnt);
+            else hit = traverse_exact<COUNT, AnyHit, true>(cx, S.sphere_root, r, bound, sink, st, cnt, true);
+          }
+          if (hit) vis |= 1u << cur;
+        } else if (n_roots) {
+          lane_slot(0) = r.o.x; lane_slot(1) = r.o.y; lane_slot(2) = r.o.z;
+          lane_slot(3) = r.d.x; lane_slot(4) = r.d.y; lane_slot(5) = r.d.z;
+          lane_slot(6) = q.far;
+          lane_slot(7) = sink.dl2;
+          directional = q.directional;
+          f = make_rayf(r, S);
+          ffar = __double2float_ru(q.far);
+          sp = 0;
+          for (uint32_t m = n_roots; m-- > 1;)  // the other roots wait on the stack (entry distance 0), first mesh on top
+            st.push(sp, m < n_meshes ? mesh_roots[m] : S.sphere_root, 0.f);
+          ref = n_meshes ? mesh_roots[0] : S.sphere_root;
+          walking = true;
+        }
       }
     }
-    // ---- inner nodes: step until every ray in flight holds a leaf (KDTree.hs:96-107 with the conservative float boxes);
-    // two steps per vote
-    auto node_step = [&]() {
-      const float4* np = ref < n_smem ? (const float4*)&sm.nodes[ref] : (const float4*)&S.wide32[ref];
-      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
-      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
-      RH_CNT(nodes, 1);
-      bool h0 = false, h1 = false;
-      float tm0 = 0, tm1 = 0;
-      if (cw.x != kEmpty) {
-        RH_CNT(box, 1);
-        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > ffar);
-      }
-      if (cw.y != kEmpty) {
-        RH_CNT(box, 1);
-        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > ffar);
-      }
-      if (h0 && h1) {
-        if (tm1 < tm0) {
-          stack[sp++] = make_uint4(cw.x, cw.z, 0, 0);
-          ref = cw.y;
-          first = cw.w;
-        } else {
-          stack[sp++] = make_uint4(cw.y, cw.w, 0, 0);
-          ref = cw.x;
-          first = cw.z;
-        }
-      } else if (h0) {
-        ref = cw.x;
-        first = cw.z;
-      } else if (h1) {
-        ref = cw.y;
-        first = cw.w;
-      } else if (sp == 0) {
-        active = false;  // nothing in front of the light
-      } else {
-        const uint4 e = stack[--sp];
-        ref = e.x;
-        first = e.y;
+    // ---- inner nodes: step until every ray in flight holds a leaf (KDTree.hs:96-107 with the conservative float
+    // boxes); RH_WALK_UNROLL steps per vote
+    auto step = [&]() {
+      if (!node_step<COUNT>(cx, ref, f, ffar, st, sp, cnt)) {
+        if (sp == 0) walking = false;  // nothing in front of the light
+        else ref = st.pop(sp).x;
       }
     };
     for (;;) {
-      bool inner = active && !(ref & kLeafBit);
+      bool inner = walking && !(ref & kLeafBit);
       if (!__any_sync(kFull, inner)) break;
-      if (inner) node_step();
+      if (inner) step();
 #if RH_WALK_UNROLL > 1
-      inner = active && !(ref & kLeafBit);
-      if (inner) node_step();
+      inner = walking && !(ref & kLeafBit);
+      if (inner) step();
 #endif
     }
     // ---- leaves: every ray in flight holds one (Mesh.hs:59-82 / Geometry.hs:81-95 per candidate)
-    if (active) {
+    if (walking) {
       Ray r;
       r.o = mk(lane_slot(0), lane_slot(1), lane_slot(2));
       r.d = mk(lane_slot(3), lane_slot(4), lane_slot(5));
@@ -2125,264 +1964,77 @@ __global__ void __launch_bounds__(kWalkBlock, 1) shadow_walk_kernel(const __grid
       sink.directional = directional;
       sink.lpos = mk(0, 0, 0);
       sink.dl2 = lane_slot(7);
+      const uint32_t first = ref & kLeafFirstMask, count = ((ref >> kLeafCountShift) & (kLeafMaxCount - 1)) + 1;
       bool hit;
-      if (ref & kSphereLeafBit) hit = test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, sink, bound, true, cnt);
-      else hit = test_leaf<COUNT>(tris, first, ref & kCountMask, r, sink, bound, cnt);
+      if (ref & kSphereLeafBit) hit = test_sphere_leaf<COUNT>(cx, first, count, r, sink, bound, true, cnt);
+      else hit = test_leaf<COUNT>(tris, first, count, r, sink, bound, cnt);
       if (hit) {
-        P.pair_flags[(size_t)__double_as_longlong(lane_slot(8))] = 1;  // shadowIntersection = Just _
-        active = false;
+        vis |= 1u << cur;  // shadowIntersection = Just _
+        walking = false;
       } else if (sp == 0) {
-        active = false;
+        walking = false;
       } else {
-        const uint4 e = stack[--sp];
-        ref = e.x;
-        first = e.y;
+        ref = st.pop(sp).x;
       }
     }
   }
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
+// Simple form, for scenes with more than 32 lights (the masks of a queued hit hold 32): every Diffuse / Plastic hit is
+// queued unclassified; one hit per lane, lights in sequence, each query over the whole object list run to completion.
+constexpr size_t kSimpleSmem = sizeof(SmemTables) + (size_t)kShortStack * kShadowBlock * sizeof(uint2);
 template <bool COUNT>
-__global__ void __launch_bounds__(kClassifyBlock) shadow_fold_kernel(const __grid_constant__ SceneView S,
-                                                                     const __grid_constant__ ChunkParams P) {
-  __shared__ rh_light lights[kFastLights];
-  const uint32_t n_lights = S.n_lights;
-  copy16(lights, S.lights, n_lights * (uint32_t)sizeof(rh_light));
-  __syncthreads();
-  ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = min((uint32_t)ctl->deferred_walk_count[P.pass], P.q_shadow.capacity);
-  const size_t cap = P.q_shadow.capacity;
-  const double2* qp = P.q_shadow.plane;
-  for (uint32_t i = blockIdx.x * kClassifyBlock + threadIdx.x; i < n_items; i += gridDim.x * kClassifyBlock) {
-    const uint32_t item = P.deferred_q[i];
-    const double2 a = qp[item], b = qp[cap + item], c = qp[2 * cap + item], d = qp[3 * cap + item], e = qp[4 * cap + item];
-    const uint32_t sbits = P.q_shadow.sample[item];
-    const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
-    const uint8_t* fl = P.pair_flags + (size_t)item * n_lights;
-    V3 acc = mk(0, 0, 0);  // foldl ... black lts
-    for (uint32_t li = 0; li < n_lights; li++) {
-      if (fl[li]) continue;  // Just _ -> black (or l.n <= 0: the term is exactly 0)
-      V3 ld, lc;
-      light_at(lights[li], p, ld, lc);
-      acc = acc + mul(hs_max(dot(ld, n), 0) * kPiInv, cmul(cd, lc));  // diffuse, Material.hs:31-33
-    }
-    const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
-    accumulate(P, sbits & 0x7fffffffu, e.y, total);
-  }
-}
-
-// ------------------------------------------------------------------ K1/K4 split: intersect -> shade
-// The closest-hit search of trace_kernel with the walk kernel's per-lane refill: a lane whose ray has finished writes
-// its hit record and takes the next work item while its neighbours keep walking.  Incoherent rays (reflections, the
-// synthetic triangle soup: 5-9 active threads per instruction in trace_kernel's walks) keep the warp busy this way;
-// trace_kernel<COUNT, true> then shades from the records with no tree code in it.  Meshes are walked in scene order
-// (their roots are stacked in reverse), planes and linear spheres are tested when the item is taken; ties between
-// objects go to the lower object index (Closest::offer), within a mesh to the reference's key.
-constexpr int kIsectBlock = RH_ISECT_BLOCK;
-constexpr size_t kIsectSmem = sizeof(SmemTables) + 10 * kIsectBlock * sizeof(double);
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kIsectBlock, 1) intersect_kernel(const __grid_constant__ SceneView S,
-                                                                   const __grid_constant__ CameraParams cam,
-                                                                   const __grid_constant__ ChunkParams P) {
+__global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __grid_constant__ SceneView S,
+                                                                        const __grid_constant__ ChunkParams P) {
   SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
   Ctx cx;
   stage_tables(sm, S, cx);
-  // per-thread columns: 0-2 origin, 3-5 direction, 6 best t, 7 u, 8 v, 9 slot | obj << 32
-  double* lane_mem = reinterpret_cast<double*>(rh_smem + sizeof(SmemTables)) + threadIdx.x;
-  auto lane_slot = [&](int k) -> double& { return lane_mem[k * kIsectBlock]; };
-  uint4 stack[kStack];
+  Stack st = make_stack(rh_smem + sizeof(SmemTables), kShadowBlock, P);
   Cnt<COUNT> cnt;
   cnt.zero();
   const uint32_t lane = threadIdx.x & 31;
-  const bool primary = (P.pass == 0);
   ChunkCtl* ctl = P.ctl;
-  const uint32_t n_items = primary ? P.n_samples : min(ctl->ray_count[P.pass], P.q_in.capacity);
-  const uint32_t n_smem = S.n_smem_nodes, n_lin = S.n_lin, sphere_root = S.sphere_root;
-  const rh_tri* tris = S.tris;
-  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-
-  uint32_t pos = 0, end = 0;
-  bool exhausted = false;
-  bool active = false;
-  RayF f;
-  f.ix = f.iy = f.iz = f.pix = f.piy = f.piz = f.mix = f.miy = f.miz = 0.f;
-  float fb = 0;  // float upper bound of best t * slack
-  uint32_t ref = 0, first = 0, item = 0;
-  int sp = 0, cur_obj = -1;
-
-  auto write_record = [&](uint32_t it, double t, double u, double v, uint32_t slot, int obj) {
-    P.hits[it] = make_double4(t, u, v, __longlong_as_double((long long)(((unsigned long long)(uint32_t)obj << 32) | slot)));
-  };
-  auto finish = [&]() {
-    const unsigned long long so = (unsigned long long)__double_as_longlong(lane_slot(9));
-    write_record(item, lane_slot(6), lane_slot(7), lane_slot(8), (uint32_t)so, (int)(uint32_t)(so >> 32));
-    active = false;
-  };
-  auto pop_next = [&]() {  // next stacked subtree the bound does not prune, or the ray is done
-    for (;;) {
-      if (sp == 0) {
-        finish();
-        return;
-      }
-      const uint4 e = stack[--sp];
-      if (__uint_as_float(e.z) > fb) continue;
-      ref = e.x;
-      first = e.y;
-      if (e.w) cur_obj = (int)e.w - 1;  // a mesh's super-root: hits below it belong to this object
-      return;
-    }
-  };
-
+  const uint32_t n_slabs = min(ctl->hit_slabs[P.pass], P.q_hits.capacity / kSlab);
+  const size_t cap = P.q_hits.capacity;
+  unsigned long long n_culled = 0;
   for (;;) {
-    // ---- refill
-    const unsigned idle = __ballot_sync(kFull, !active);
-    const uint32_t n_idle = __popc(idle);
-    if (n_idle >= kRefillMin) {
-      if (pos == end && !exhausted) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(&ctl->isect_cursor[P.pass], kWalkChunk);
-        b = __shfl_sync(kFull, b, 0);
-        if (b >= n_items) exhausted = true;
-        else {
-          pos = b;
-          end = min(b + kWalkChunk, n_items);
+    uint32_t slab = 0;
+    if (lane == 0) slab = atomicAdd(&ctl->hit_cursor[P.pass], 1u);
+    slab = __shfl_sync(kFull, slab, 0);
+    if (slab >= n_slabs) break;
+    const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
+    for (uint32_t j = lane; j < n_here; j += 32) {
+      const uint32_t item = slab * kSlab + j;
+      const double2 a = P.q_hits.plane[item], b = P.q_hits.plane[cap + item], c = P.q_hits.plane[2 * cap + item],
+                    d = P.q_hits.plane[3 * cap + item], e = P.q_hits.plane[4 * cap + item];
+      const uint32_t sbits = P.q_hits.sample[item];
+      const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
+      const double w = e.y;
+      const bool cd_finite = isfinite(cd.x) && isfinite(cd.y) && isfinite(cd.z);
+      V3 acc = mk(0, 0, 0);  // foldl ... black lts
+      for (uint32_t li = 0; li < S.n_lights; li++) {
+        const rh_light& L = cx.lights[li];
+        V3 ld, lc;
+        light_at(L, p, ld, lc);
+        // diffuse (Material.hs:31-33) = (max (l.n) 0 / pi) * (cd (*) lc): exactly zero when l.n <= 0 (and the colours
+        // are finite), whether or not the point is shadowed, so the occlusion query cannot change the sum
+        const double ldn = dot(ld, n);
+        if (ldn <= 0 && cd_finite && light_is_tame(L)) {
+          n_culled++;
+          continue;
         }
+        const Ray sr = rayEps(p, ld);
+        const bool shadowed = occluded<COUNT>(cx, sr, P.exact_boxes || needs_exact_walk(sr, S), L, st, cnt);
+        if (!shadowed) acc = acc + mul(hs_max(ldn, 0) * kPiInv, cmul(cd, lc));
       }
-      if (pos < end) {
-        const uint32_t take = min(n_idle, end - pos);
-        const uint32_t rank = __popc(idle & ((1u << lane) - 1));
-        if (!active && rank < take) {
-          item = pos + rank;
-          Ray r;
-          double w = 1;
-          uint32_t sample = 0, probe_mat = 0;
-          int depth = 0, kind = 0;
-          if (!load_item(P, cam, item, primary, r, w, sample, depth, kind, probe_mat)) {
-            write_record(item, kInf, 0, 0, 0, -1);  // padding row
-          } else if (P.exact_boxes || needs_exact_walk(r, S)) {
-            // rare (far origins): the whole search with the reference's double boxes, right here
-            Closest best;
-            if constexpr (COUNT) atomicAdd(&P.counters->exact_closest, 1ull);
-            closest_hit<COUNT>(cx, r, true, best, stack, cnt);
-            write_record(item, best.t, best.u, best.v, best.slot, best.obj);
-          } else {
-            // planes and linear spheres (Geometry.hs:68-96) now; mesh roots on the stack, first mesh on top
-            double bt = kInf;
-            int bobj = -1;
-            sp = 0;
-            if (sphere_root != kEmpty) stack[sp++] = make_uint4(sphere_root, 0, 0, 0);
-            for (uint32_t k = n_lin; k-- > 0;) {
-              const uint32_t i = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
-              const DObject& ob = cx.objects[i];
-              if (ob.kind == RH_OBJ_MESH && ob.root != kEmpty) stack[sp++] = make_uint4(ob.root, 0, 0, i + 1);
-            }
-            for (uint32_t k = 0; k < n_lin; k++) {
-              const uint32_t i = sphere_root == kEmpty ? k : __ldg(S.lin_objs + k);
-              const DObject& ob = cx.objects[i];
-              const int okind = ob.kind;
-              if (okind == RH_OBJ_MESH) continue;
-              double time;
-              RH_CNT(prim, 1);
-              const bool hit = (okind == RH_OBJ_PLANE) ? plane_time(r, ob, bt, time) : sphere_time(r, ob, time);
-              if (hit && time < bt) {
-                bt = time;
-                bobj = (int)i;
-              }
-            }
-            lane_slot(0) = r.o.x; lane_slot(1) = r.o.y; lane_slot(2) = r.o.z;
-            lane_slot(3) = r.d.x; lane_slot(4) = r.d.y; lane_slot(5) = r.d.z;
-            lane_slot(6) = bt;
-            lane_slot(7) = 0;
-            lane_slot(8) = 0;
-            lane_slot(9) = __longlong_as_double((long long)((unsigned long long)(uint32_t)bobj << 32));
-            f = make_rayf(r, S);
-            fb = __double2float_ru(bt * kPruneSlack);
-            cur_obj = -1;
-            active = true;
-            pop_next();  // (no tree at all: writes the record)
-          }
-        }
-        pos += take;
-      } else if (n_idle == 32) {
-        break;
-      }
-    }
-    // ---- inner nodes (KDTree.hs:96-107, ordered and pruned, conservative float boxes); two steps per vote
-    auto node_step = [&]() {
-      const float4* np = ref < n_smem ? (const float4*)&sm.nodes[ref] : (const float4*)&S.wide32[ref];
-      const float4 b0 = np[0], b1 = np[1], b2 = np[2];
-      const uint4 cw = *(const uint4*)(np + 3);  // child0, child1, first0, first1
-      RH_CNT(nodes, 1);
-      bool h0 = false, h1 = false;
-      float tm0 = 0, tm1 = 0;
-      if (cw.x != kEmpty) {
-        RH_CNT(box, 1);
-        h0 = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm0) && !(tm0 > fb);
-      }
-      if (cw.y != kEmpty) {
-        RH_CNT(box, 1);
-        h1 = slab32(f, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, tm1) && !(tm1 > fb);
-      }
-      if (h0 && h1) {
-        if (tm1 < tm0) {
-          stack[sp++] = make_uint4(cw.x, cw.z, __float_as_uint(tm0), 0);
-          ref = cw.y;
-          first = cw.w;
-        } else {
-          stack[sp++] = make_uint4(cw.y, cw.w, __float_as_uint(tm1), 0);
-          ref = cw.x;
-          first = cw.z;
-        }
-      } else if (h0) {
-        ref = cw.x;
-        first = cw.z;
-      } else if (h1) {
-        ref = cw.y;
-        first = cw.w;
-      } else {
-        pop_next();
-      }
-    };
-    for (;;) {
-      bool inner = active && !(ref & kLeafBit);
-      if (!__any_sync(kFull, inner)) break;
-      if (inner) node_step();
-      inner = active && !(ref & kLeafBit);
-      if (inner) node_step();
-    }
-    // ---- leaves
-    if (active) {
-      Ray r;
-      r.o = mk(lane_slot(0), lane_slot(1), lane_slot(2));
-      r.d = mk(lane_slot(3), lane_slot(4), lane_slot(5));
-      Closest best;
-      const unsigned long long so = (unsigned long long)__double_as_longlong(lane_slot(9));
-      best.t = lane_slot(6);
-      best.u = lane_slot(7);
-      best.v = lane_slot(8);
-      best.slot = (uint32_t)so;
-      best.obj = (int)(uint32_t)(so >> 32);
-      best.cur_obj = cur_obj;
-      best.tris = tris;
-      const double t_before = best.t;
-      const uint32_t slot_before = best.slot;
-      const int obj_before = best.obj;
-      double bound = best.t * kPruneSlack;
-      if (ref & kSphereLeafBit) test_sphere_leaf<COUNT>(cx, first, ref & kCountMask, r, best, bound, false, cnt);
-      else test_leaf<COUNT>(tris, first, ref & kCountMask, r, best, bound, cnt);
-      if (best.t != t_before || best.slot != slot_before || best.obj != obj_before) {
-        lane_slot(6) = best.t;
-        lane_slot(7) = best.u;
-        lane_slot(8) = best.v;
-        lane_slot(9) = __longlong_as_double((long long)(((unsigned long long)(uint32_t)best.obj << 32) | best.slot));
-        fb = __double2float_ru(best.t * kPruneSlack);
-      }
-      pop_next();
+      const V3 total = (sbits & 0x80000000u) ? mul(0.2, cd) + acc : acc;
+      accumulate(P, sbits & 0x7fffffffu, w, total);
     }
   }
-  flush_counters<COUNT>(cnt, P.counters, 0);
+  for (int o = 16; o > 0; o >>= 1) n_culled += __shfl_xor_sync(kFull, n_culled, o);
+  if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
+  flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
@@ -2514,30 +2166,28 @@ __global__ void dfma_bench_kernel(double* sink, int iters) {
   if (s == 1.2345e300) sink[0] = s;
 }
 
+// Sequential 16-byte loads over a buffer (coalesced, every byte once per sweep): with a buffer that fits the 126 MB L2
+// this is the L2 -> SM streaming rate, the denominator for `lts__t_bytes` of the traversal kernels.
+__global__ void stream_bench_kernel(const double2* __restrict__ buf, uint64_t n_elems, double2* sink) {
+  double2 acc = make_double2(0, 0);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += 4 * stride) {
+    double2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (i + k * stride < n_elems) ? __ldg(buf + i + k * stride) : make_double2(0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      acc.x += v[k].x;
+      acc.y += v[k].y;
+    }
+  }
+  if (acc.x == 1.2345e300) sink[0] = acc;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
-constexpr size_t kTraceSmem = sizeof(SmemTables);
-constexpr size_t kShadowSmem = sizeof(SmemTables) + (kShadowBlock / 32) * sizeof(ShadowWarpSmem);
-// fast kernel: tables + per-warp vis/pool + per-warp pair terms (at most 32 * kShadowT * 3 pairs of 16 bytes)
-constexpr size_t kShadowFastSmem =
-    sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * kPairSlots * sizeof(double2));
-static_assert(kShadowFastSmem <= 227 * 1024, "fast shadow kernel shared memory");
-// What a launch really asks for: the pair terms of T(n_lights) hits per lane.  Shared memory is carved out of the same
-// 256 KB as the L1 cache, and the walks live on L1 hits: 4.6 KB of terms per warp instead of the 6 KB maximum is worth
-// 3 % of the shadow time on the bench frame.
-static size_t shadow_fast_smem(uint32_t n_lights) {
-  const uint32_t L = n_lights ? n_lights : 1;
-  uint32_t T = RH_SHADOW_PAIRS / L;
-  T = T < 1 ? 1 : (T > (uint32_t)kShadowT ? (uint32_t)kShadowT : T);
-  return sizeof(ShadowTables) + (kShadowBlock / 32) * (sizeof(ShadowWarpSmem) + 32 * (size_t)T * L * sizeof(double2));
-}
-
-constexpr size_t kWalkSmem = sizeof(ShadowTables) + 9 * kWalkBlock * sizeof(double);  // tables + per-thread ray columns
 static int g_classify_grid[2] = {148, 148};
-static int g_walk_grid = 148;
-bool shadow_split_possible(const SceneView& S) { return S.shadow_fast && RH_SHADOW_SPLIT && RH_SHADOW_POOL; }
-
 int configure_kernels() {
   cudaError_t e = cudaSuccess;
   auto set = [&](const void* fn, size_t bytes) {
@@ -2545,75 +2195,53 @@ int configure_kernels() {
   };
   set((const void*)trace_kernel<true>, kTraceSmem);
   set((const void*)trace_kernel<false>, kTraceSmem);
-  set((const void*)trace_kernel<true, true>, kTraceSmem);
-  set((const void*)trace_kernel<false, true>, kTraceSmem);
-  set((const void*)intersect_kernel<true>, kIsectSmem);
-  set((const void*)intersect_kernel<false>, kIsectSmem);
-  set((const void*)shadow_kernel<true>, kShadowSmem);
-  set((const void*)shadow_kernel<false>, kShadowSmem);
-  set((const void*)shadow_kernel_fast<true>, kShadowFastSmem);
-  set((const void*)shadow_kernel_fast<false>, kShadowFastSmem);
-  set((const void*)shadow_walk_kernel<true>, kWalkSmem);
-  set((const void*)shadow_walk_kernel<false>, kWalkSmem);
-  set((const void*)shadow_kernel_simple<true>, kShadowSmem);
-  set((const void*)shadow_kernel_simple<false>, kShadowSmem);
+  set((const void*)shadow_pooled_kernel<true>, kShadowSmem);
+  set((const void*)shadow_pooled_kernel<false>, kShadowSmem);
+  set((const void*)shadow_refill_kernel<true>, kWalkSmem);
+  set((const void*)shadow_refill_kernel<false>, kWalkSmem);
+  set((const void*)shadow_simple_kernel<true>, kSimpleSmem);
+  set((const void*)shadow_simple_kernel<false>, kSimpleSmem);
+  set((const void*)classify_kernel<true>, kClassifySmem);
+  set((const void*)classify_kernel<false>, kClassifySmem);
   if (e == cudaSuccess) {
     int dev = 0, sms = 0, nb = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shadow_classify_kernel<false>, kClassifyBlock, sizeof(ShadowTables));
-    g_classify_grid[0] = sms * (nb > 0 ? nb : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, shadow_classify_kernel<true>, kClassifyBlock, sizeof(ShadowTables));
-    g_classify_grid[1] = sms * (nb > 0 ? nb : 1);
-    g_walk_grid = sms;  // persistent: one block per SM
+    for (int c = 0; c < 2; c++) {
+      if (c) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<true>, kClassifyBlock, kClassifySmem);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<false>, kClassifyBlock, kClassifySmem);
+      g_classify_grid[c] = sms * (nb > 0 ? nb : 1);
+    }
   }
   return (int)e;
 }
-void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, bool split, int grid, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (split) {  // intersect (per-lane refill) -> shade from the hit records
-    if (count) {
-      intersect_kernel<true><<<g_walk_grid, kIsectBlock, kIsectSmem, st>>>(S, cam, P);
-      trace_kernel<true, true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
-    } else {
-      intersect_kernel<false><<<g_walk_grid, kIsectBlock, kIsectSmem, st>>>(S, cam, P);
-      trace_kernel<false, true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
-    }
-  } else if (count) {
-    trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
-  } else {
-    trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
-  }
+int max_threads_per_launch(int n_sms) {
+  const int b = kTraceBlock > kShadowBlock ? (kTraceBlock > kWalkBlock ? kTraceBlock : kWalkBlock)
+                                           : (kShadowBlock > kWalkBlock ? kShadowBlock : kWalkBlock);
+  return n_sms * b;  // every traversal kernel runs one block per SM
 }
-void launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool split, int grid, void* stream) {
-  const bool simple = S.n_lights > 32 || RH_SHADOW_POOL == 0;
-  if (split && shadow_split_possible(S)) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (count) {
-      shadow_classify_kernel<true><<<g_classify_grid[1], kClassifyBlock, sizeof(ShadowTables), st>>>(S, P);
-      shadow_walk_kernel<true><<<g_walk_grid, kWalkBlock, kWalkSmem, st>>>(S, P);
-      shadow_fold_kernel<true><<<g_classify_grid[1], kClassifyBlock, 0, st>>>(S, P);
-    } else {
-      shadow_classify_kernel<false><<<g_classify_grid[0], kClassifyBlock, sizeof(ShadowTables), st>>>(S, P);
-      shadow_walk_kernel<false><<<g_walk_grid, kWalkBlock, kWalkSmem, st>>>(S, P);
-      shadow_fold_kernel<false><<<g_classify_grid[0], kClassifyBlock, 0, st>>>(S, P);
-    }
-  } else if (S.shadow_fast && RH_SHADOW_FAST && !simple) {
-    if (count)
-      shadow_kernel_fast<true><<<grid, kShadowBlock, shadow_fast_smem(S.n_lights), (cudaStream_t)stream>>>(S, P);
-    else
-      shadow_kernel_fast<false><<<grid, kShadowBlock, shadow_fast_smem(S.n_lights), (cudaStream_t)stream>>>(S, P);
-  } else if (simple) {
-    if (count)
-      shadow_kernel_simple<true><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
-    else
-      shadow_kernel_simple<false><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
-  } else {
-    if (count)
-      shadow_kernel<true><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
-    else
-      shadow_kernel<false><<<grid, kShadowBlock, kShadowSmem, (cudaStream_t)stream>>>(S, P);
+void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count) trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  else trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+}
+int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S.n_lights > (uint32_t)kMaskLights) {
+    if (count) shadow_simple_kernel<true><<<grid, kShadowBlock, kSimpleSmem, st>>>(S, P);
+    else shadow_simple_kernel<false><<<grid, kShadowBlock, kSimpleSmem, st>>>(S, P);
+    return 1;
   }
+  if (count) classify_kernel<true><<<g_classify_grid[1], kClassifyBlock, kClassifySmem, st>>>(S, P);
+  else classify_kernel<false><<<g_classify_grid[0], kClassifyBlock, kClassifySmem, st>>>(S, P);
+  if (refill) {
+    if (count) shadow_refill_kernel<true><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
+    else shadow_refill_kernel<false><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
+  } else {
+    if (count) shadow_pooled_kernel<true><<<grid, kShadowBlock, kShadowSmem, st>>>(S, P);
+    else shadow_pooled_kernel<false><<<grid, kShadowBlock, kShadowSmem, st>>>(S, P);
+  }
+  return 2;
 }
 void launch_resolve(const ChunkParams& P, void* stream) {
   const uint32_t n_pixels = P.n_rows * P.width;
@@ -2627,25 +2255,12 @@ void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int h
   deinterleave_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gathered, out, (uint32_t)width * 3, height, shard_count,
                                                               band_height, rows_per_shard);
 }
-int trace_blocks_per_sm(bool count) {
-  int n = 0;
-  if (count)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<true>, kTraceBlock, kTraceSmem);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<false>, kTraceBlock, kTraceSmem);
-  return n;
-}
-int shadow_blocks_per_sm(bool count) {
-  int n = 0;
-  if (count)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<true>, kShadowBlock, kShadowSmem);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shadow_kernel<false>, kShadowBlock, kShadowSmem);
-  return n;
-}
 void launch_gather_bench(const double2* buf, uint64_t n_records, uint32_t loads_per_thread, double2* sink, int grid, int block,
                          void* stream) {
   gather_bench_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(buf, n_records, loads_per_thread, sink);
+}
+void launch_stream_bench(const double2* buf, uint64_t n_elems, double2* sink, int grid, int block, void* stream) {
+  stream_bench_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(buf, n_elems, sink);
 }
 void launch_dfma_bench(double* sink, int iters, int grid, int block, void* stream) {
   dfma_bench_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sink, iters);

@@ -85,12 +85,12 @@ struct Device {
   std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
   // per-lane scratch: a chunk's accumulators and queues
   struct Scratch {
-    DevBuf accum, rayq[2], shq, shq_sample, walk_q, deferred_q, pair_flags, hits;
+    DevBuf accum, rayq[2], rayq_fill[2], hitq, hitq_words, shq, shq_words, deep;
   } lane[2];
   DevBuf ctl, counters, offsets, rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
   size_t pinned_bytes = 0;
-  int grid_trace[2] = {0, 0}, grid_shadow[2] = {0, 0};
+  int max_threads = 0;  // largest grid * block of the traversal kernels (one block per SM)
   std::vector<cudaEvent_t> prof_events;
 
   int open(int device) {
@@ -109,10 +109,7 @@ struct Device {
     RH_CUDA(cudaEventCreate(&ev_begin));
     RH_CUDA(cudaEventCreate(&ev_end));
     RH_CUDA((cudaError_t)configure_kernels());
-    for (int c = 0; c < 2; c++) {
-      grid_trace[c] = n_sms * std::max(1, trace_blocks_per_sm(c != 0));
-      grid_shadow[c] = n_sms * std::max(1, shadow_blocks_per_sm(c != 0));
-    }
+    max_threads = max_threads_per_launch(n_sms);
     RH_CUDA(cudaGetLastError());
     return RH_OK;
   }
@@ -120,7 +117,7 @@ struct Device {
     if (dev < 0) return;
     cudaSetDevice(dev);
     for (Scratch& sc : lane)
-      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.shq, &sc.shq_sample, &sc.walk_q, &sc.deferred_q, &sc.pair_flags, &sc.hits})
+      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.rayq_fill[0], &sc.rayq_fill[1], &sc.hitq, &sc.hitq_words, &sc.shq, &sc.shq_words, &sc.deep})
         b->release();
     for (DevBuf* b : {&ctl, &counters, &offsets, &rgb, &ids})
       b->release();
@@ -154,13 +151,17 @@ struct rh_scene {
   DevBuf wide, wide32, tris, shade, objects, materials, lights, textures, texels, lin_objs, sphere_refs, occ_planes, occ_spheres, occ_meshes, exact_index, light_maps, light_map_index, lit_flags;
   SceneView view{};
   uint32_t max_tree_depth = 0;
+  uint32_t deep_entries = 1;     // per-thread entries of the deep-stack scratch this scene's walks can need
+  bool refill_possible = true;   // the per-lane-refill shadow kernel stacks every tree root: not with hundreds of meshes
   bool has_transparent = false;  // some material is Transparent (Material.hs:18): frames need the probe passes
-  // shadow schedule chosen for this scene: 0 = undecided (timing frames, see render_on), 1 = pooled, 2 = split
+  // Shadow-walk schedule of this scene: 0 = undecided, 1 = pooled, 2 = per-lane refill.  Decided by timing one large
+  // frame with each (render_on); frames too small to time use the pooled kernel and do not count, and after
+  // kTuneGiveUp of those the scene stays pooled.
   mutable int shadow_mode = 0;
-  mutable int trace_mode = 0;  // closest-hit schedule, same convention: 1 = fused, 2 = split
-  mutable int tune_frames = 0;
-  mutable double tune_ns_per_task[2] = {0, 0};
-  mutable double tune_ns_per_ray[2] = {0, 0};
+  mutable int tune_frames = 0, tune_small_frames = 0;
+  mutable double tune_ns_per_pair[2] = {0, 0};
+  // set-up times of rh_scene_create (milliseconds)
+  double ms_trees = 0, ms_light_tables = 0, ms_upload = 0;
   // Per-chunk kernel time of the last frame that streamed its sample offsets from the host (key: the chunk plan).
   // The next such frame processes its chunks in descending cost per sample, so that the uploads of the cheap chunks
   // hide behind the kernels of the expensive ones instead of the other way round.
@@ -603,6 +604,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   std::vector<uint32_t> lin_objs, sphere_refs;
   uint32_t sphere_root = kEmpty;
   std::vector<WideNode> wide_cull;      // the float path's own tree (same super-root indices as `wide`)
+  uint32_t cull_depth = 0;              // its depth (the reference tree's is `depth`)
   std::vector<uint32_t> exact_index;    // reference slot -> slot in the permuted triangle arrays
   try {
     int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
@@ -656,9 +658,10 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       for (size_t i = 0; i < objs.size(); i++)
         if (objs[i].root != objs2[i].root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: cull tree roots out of step");
       if (sroot2 != sphere_root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: sphere tree roots out of step");
-      depth = std::max(depth, depth2);
+      cull_depth = depth2;
     }
-    if (depth + 4 > (uint32_t)kStack) return rh::set_error(RH_ERR_ARG, "rh_scene_create: tree too deep for the traversal stack");
+    if (std::max(depth, cull_depth) + 4 > (uint32_t)kStack)
+      return rh::set_error(RH_ERR_ARG, "rh_scene_create: tree too deep for the traversal stack");
   } catch (const std::bad_alloc&) {
     return rh::set_error(RH_ERR_OOM, "rh_scene_create: out of host memory");
   }
@@ -666,7 +669,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   RH_CUDA(cudaSetDevice(D->dev));
   auto S = std::make_unique<rh_scene>();
   S->device = D;
-  S->max_tree_depth = depth;
+  S->max_tree_depth = std::max(depth, cull_depth);
   for (uint32_t i = 0; i < d->n_materials; i++) S->has_transparent |= d->materials[i].kind == RH_MAT_TRANSPARENT;
   int rc;
   // conservative float copy of the boxes: lower bounds rounded down, upper bounds rounded up
@@ -707,9 +710,17 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
         n.box[6 * c + 3 + k] = fhi;
         if (w.child[c] != kEmpty) abs_max = std::max(abs_max, std::max(std::fabs(flo), std::fabs(fhi)));
       }
-      n.child[c] = w.child[c];
-      n.first[c] = w.first[c];
+      // leaf references of the cull tree carry their slot range (see kLeafCountShift): a stacked subtree is one word
+      uint32_t ch = w.child[c];
+      if (ch != kEmpty && (ch & kLeafBit)) {
+        const uint32_t count = ch & kCountMask;
+        if (count == 0 || count > kLeafMaxCount || w.first[c] > kLeafFirstMask)
+          return rh::set_error(RH_ERR_ARG, "rh_scene_create: more than 134 M triangle slots, or a cull-tree leaf out of range");
+        ch = (ch & (kLeafBit | kSphereLeafBit)) | ((count - 1) << kLeafCountShift) | w.first[c];
+      }
+      n.child[c] = ch;
     }
+    n.pad_[0] = n.pad_[1] = 0;
   }
   if ((rc = upload(S->wide, wide.data(), wide.size()))) return rc;
   if ((rc = upload(S->wide32, wide32.data(), wide32.size()))) return rc;
@@ -756,6 +767,14 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.n_occ_meshes = (uint32_t)occ_meshes.size();
   v.shadow_fast = occ_planes.size() <= (size_t)kOccPlanes && occ_spheres.size() <= (size_t)kOccSpheres &&
                   occ_meshes.size() <= (size_t)kOccMeshes && d->n_lights <= (uint32_t)kFastLights;
+  {
+    // Deep-stack scratch (entries beyond the shared-memory short stack, and the exact walk's whole stack): a walk
+    // stacks at most one entry per level of its tree; the per-lane-refill shadow kernel also stacks the other roots.
+    const uint32_t n_roots = (uint32_t)occ_meshes.size() + (sphere_root != kEmpty ? 1u : 0u);
+    S->refill_possible = n_roots <= 64;
+    const uint32_t float_need = cull_depth + (S->refill_possible ? n_roots : 1u) + 4;
+    S->deep_entries = std::max<uint32_t>(depth + 4, float_need > (uint32_t)kShortStack ? float_need - kShortStack : 1u);
+  }
   // Light-space tables of the shadow kernels (light_maps.cpp): cube maps of the nearest possible occluder distance, one
   // per (point light, occluder mesh), and lit-triangle flags per (triangle, light of either kind).  Only the
   // shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
@@ -977,23 +996,24 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   if (want_ids && !hit_ids_out) return rh::set_error(RH_ERR_ARG, "rh_render: RH_FLAG_HIT_IDS without hit_ids_out");
   const bool dev_out = (o->flags & RH_FLAG_DEVICE_OUT) != 0;
   const bool dev_off = (o->flags & RH_FLAG_DEVICE_OFFSETS) != 0;
+  const bool shard_offsets = (o->flags & RH_FLAG_SHARD_OFFSETS) != 0;  // offsets = this shard's rows only, shard-compact
   const bool counting = (o->flags & RH_FLAG_COUNT) != 0;
-  // Shadow and closest-hit schedules: forced by flags, else the scene's measured choice, else this is one of the
-  // timing frames of a scene: frame 1 pooled + fused (not compared: first use of freshly allocated queues), frame 2 the
-  // same, frame 3 split + split; the kernels' times of frames 2 and 3 are compared per unit of work.
-  const bool split_ok = shadow_split_possible(scene->view);
-  const bool forced = (o->flags & (RH_FLAG_SHADOW_POOLED | RH_FLAG_SHADOW_SPLIT | RH_FLAG_TRACE_FUSED | RH_FLAG_TRACE_SPLIT)) != 0;
-  const bool decided = scene->tune_frames >= 3;
-  const bool tuning = !forced && !decided && !(o->flags & RH_FLAG_COUNT);
-  bool use_split = false, use_split_trace = false;
-  if (o->flags & RH_FLAG_SHADOW_SPLIT) use_split = split_ok;
-  else if (o->flags & RH_FLAG_SHADOW_POOLED) use_split = false;
-  else if (decided) use_split = split_ok && scene->shadow_mode == 2;
-  else if (tuning) use_split = split_ok && scene->tune_frames == 2;
-  if (o->flags & RH_FLAG_TRACE_SPLIT) use_split_trace = true;
-  else if (o->flags & RH_FLAG_TRACE_FUSED) use_split_trace = false;
-  else if (decided) use_split_trace = scene->trace_mode == 2;
-  else if (tuning) use_split_trace = scene->tune_frames == 2;
+  // Shadow-walk schedule: forced by flags, else the scene's measured choice, else — on frames large enough to time —
+  // one of the scene's timing frames: the first is pooled and not compared (first use of freshly allocated queues), the
+  // second pooled, the third per-lane refill; the two kernels' times per walked (hit, light) pair are compared.  Small
+  // frames never take part: they run pooled, unprofiled, and after kTuneGiveUp of them the scene stays pooled.
+  constexpr int kTuneGiveUp = 8;
+  const bool refill_ok = scene->refill_possible && scene->view.n_lights <= (uint32_t)kMaskLights;
+  const bool forced = (o->flags & (RH_FLAG_SHADOW_POOLED | RH_FLAG_SHADOW_SPLIT)) != 0;
+  if (!refill_ok && scene->shadow_mode == 0) scene->shadow_mode = 1;
+  const bool decided = scene->shadow_mode != 0;
+  const bool big_frame = (uint64_t)rows_local * W * spp >= (1ull << 21);
+  const bool tuning = !forced && !decided && !(o->flags & RH_FLAG_COUNT) && big_frame;
+  bool use_refill = false;
+  if (o->flags & RH_FLAG_SHADOW_SPLIT) use_refill = refill_ok;
+  else if (o->flags & RH_FLAG_SHADOW_POOLED) use_refill = false;
+  else if (decided) use_refill = scene->shadow_mode == 2;
+  else if (tuning) use_refill = scene->tune_frames == 2;
   const bool profile = (o->flags & RH_FLAG_PROFILE) != 0 || tuning;
   const bool exact_boxes = (o->flags & RH_FLAG_EXACT_BOXES) != 0;
 
@@ -1016,9 +1036,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   {
     size_t want = (size_t)o->chunk_samples, first = want;
     if (o->chunk_samples <= 0) {
-      const size_t L = std::max<uint32_t>(1, scene->view.n_lights);
-      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + 5 * sizeof(double2) + 4 + 4 + sizeof(double4) + L * (sizeof(uint2) + 1));
-      want = std::min<size_t>((size_t)(0.4 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
+      // accumulators + (two ray queues + hit queue + half a walk queue) at 2 entries per sample
+      const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + (5 * sizeof(double2) + 8) + (5 * sizeof(double2) + 12) / 2);
+      want = std::min<size_t>((size_t)(0.45 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
       if (host_offsets) want = std::min<size_t>(want, (size_t)RH_STREAM_CHUNK_MI << 20);
       first = host_offsets ? std::min<size_t>(want, (size_t)RH_STREAM_FIRST_MI << 20) : want;
     }
@@ -1087,7 +1107,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   } else if (mode != RH_OFFSETS_NONE) {
     if (dev_off) {
       d_offsets = o->offsets;
-      off_index = kOffIndexGlobal;
+      off_index = shard_offsets ? kOffIndexLocal : kOffIndexGlobal;  // (compact: each chunk's slice is in work-item order)
     } else {
       stream_offsets = true;
       // Upload ring: as many chunk-sized slots as 10 % of the device memory holds (all chunks, for the frames of
@@ -1107,21 +1127,26 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
 
   uint32_t factor = 2;  // queue capacity = factor * chunk samples; doubled when a chunk overflows
   for (;;) {
-    const size_t cap = std::min<size_t>((size_t)factor * chunk_samples, 0x7ffffff0u);
-    const bool split = use_split;
-    const size_t walk_cap = std::min<size_t>(cap * std::max<uint32_t>(1, scene->view.n_lights), 0xfffffff0u);
+    // Queue capacity in entries, a whole number of slabs: factor x the chunk's samples, plus one partly filled slab
+    // per warp that can be producing (each warp leaves its last slab of a queue open).
+    const size_t producers = std::min<size_t>((size_t)D->max_threads / 32, (chunk_samples + kSlab - 1) / kSlab + 1);
+    size_t cap = std::min<size_t>((size_t)factor * chunk_samples + 2 * producers * kSlab, 0x7fffff00u);
+    cap = (cap + kSlab - 1) / kSlab * kSlab;
+    const size_t n_slabs_cap = cap / kSlab;
+    const size_t walk_cap = std::max<size_t>((cap / 2 + kSlab - 1) / kSlab * kSlab, 2 * producers * kSlab);
+    const size_t deep_bytes = (size_t)scene->deep_entries * D->max_threads * sizeof(uint2);
     for (int l = 0; l < n_lanes; l++) {
       Device::Scratch& sc = D->lane[l];
-      for (int k = 0; k < 2; k++)
+      for (int k = 0; k < 2; k++) {
         if ((rc = sc.rayq[k].reserve(cap * 4 * sizeof(double2)))) return rc;
-      if ((rc = sc.shq.reserve(cap * 5 * sizeof(double2)))) return rc;
-      if ((rc = sc.shq_sample.reserve(2 * cap * sizeof(uint32_t)))) return rc;  // sample ids, then lit flags
-      if (use_split_trace && (rc = sc.hits.reserve(cap * sizeof(double4)))) return rc;
-      if (split) {
-        if ((rc = sc.walk_q.reserve(walk_cap * sizeof(uint2)))) return rc;
-        if ((rc = sc.deferred_q.reserve(cap * sizeof(uint32_t)))) return rc;
-        if ((rc = sc.pair_flags.reserve(cap * scene->view.n_lights))) return rc;
+        if ((rc = sc.rayq_fill[k].reserve(n_slabs_cap * sizeof(uint32_t)))) return rc;
       }
+      // hit queue (every shaded hit of a pass) and walk queue (the hits that need a tree walk: half as many entries)
+      if ((rc = sc.hitq.reserve(cap * 5 * sizeof(double2)))) return rc;
+      if ((rc = sc.hitq_words.reserve((2 * cap + n_slabs_cap) * sizeof(uint32_t)))) return rc;  // sample ids, lit flags, slab fills
+      if ((rc = sc.shq.reserve(walk_cap * 5 * sizeof(double2)))) return rc;
+      if ((rc = sc.shq_words.reserve((3 * walk_cap + walk_cap / kSlab) * sizeof(uint32_t)))) return rc;  // sample ids, walk masks, settled masks, slab fills
+      if ((rc = sc.deep.reserve(deep_bytes))) return rc;
     }
 
     size_t ev_used = 0;
@@ -1196,15 +1221,20 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       }
       P.ctl = (ChunkCtl*)D->ctl.p + ck;
       P.counters = (FrameCounters*)D->counters.p;
+      P.q_hits.plane = (double2*)sc.hitq.p;
+      P.q_hits.sample = (uint32_t*)sc.hitq_words.p;
+      P.q_hits.walk = (uint32_t*)sc.hitq_words.p + cap;
+      P.q_hits.settled = nullptr;
+      P.q_hits.fill = (uint32_t*)sc.hitq_words.p + 2 * cap;
+      P.q_hits.capacity = (uint32_t)cap;
       P.q_shadow.plane = (double2*)sc.shq.p;
-      P.q_shadow.sample = (uint32_t*)sc.shq_sample.p;
-      P.q_shadow.lit = (uint32_t*)sc.shq_sample.p + cap;
-      P.q_shadow.capacity = (uint32_t)cap;
-      P.walk_q = (uint2*)sc.walk_q.p;
-      P.deferred_q = (uint32_t*)sc.deferred_q.p;
-      P.pair_flags = (uint8_t*)sc.pair_flags.p;
-      P.hits = (double4*)sc.hits.p;
-      P.walk_capacity = (uint32_t)walk_cap;
+      P.q_shadow.sample = (uint32_t*)sc.shq_words.p;
+      P.q_shadow.walk = (uint32_t*)sc.shq_words.p + walk_cap;
+      P.q_shadow.settled = (uint32_t*)sc.shq_words.p + 2 * walk_cap;
+      P.q_shadow.fill = (uint32_t*)sc.shq_words.p + 3 * walk_cap;
+      P.q_shadow.capacity = (uint32_t)walk_cap;
+      P.deep_stack = (uint2*)sc.deep.p;
+      P.deep_stride = (uint32_t)D->max_threads;
 
       if (stream_offsets) {
         // upload this chunk's rows (runs of image rows that are contiguous inside one band) on the copy stream
@@ -1219,8 +1249,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
           const long long rows_ok = std::max<long long>(0, std::min<long long>(run, (long long)H - grow));
           if (rows_ok > 0) {
             const size_t bytes = (size_t)rows_ok * row_samples * off_elem;
+            const size_t src_row = shard_offsets ? (size_t)lr : (size_t)grow;
             RH_CUDA(cudaMemcpyAsync(slot + (size_t)(lr - first_row) * row_samples * off_elem,
-                                    (const char*)o->offsets + (size_t)grow * row_samples * off_elem, bytes,
+                                    (const char*)o->offsets + src_row * row_samples * off_elem, bytes,
                                     cudaMemcpyHostToDevice, D->copy_stream));
             upload_bytes += bytes;
           }
@@ -1232,21 +1263,27 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         chunk_ev.push_back(prof_event());  // after the wait: the span holds kernel time only
       }
 
+      if (dev_off && shard_offsets && d_offsets) P.offsets = (const char*)d_offsets + (size_t)first_row * row_samples * off_elem;
+      // offsets in work-item order?  chunk-local slices always; the full-frame array when the frame is not sharded
+      P.offset_linear = (mode == RH_OFFSETS_F64 && (P.offset_index == kOffIndexLocal || G == 1)) ? 1u : 0u;
+      P.offset_base = (P.offset_index == kOffIndexLocal) ? 0ull : (unsigned long long)first_row * row_samples;
       for (int plane = 0; plane < 3; plane++)  // (three 1-D memsets: a 2-D one is limited to 2 GB of pitch)
         RH_CUDA(cudaMemsetAsync((double*)sc.accum.p + (size_t)plane * chunk_samples, 0, (size_t)P.n_samples * sizeof(double), lane_stream));
       for (int pass = 0; pass < n_passes; pass++) {
         P.pass = pass;
         P.q_in.plane = (double2*)sc.rayq[(pass + 1) & 1].p;
+        P.q_in.fill = (uint32_t*)sc.rayq_fill[(pass + 1) & 1].p;
         P.q_in.capacity = (uint32_t)cap;
         P.q_out.plane = (double2*)sc.rayq[pass & 1].p;
+        P.q_out.fill = (uint32_t*)sc.rayq_fill[pass & 1].p;
         P.q_out.capacity = (uint32_t)cap;  // (the last pass cannot emit: every ray in it has depth == maxDepth)
         cudaEvent_t a = nullptr;
         if (profile) a = prof_event();
-        launch_trace(scene->view, cam, P, counting, use_split_trace, D->grid_trace[counting], lane_stream);
+        launch_trace(scene->view, cam, P, counting, D->n_sms, lane_stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
-        launch_shadow(scene->view, P, counting, use_split, D->grid_shadow[counting], lane_stream);
+        const int n_shadow = launch_shadow(scene->view, P, counting, use_refill, D->n_sms, lane_stream);
         if (profile) spans.push_back({a, prof_event(), 1});
-        launches += (use_split_trace ? 2 : 1) + (use_split ? 3 : 1);
+        launches += 1 + n_shadow;
       }
       cudaEvent_t a = nullptr;
       if (profile) a = prof_event();
@@ -1279,7 +1316,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     bool overflow = false;
     for (int ck = 0; ck < n_chunks; ck++) overflow |= ctl[ck].overflow != 0;
     if (overflow) {
-      if ((size_t)factor * chunk_samples >= 0x7ffffff0u || factor >= (1u << 16))
+      if (cap >= 0x7fffff00u || factor >= (1u << 16))
         return rh::set_error(RH_ERR_OVERFLOW, "rh_render: ray queue overflow; lower chunk_samples");
       factor *= 2;
       continue;
@@ -1287,9 +1324,10 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     if (stats) {
       memset(stats, 0, sizeof *stats);
       const FrameCounters* fc = (const FrameCounters*)((const char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl));
-      uint64_t shadow_tasks = 0;
+      const uint64_t shadow_tasks = fc->shaded_hits;
+      uint64_t queued_hits = 0;
       for (int ck = 0; ck < n_chunks; ck++)
-        for (int p = 0; p < n_passes; p++) shadow_tasks += ctl[ck].shadow_count[p];
+        for (int p = 0; p < n_passes; p++) queued_hits += ctl[ck].shadow_items[p];
       // padding rows of the last band trace nothing
       uint64_t real_rows = 0;
       for (int lr = 0; lr < rows_local; lr++) {
@@ -1312,8 +1350,11 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->shadow_prim_tests = fc->k[1].prim_tests;
       stats->shadow_node_visits = fc->k[1].node_visits;
       for (int ck = 0; ck < n_chunks; ck++)
-        for (int p = 1; p < n_passes; p++) stats->queued_rays += std::min<uint64_t>(ctl[ck].ray_count[p], cap);
+        for (int p = 1; p < n_passes; p++) stats->queued_rays += ctl[ck].ray_items[p];
       stats->shadow_tasks = shadow_tasks;
+      stats->shadow_tasks_queued = queued_hits;
+      stats->shadow_walk_pairs = fc->shadow_walk_pairs;
+      stats->deep_stack_pushes = fc->deep_pushes;
       stats->rays_shadow_culled = fc->shadow_culled;
       if (counting && getenv("RAYHS_B200_DEBUG"))
         fprintf(stderr, "rayhs_b200: exact shadow walks %llu, most nodes visited by one shadow ray %llu; exact closest-hit walks %llu, "
@@ -1334,8 +1375,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->chunks = (uint32_t)n_chunks;
       stats->negative_channels = (uint32_t)std::min<unsigned long long>(fc->negative_channels, 0xffffffffu);
       stats->queue_factor = factor;
-      stats->shadow_split = use_split ? 1 : 0;
-      stats->trace_split = use_split_trace ? 1 : 0;
+      stats->shadow_split = use_refill ? 1 : 0;
     }
     if (stream_offsets && (int)chunk_ev.size() == 2 * n_chunks) {
       scene->chunk_ms.assign(n_chunks, 0.f);
@@ -1343,30 +1383,22 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       scene->cost_key = key;
     }
     if (tuning) {
-      // only frames with enough shadow work to time say anything (1 M shaded hits ~ 0.3 ms)
-      const ChunkCtl* c2 = (const ChunkCtl*)D->pinned;
-      uint64_t tasks = 0, rays = (uint64_t)rows_local * row_samples;
-      double ms = 0, ms_trace = 0;
-      for (int ck = 0; ck < n_chunks; ck++)
-        for (int p = 0; p < n_passes; p++) {
-          tasks += c2[ck].shadow_count[p];
-          if (p > 0) rays += std::min<uint64_t>(c2[ck].ray_count[p], cap);
-        }
+      // only frames with enough walks to time say anything (256 Ki pairs ~ 0.2 ms)
+      const FrameCounters* fc = (const FrameCounters*)((const char*)D->pinned + (size_t)n_chunks * sizeof(ChunkCtl));
+      double ms = 0;
       for (const Span& sp : spans) {
         float m = 0;
         cudaEventElapsedTime(&m, sp.a, sp.b);
         if (sp.kind == 1) ms += m;
-        if (sp.kind == 0) ms_trace += m;
       }
-      if (tasks >= (1u << 20)) {
-        const int slot = scene->tune_frames == 2 ? 1 : 0;
-        scene->tune_ns_per_task[slot] = ms * 1e6 / (double)tasks;
-        scene->tune_ns_per_ray[slot] = ms_trace * 1e6 / (double)rays;
-        if (++scene->tune_frames == 3) {
-          scene->shadow_mode = scene->tune_ns_per_task[1] < scene->tune_ns_per_task[0] ? 2 : 1;
-          scene->trace_mode = scene->tune_ns_per_ray[1] < scene->tune_ns_per_ray[0] ? 2 : 1;
-        }
+      if (fc->shadow_walk_pairs >= (1u << 18)) {
+        if (scene->tune_frames >= 1) scene->tune_ns_per_pair[scene->tune_frames - 1] = ms * 1e6 / (double)fc->shadow_walk_pairs;
+        if (++scene->tune_frames == 3) scene->shadow_mode = scene->tune_ns_per_pair[1] < scene->tune_ns_per_pair[0] ? 2 : 1;
+      } else if (++scene->tune_small_frames >= kTuneGiveUp) {
+        scene->shadow_mode = 1;
       }
+    } else if (!forced && !decided && !(o->flags & RH_FLAG_COUNT)) {
+      if (++scene->tune_small_frames >= kTuneGiveUp) scene->shadow_mode = 1;
     }
     return RH_OK;
   }
@@ -1642,6 +1674,33 @@ int rh_bench_gather(uint64_t bytes, int iters, double* gbs_out) {
   float ms = 0;
   cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
   *gbs_out = (double)grid * block * loads * 128.0 * iters / (ms * 1e-3) / 1e9;
+  cudaFree(buf);
+  cudaFree(sink);
+  RH_CUDA(cudaGetLastError());
+  return RH_OK;
+}
+
+int rh_bench_stream(uint64_t bytes, int iters, double* gbs_out) {
+  if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_bench_stream: call rh_init first");
+  if (bytes < 4096 || iters <= 0 || !gbs_out) return rh::set_error(RH_ERR_ARG, "rh_bench_stream: bad argument");
+  Device* D = g_dev.get();
+  RH_CUDA(cudaSetDevice(D->dev));
+  void* buf = nullptr;
+  double2* sink = nullptr;
+  RH_CUDA(cudaMalloc(&buf, bytes));
+  RH_CUDA(cudaMalloc(&sink, 64));
+  RH_CUDA(cudaMemsetAsync(buf, 0, bytes, D->stream));
+  const int block = 256, grid = D->n_sms * 8;
+  const uint64_t n = bytes / 16;
+  for (int i = 0; i < 2; i++) launch_stream_bench((const double2*)buf, n, sink, grid, block, D->stream);  // warm-up: fills L2
+  RH_CUDA(cudaEventRecord(D->ev_begin, D->stream));
+  for (int i = 0; i < iters; i++) launch_stream_bench((const double2*)buf, n, sink, grid, block, D->stream);
+  RH_CUDA(cudaEventRecord(D->ev_end, D->stream));
+  RH_CUDA(cudaStreamSynchronize(D->stream));
+  g_launches.fetch_add(iters + 2);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
+  *gbs_out = (double)n * 16.0 * iters / (ms * 1e-3) / 1e9;
   cudaFree(buf);
   cudaFree(sink);
   RH_CUDA(cudaGetLastError());

@@ -208,23 +208,22 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
 
 
 def _shadow_flag(shadow: str | None) -> int:
-    """Shadow-ray schedule: None = the library's per-scene choice, 'pooled' / 'split' = forced (same image); a pair
-    (shadow, trace) also forces the closest-hit schedule: 'fused' / 'split' / None."""
+    """Shadow-walk schedule: None = the library's per-scene choice, 'pooled' / 'split' (per-lane refill) = forced
+    (same image)."""
     if shadow is None:
         return 0
-    if isinstance(shadow, (tuple, list)):   # (shadow schedule, closest-hit schedule)
-        return _shadow_flag(shadow[0]) | {None: 0, "fused": capi.RH_FLAG_TRACE_FUSED, "split": capi.RH_FLAG_TRACE_SPLIT}[shadow[1]]
     return {"pooled": capi.RH_FLAG_SHADOW_POOLED, "split": capi.RH_FLAG_SHADOW_SPLIT}[shadow]
 
 
 def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offset_tile: int = 0, shard_index: int = 0,
                   shard_count: int = 1, band_height: int = 0, chunk_samples: int = 0, count: bool = False,
                   profile: bool = False, shadow: str | None = None, seed: int | None = None, peer_frames=None,
-                  light_maps: bool = True) -> dict:
+                  light_maps: bool = True, shard_offsets: bool = False, hit_ids_dev=None) -> dict:
     """rh_render into a DEVICE framebuffer (torch CUDA uint8 tensor [rows, width, 3]).  `offsets_dev` is the
     full-frame [height*width, spp, 2] float64/float32 stream (or the [tile*tile, spp, 2] tile), either a CUDA
-    tensor (already uploaded) or a pinned CPU tensor (uploaded chunk by chunk inside the call).  The call
-    returns after the frame is complete."""
+    tensor (already uploaded) or a pinned CPU tensor (uploaded chunk by chunk inside the call); with `shard_offsets`
+    it holds only this shard's rows, shard-compact ([rows*width, spp, 2]).  `hit_ids_dev`: CUDA int32 tensor
+    [rows*width*spp, 2] for the primary hit ids.  The call returns after the frame is complete."""
     import torch
 
     L = lib()
@@ -234,7 +233,8 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
     if peer_frames is None and (tuple(rgb_dev.shape) != (rows, job.width, 3) or rgb_dev.dtype != torch.uint8 or not rgb_dev.is_cuda):
         raise ValueError("rgb_dev must be a CUDA uint8 tensor of shape [rows, width, 3]")
     flags = (capi.RH_FLAG_DEVICE_OUT | (capi.RH_FLAG_COUNT if count else 0) | (capi.RH_FLAG_PROFILE if profile else 0)
-             | _shadow_flag(shadow) | (0 if light_maps else capi.RH_FLAG_NO_LIGHT_MAPS))
+             | _shadow_flag(shadow) | (0 if light_maps else capi.RH_FLAG_NO_LIGHT_MAPS)
+             | (capi.RH_FLAG_SHARD_OFFSETS if shard_offsets else 0) | (capi.RH_FLAG_HIT_IDS if hit_ids_dev is not None else 0))
     if off is not None and off.is_cuda:
         flags |= capi.RH_FLAG_DEVICE_OFFSETS
         torch.cuda.current_stream().synchronize()
@@ -252,7 +252,7 @@ def render_device(job: Rendering, rgb_dev, spp: int = 1, offsets_dev=None, offse
         o.n_peer_frames, o.peer_frames = len(peer_frames), ptrs
     st = capi.rh_stats()
     check(L.rh_render(job.scene.device, C.byref(job.camera), C.byref(o), rgb_dev.data_ptr() if rgb_dev is not None else None,
-                      None, C.byref(st)))
+                      hit_ids_dev.data_ptr() if hit_ids_dev is not None else None, C.byref(st)))
     return st.as_dict()
 
 

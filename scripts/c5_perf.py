@@ -15,7 +15,6 @@ ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--spp", type=int, default=4)
 ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--count", action="store_true")
-ap.add_argument("--trace", default=None, choices=["fused", "split"])
 ap.add_argument("--shadow", default="auto", choices=["auto", "pooled", "split"])
 a = ap.parse_args()
 rh.init(0)
@@ -28,7 +27,7 @@ tile = torch.from_numpy(rh.sample_offsets(64 * 64, a.spp, 24)).cuda()
 rgb = torch.empty((a.height, a.width, 3), dtype=torch.uint8, device="cuda")
 for i in range(a.frames):
     st = rh.render_device(job, rgb, spp=a.spp, offsets_dev=tile, offset_tile=64, profile=True, count=(a.count and i == a.frames - 1),
-                          shadow=None if a.shadow == "auto" else (a.shadow, a.trace))
+                          shadow=None if a.shadow == "auto" else a.shadow)
 rays = st["rays_primary"] + st["rays_reflect"] + st["rays_probe"] + st["rays_exit"] + st["rays_shadow"]
 st.update(build_s=t_build, mrays_per_s=rays / st["ms_total"] / 1e3, tris=a.tris, spheres=a.spheres, w=a.width, h=a.height, spp=a.spp,
           mem_GB=torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9)

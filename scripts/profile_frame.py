@@ -22,7 +22,6 @@ ap.add_argument("--pack", default="dragon_full")
 ap.add_argument("--count", action="store_true")
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--no-profile", action="store_true", help="no per-launch events: lets two chunks be in flight")
-ap.add_argument("--trace", default=None, choices=["fused", "split"])
 ap.add_argument("--shadow", default="pooled", choices=["auto", "pooled", "split"],
                 help="shadow-ray schedule; forced by default so that every frame launches the same kernels")
 a = ap.parse_args()
@@ -36,5 +35,5 @@ off_dev = off.cuda()
 rgb = torch.empty((a.height, a.width, 3), dtype=torch.uint8, device="cuda")
 for i in range(a.frames):
     st = rh.render_device(job, rgb, spp=a.spp, offsets_dev=off_dev, profile=not a.no_profile, count=a.count, chunk_samples=a.chunk,
-                          shadow=None if a.shadow == "auto" else (a.shadow, a.trace))
+                          shadow=None if a.shadow == "auto" else a.shadow)
 print(json.dumps(st))

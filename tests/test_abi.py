@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/rayhs_b200.h but not exported"
         assert s in capi.SIGNATURES, f"{s} has no ctypes signature"
-    assert L.rh_abi_version() == 1
+    assert L.rh_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():

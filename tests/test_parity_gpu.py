@@ -11,18 +11,16 @@ RES = {"cornellBox": (256, 256), "texture": (320, 180), "transform": (320, 180),
        "dragon_low": (320, 180), "dragon_full": (320, 180), "outScene": (320, 180)}
 
 
-@pytest.mark.parametrize("shadow", [("pooled", "fused"), ("split", "split")])
+@pytest.mark.parametrize("shadow", ["pooled", "split"])
 @pytest.mark.parametrize("name", SCENES)
 def test_one_sample_parity(name, shadow):
     """rayTrace (RayHs.hs:161-166): hit ids bit-exact, image within tolerance, ray counts equal — with either schedule
-    of the shadow rays (one pooled kernel per pass, or classify -> walk -> fold) and of the closest-hit search (fused
-    with the shading, or intersect with per-lane refill -> shade)."""
+    of the shadow walks (pooled per light in warp-local rounds, or one queued hit per lane with per-lane refill)."""
     sc = load_scene(name)
     w, h = RES[name]
     job = rh.renderingFromScene(sc, w, h)
     img = rh.render(job, want_hit_ids=True, shadow=shadow)
-    assert img.stats["shadow_split"] == (1 if shadow[0] == "split" else 0)
-    assert img.stats["trace_split"] == (1 if shadow[1] == "split" else 0)
+    assert img.stats["shadow_split"] == (1 if shadow == "split" else 0)
     ref = oracle_for(sc).render(sc.camera, w, h, sc.max_depth)
     ids_gpu = img.hit_ids.reshape(h, w, 2)
     ids_ref = ref["hit_ids"].reshape(h, w, 2)
@@ -111,16 +109,20 @@ def test_light_maps_change_no_byte_and_save_walks(name, shadow):
 
 
 def test_shadow_schedule_is_chosen_per_scene_and_keeps_the_bytes():
-    """Default flags: the first three large frames of a scene are timing frames (warm-up, pooled + fused, split + split)
-    and the faster schedules are kept; every frame must carry the same bytes whichever schedule rendered it."""
+    """Default flags: the first three large frames of a scene are timing frames (warm-up, pooled, per-lane refill) and the
+    faster schedule is kept; every frame must carry the same bytes whichever schedule rendered it.  Small frames never
+    take part in the timing: they render pooled."""
     sc = load_scene("dragon_low")
-    w, h = 1600, 900   # > 1 Mi shaded hits: counts as a timing frame
+    small = rh.renderingFromScene(sc, 160, 90)
+    assert [rh.render(small).stats["shadow_split"] for _ in range(3)] == [0, 0, 0]   # too small to time: pooled, not counted
+    w, h = 2400, 1350   # > 2 Mi samples and enough walked pairs: counts as a timing frame
     job = rh.renderingFromScene(sc, w, h)
     frames = [rh.render(job) for _ in range(4)]
-    assert [f.stats["shadow_split"] for f in frames[:3]] == [0, 0, 1] and [f.stats["trace_split"] for f in frames[:3]] == [0, 0, 1]
+    assert [f.stats["shadow_split"] for f in frames[:3]] == [0, 0, 1]
     assert all(np.array_equal(frames[0].pixels, f.pixels) for f in frames[1:])
-    forced = rh.render(job, shadow=("split", "split"))
-    assert forced.stats["shadow_split"] == 1 and forced.stats["trace_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
+    assert rh.render(small).stats["shadow_split"] == frames[3].stats["shadow_split"]   # decided: small frames follow
+    forced = rh.render(job, shadow="split")
+    assert forced.stats["shadow_split"] == 1 and np.array_equal(forced.pixels, frames[0].pixels)
 
 
 def test_offsets_regenerated_on_the_device_equal_the_uploaded_stream():
