@@ -275,6 +275,8 @@ typedef struct rh_stats {
   uint64_t shadow_tri_tests;
   uint64_t shadow_prim_tests;
   uint64_t shadow_node_visits;
+  uint64_t node_visits_global;        /* of node_visits: records read from global memory (not the staged top levels) */
+  uint64_t shadow_node_visits_global;
   uint64_t upload_bytes;  /* sample-offset bytes copied host -> device           */
   double ms_total;        /* CUDA events around the whole call's device work (uploads and read-back included) */
   double ms_trace;        /* RH_FLAG_PROFILE only: closest-hit + shade kernels   */
@@ -303,6 +305,10 @@ uint64_t rh_launch_count(void);
 /* Upload a flat scene.  Copies everything; host arrays may be freed after return. */
 int rh_scene_create(const rh_scene_desc* desc, rh_scene** out);
 void rh_scene_destroy(rh_scene* scene);
+/* What rh_scene_create did: setup_ms3 = milliseconds for {cull / sphere trees + flattening, light-space tables (cube
+ * maps, lit-triangle flags), uploads}; info4 = {object / material / light tables staged in shared memory, occluder
+ * tables staged, deepest tree, deep-stack entries per thread}.  Either pointer may be NULL. */
+int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4);
 
 /* Replaces `rayTrace` (RayHs.hs:161-166) / `distributedRayTrace` (RayHs.hs:190-195).
  * rgb_out: RGB8, row-major.  For shard_count == 1 it is width*height*3 bytes.

@@ -101,7 +101,7 @@ class rh_stats(C.Structure):
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("shade_fetches", C.c_uint64), ("texel_fetches", C.c_uint64), ("node_visits", C.c_uint64),
                 ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
-                ("shadow_node_visits", C.c_uint64),
+                ("shadow_node_visits", C.c_uint64), ("node_visits_global", C.c_uint64), ("shadow_node_visits_global", C.c_uint64),
                 ("upload_bytes", C.c_uint64), ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_resolve", C.c_double), ("trace_launches", C.c_uint32), ("shadow_launches", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("negative_channels", C.c_uint32),
@@ -129,6 +129,7 @@ SIGNATURES = {
     "rh_launch_count": (C.c_uint64, []),
     "rh_scene_create": (C.c_int, [C.POINTER(rh_scene_desc), C.POINTER(vp)]),
     "rh_scene_destroy": (None, [vp]),
+    "rh_scene_info": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "rh_render": (C.c_int, [vp, C.POINTER(rh_camera), C.POINTER(rh_render_opts), vp, vp, C.POINTER(rh_stats)]),
     "rh_shard_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rh_default_band_height": (C.c_int, [C.c_int, C.c_int]),

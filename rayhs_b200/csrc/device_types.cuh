@@ -19,7 +19,7 @@ constexpr int kMaxDepth = 30;               // ray-tree depth limit accepted by 
 constexpr int kMaxPasses = 2 * kMaxDepth + 2;  // a Transparent hit inserts one probe pass per level (RayHs.hs:136-143)
 constexpr int kStack = 112;                 // deepest stack a walk may need: tree depth <= 100 (KDTree.hs:76-77, 82) + roots
 #ifndef RH_SHORT_STACK
-#define RH_SHORT_STACK 12
+#define RH_SHORT_STACK 8
 #endif
 // Traversal stack entries per thread held in SHARED memory (8 bytes each: subtree reference + float entry distance).
 // Deeper entries — and the whole stack of the rare exact (double box) walk — go to the thread's column of a scratch
@@ -51,7 +51,7 @@ constexpr int kMaxPeers = 16;
 #define RH_REFILL_MIN 16
 #endif
 #ifndef RH_TMA_STAGE
-#define RH_TMA_STAGE 1  // trace kernel: the next batch of queued rays / sample offsets arrives by a bulk async copy (cp.async.bulk + mbarrier) while the current batch is traced
+#define RH_TMA_STAGE 0  // trace kernel: the next batch's sample offsets (1) or also the next batch of queued rays (2) arrive by a bulk async copy (cp.async.bulk + mbarrier) while the current batch is traced; 0 = plain loads.  Measured on the bench frame: 0 = 41.3 ms, 1 = 42.4 ms, 2 = 42.8 ms — the loads it replaces are one coalesced LDG.128 per lane whose latency the other warps of the SM already hide, while the tile, the mbarrier handshake and the shared memory taken from L1 cost more than they save: off by default
 #endif
 constexpr int kTraceBlock = RH_TRACE_BLOCK;    // one block per SM, tables staged once per SM
 constexpr int kShadowBlock = RH_SHADOW_BLOCK;
@@ -173,7 +173,7 @@ struct ChunkCtl {
 
 // Frame-level counters (zeroed per rh_render).
 struct KernelCounters {  // RH_FLAG_COUNT only
-  unsigned long long box_tests, tri_tests, prim_tests, node_visits, shade_fetches, texel_fetches;
+  unsigned long long box_tests, tri_tests, prim_tests, node_visits, shade_fetches, texel_fetches, global_node_visits;
 };
 struct FrameCounters {
   unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;

@@ -245,8 +245,8 @@ __device__ __forceinline__ void stage_walk_tables(WalkTables& sm, const SceneVie
 // ------------------------------------------------------------------ counters
 template <bool COUNT>
 struct Cnt {
-  unsigned long long box, tri, prim, nodes, shade, texel, deep;
-  __device__ __forceinline__ void zero() { box = tri = prim = nodes = shade = texel = deep = 0; }
+  unsigned long long box, tri, prim, nodes, gnodes, shade, texel, deep;
+  __device__ __forceinline__ void zero() { box = tri = prim = nodes = gnodes = shade = texel = deep = 0; }
 };
 template <>
 struct Cnt<false> {
@@ -259,10 +259,10 @@ template <bool COUNT>
 __device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc, int which) {
   if constexpr (COUNT) {
     KernelCounters* kc = &fc->k[which];
-    unsigned long long* src[6] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel};
-    unsigned long long* dst[6] = {&kc->box_tests, &kc->tri_tests, &kc->prim_tests, &kc->node_visits, &kc->shade_fetches,
-                                  &kc->texel_fetches};
-    for (int k = 0; k < 6; k++) {
+    unsigned long long* src[7] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel, &cnt.gnodes};
+    unsigned long long* dst[7] = {&kc->box_tests, &kc->tri_tests, &kc->prim_tests, &kc->node_visits, &kc->shade_fetches,
+                                  &kc->texel_fetches, &kc->global_node_visits};
+    for (int k = 0; k < 7; k++) {
       unsigned long long v = *src[k];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
       if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst[k], v);
@@ -518,6 +518,9 @@ __device__ __forceinline__ bool node_step(const Ctx& cx, uint32_t& ref, const Ra
   const float4 b0 = np[0], b1 = np[1], b2 = np[2];
   const uint2 cw = *(const uint2*)(np + 3);  // child0, child1
   RH_CNT(nodes, 1);
+  if constexpr (COUNT) {
+    if (ref >= cx.S->n_smem_nodes) cnt.gnodes += 1;  // a record read from global memory (not one of the staged top levels)
+  }
   bool h0 = false, h1 = false;
   float tm0 = 0, tm1 = 0;
   if (cw.x != kEmpty) {
@@ -610,6 +613,7 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
       const uint32_t refine = *(const uint32_t*)(np + 7);  // bit c: child c's box is not a box the reference tests
                                                            // (sphere tree): it always passes here
       RH_CNT(nodes, 2);  // a 128-byte record = two 64-byte units
+      RH_CNT(gnodes, 2);
       bool h0 = false, h1 = false;
       double tm0 = 0, tm1 = 0;
       if (cw.x != kEmpty) {
@@ -888,6 +892,24 @@ __device__ __forceinline__ void slab_close(const SlabWriter& w, uint32_t lane, u
   }
 }
 
+// Work claim of a persistent warp: consecutive batches of 32 work items (kSlab / 32 per slab).  Guided self-scheduling:
+// whole slabs (one atomic per 128 items) while plenty of work is left, single batches near the end of the queue and for
+// small launches, so that no warp ends up with a long tail — the secondary passes are short launches whose duration
+// is set by their slowest warp.  Returns (first batch, number of batches); first >= n_batches: nothing left.
+constexpr uint32_t kSlabBatches = kSlab / 32;
+__device__ __forceinline__ uint2 claim_batches(uint32_t* cursor, uint32_t n_batches, uint32_t total_warps, uint32_t lane) {
+  uint2 c = make_uint2(0, 1);
+  if (lane == 0) {
+    const uint32_t seen = *(volatile uint32_t*)cursor;
+    const uint32_t left = seen < n_batches ? n_batches - seen : 0;
+    c.y = min(kSlabBatches, max(1u, left / (2u * total_warps)));
+    c.x = atomicAdd(cursor, c.y);
+  }
+  c.x = __shfl_sync(kFull, c.x, 0);
+  c.y = __shfl_sync(kFull, c.y, 0);
+  return c;
+}
+
 __device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint64_t bits, const RayQueue& q, SlabWriter& sw,
                                          uint32_t* slab_counter, uint32_t* overflow, uint32_t lane) {
   const unsigned m = __ballot_sync(kFull, has);
@@ -923,7 +945,7 @@ __device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const
     q.plane[4 * cap + idx] = make_double2(t.cd.z, t.w);
     q.sample[idx] = t.sample;
     q.walk[idx] = t.walk;
-    q.settled[idx] = t.settled;
+    if (q.settled) q.settled[idx] = t.settled;  // (the hit queue has no settled masks)
   }
 }
 
@@ -1063,11 +1085,15 @@ template <bool COUNT>
 __device__ __forceinline__ bool primitives_occlude(const OccPlane* planes, uint32_t n_planes, const OccSphere* spheres,
                                                    uint32_t n_spheres, const LightPair& q, uint32_t skip, Cnt<COUNT>& cnt) {
   bool shadowed = false;
+#pragma unroll 1
   for (uint32_t k0 = 0; k0 < n_planes && !shadowed; k0 += 32) {
     uint32_t maybe = 0;
     const uint32_t kn = min(32u, n_planes - k0);
-    for (uint32_t k = 0; k < kn; k++) {
-      if (k0 == 0 && ((skip >> k) & 1u)) continue;
+    uint32_t todo = (kn == 32 ? kFull : (1u << kn) - 1u) & (k0 == 0 ? ~skip : kFull);
+#pragma unroll 1
+    while (todo) {
+      const uint32_t k = __ffs(todo) - 1;
+      todo &= todo - 1;
       const double2* pl = (const double2*)&planes[k0 + k];
       const double2 u0 = pl[0], u1 = pl[1], u2 = pl[2];  // (px,py) (pz,nx) (ny,nz)
       const V3 pp = mk(u0.x, u0.y, u1.x), pn = mk(u1.y, u2.x, u2.y);
@@ -1278,8 +1304,13 @@ __device__ __forceinline__ bool offset_slot(const ChunkParams& P, uint32_t item,
 
 // One warp's staging tile for the NEXT batch of 32 work items: the four planes of a ray-queue batch (pass >= 1) or the
 // f64 offset pairs of 32 pixel samples (pass 0, plane 0 only), filled by bulk async copies.
+#if RH_TMA_STAGE >= 2
+constexpr int kStagePlanes = 4;  // also the four planes of a ray-queue batch (passes >= 1)
+#else
+constexpr int kStagePlanes = 1;  // the sample offsets of pass 0 only: 512 bytes per warp
+#endif
 struct __align__(128) StageTile {
-  double2 plane[4][32];
+  double2 plane[kStagePlanes][32];
 };
 struct Staged {
   uint32_t first;   // first work item of the staged batch, kEmpty = nothing staged
@@ -1302,11 +1333,15 @@ __device__ __forceinline__ bool stage_start(const ChunkParams& P, bool primary, 
     bulk_g2s(tile->plane[0], (const double2*)P.offsets + P.offset_base + first, n * 16u, bar);
     return true;
   }
+#if RH_TMA_STAGE >= 2
   const size_t cap = P.q_in.capacity;
   mbar_expect(bar, 4u * n * 16u);
 #pragma unroll
   for (int k = 0; k < 4; k++) bulk_g2s(tile->plane[k], P.q_in.plane + (size_t)k * cap + first, n * 16u, bar);
   return true;
+#else
+  return false;
+#endif
 }
 
 // Work item -> ray: the camera ray of a pixel sample (pass 0: pixelCoord, Image.hs:31-32, + sample offset,
@@ -1342,8 +1377,8 @@ __device__ __forceinline__ bool load_item(const ChunkParams& P, const CameraPara
     return true;
   }
   double2 a, b, c, d;
-  if (tile) {
-    a = tile->plane[0][lane], b = tile->plane[1][lane], c = tile->plane[2][lane], d = tile->plane[3][lane];
+  if (RH_TMA_STAGE >= 2 && tile) {
+    a = tile->plane[0][lane], b = tile->plane[1 % kStagePlanes][lane], c = tile->plane[2 % kStagePlanes][lane], d = tile->plane[3 % kStagePlanes][lane];
   } else {
     const size_t cap = P.q_in.capacity;
     a = P.q_in.plane[item], b = P.q_in.plane[cap + item], c = P.q_in.plane[2 * cap + item], d = P.q_in.plane[3 * cap + item];
@@ -1405,14 +1440,15 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
 #endif
   __syncwarp();
 
+  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kTraceBlock / 32);
   for (;;) {
-    uint32_t slab = 0;
-    if (lane == 0) slab = atomicAdd(&ctl->trace_cursor[P.pass], 1u);  // one atomic per kSlab work items
-    slab = __shfl_sync(kFull, slab, 0);
-    if (slab >= n_slabs) break;
-    const uint32_t slab_first = slab * kSlab;
-    const uint32_t count = primary ? min(kSlab, P.n_samples - slab_first) : min(__ldg(P.q_in.fill + slab), kSlab);
-    for (uint32_t b = 0; b < count; b += 32) {
+    const uint2 claim = claim_batches(&ctl->trace_cursor[P.pass], n_batches, total_warps, lane);
+    if (claim.x >= n_batches) break;
+    const uint32_t claim_end = min(claim.x + claim.y, n_batches);
+    for (uint32_t bi = claim.x; bi < claim_end; bi++) {
+      const uint32_t slab = bi / kSlabBatches, b = (bi % kSlabBatches) * 32, slab_first = slab * kSlab;
+      const uint32_t count = primary ? min(kSlab, P.n_samples - slab_first) : min(__ldg(P.q_in.fill + slab), kSlab);
+      if (b >= count) continue;
       const uint32_t item = slab_first + b + lane;
       bool valid = b + lane < count;
       Ray r;
@@ -1430,10 +1466,10 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
       if (valid) valid = load_item(P, cam, item, primary, tile, lane, r, w, sample, depth, kind, probe_mat);
       else r.o = r.d = mk(0, 0, 1);
 #if RH_TMA_STAGE
-      // the tile is in registers now: ask for the next batch of this slab; it lands while this one is traced
+      // the tile is in registers now: ask for the next batch of this claim (same slab); it lands while this one is traced
       __syncwarp();
       staged.first = kEmpty;
-      if (b + 32 < count) {
+      if (b + 32 < count && bi + 1 < claim_end) {
         uint32_t ok = 0;
         const uint32_t dep = (uint32_t)(__double2loint(r.o.x) ^ __double2loint(r.d.x) ^ __double2loint(w));
         if (lane == 0) ok = stage_start(P, primary, slab_first + b + 32, min(32u, count - b - 32), &wsm.tile, &wsm.bar, dep) ? 1u : 0u;
@@ -1609,7 +1645,7 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
 // queue with the two light masks.  Straight-line code, no stack, small enough for the instruction cache.
 #ifndef RH_CLASSIFY_BLOCK
 #define RH_CLASSIFY_BLOCK 256
-#define RH_CLASSIFY_MINB 3
+#define RH_CLASSIFY_MINB 3  // 3 blocks of 256 per SM at 80 registers (measured on the bench frame: 23.6 ms of shadow work against 25.5 with 2 blocks at up to 128 registers and 26.8 with 4 at 64)
 #endif
 constexpr int kClassifyBlock = RH_CLASSIFY_BLOCK;
 struct ClassifyWarpSmem {
@@ -1618,7 +1654,7 @@ struct ClassifyWarpSmem {
 };
 constexpr size_t kClassifySmem = sizeof(SmemTables) + (kClassifyBlock / 32) * sizeof(ClassifyWarpSmem);
 
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_kernel(const __grid_constant__ SceneView S,
                                                                      const __grid_constant__ ChunkParams P) {
   SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
@@ -1635,13 +1671,15 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
   const size_t cap = P.q_hits.capacity;
   const double2* qp = P.q_hits.plane;
   uint32_t n_culled = 0, n_walk_pairs = 0;
+  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kClassifyBlock / 32);
   for (;;) {
-    uint32_t slab = 0;
-    if (lane == 0) slab = atomicAdd(&ctl->hit_cursor[P.pass], 1u);
-    slab = __shfl_sync(kFull, slab, 0);
-    if (slab >= n_slabs) break;
-    const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
-    for (uint32_t b = 0; b < n_here; b += 32) {
+    const uint2 claim = claim_batches(&ctl->hit_cursor[P.pass], n_batches, total_warps, lane);
+    if (claim.x >= n_batches) break;
+    const uint32_t claim_end = min(claim.x + claim.y, n_batches);
+    for (uint32_t bi = claim.x; bi < claim_end; bi++) {
+      const uint32_t slab = bi / kSlabBatches, b = (bi % kSlabBatches) * 32;
+      const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
+      if (b >= n_here) continue;
       const uint32_t item = slab * kSlab + b + lane;
       const bool valid = b + lane < n_here;
       ShadowTask task;
@@ -1654,8 +1692,7 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
         task.n = mk(bq.y, c.x, c.y);
         task.cd = mk(d.x, d.y, e.x);
         task.w = e.y;
-        const LightFold F = S.shadow_fast ? fold_lights<COUNT, true>(sm, cx, P, task.p, task.n, task.cd, lit, cnt)
-                                          : fold_lights<COUNT, false>(sm, cx, P, task.p, task.n, task.cd, lit, cnt);
+        const LightFold F = fold_lights<COUNT, FAST>(sm, cx, P, task.p, task.n, task.cd, lit, cnt);
         n_culled += F.culled;
         if (F.walk) {
           queue = true;
@@ -2058,10 +2095,24 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(const __grid_constant__
     if (global_row(P, P.first_row + lrow) < P.height) {
       double sr = 0, sg = 0, sb = 0;  // foldl (+) black
       const double* a = P.accum + (size_t)lp * P.spp;
-      for (uint32_t s = 0; s < P.spp; s++) {
-        sr = sr + a[s];
-        sg = sg + a[P.accum_stride + s];
-        sb = sb + a[2 * (size_t)P.accum_stride + s];
+      if ((P.spp & 1u) == 0 && (P.accum_stride & 1u) == 0) {
+        // a pixel's samples are one contiguous run per plane: 16-byte loads halve the L1 wavefronts of this streaming
+        // read (every lane of a warp is in a different 128-byte line); the sum stays in sample order
+        const double2* a0 = (const double2*)a;
+        const double2* a1 = (const double2*)(a + P.accum_stride);
+        const double2* a2 = (const double2*)(a + 2 * (size_t)P.accum_stride);
+        for (uint32_t s = 0; s < P.spp / 2; s++) {
+          const double2 r2 = __ldcs(a0 + s), g2 = __ldcs(a1 + s), b2 = __ldcs(a2 + s);
+          sr = (sr + r2.x) + r2.y;
+          sg = (sg + g2.x) + g2.y;
+          sb = (sb + b2.x) + b2.y;
+        }
+      } else {
+        for (uint32_t s = 0; s < P.spp; s++) {
+          sr = sr + a[s];
+          sg = sg + a[P.accum_stride + s];
+          sb = sb + a[2 * (size_t)P.accum_stride + s];
+        }
       }
       const double inv = 1.0 / (double)P.spp;
       r8 = (uint8_t)to_int_c(inv * sr, negative);
@@ -2201,15 +2252,17 @@ int configure_kernels() {
   set((const void*)shadow_refill_kernel<false>, kWalkSmem);
   set((const void*)shadow_simple_kernel<true>, kSimpleSmem);
   set((const void*)shadow_simple_kernel<false>, kSimpleSmem);
-  set((const void*)classify_kernel<true>, kClassifySmem);
-  set((const void*)classify_kernel<false>, kClassifySmem);
+  set((const void*)classify_kernel<true, true>, kClassifySmem);
+  set((const void*)classify_kernel<false, true>, kClassifySmem);
+  set((const void*)classify_kernel<true, false>, kClassifySmem);
+  set((const void*)classify_kernel<false, false>, kClassifySmem);
   if (e == cudaSuccess) {
     int dev = 0, sms = 0, nb = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     for (int c = 0; c < 2; c++) {
-      if (c) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<true>, kClassifyBlock, kClassifySmem);
-      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<false>, kClassifyBlock, kClassifySmem);
+      if (c) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<true, true>, kClassifyBlock, kClassifySmem);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, classify_kernel<false, true>, kClassifyBlock, kClassifySmem);
       g_classify_grid[c] = sms * (nb > 0 ? nb : 1);
     }
   }
@@ -2232,8 +2285,14 @@ int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool ref
     else shadow_simple_kernel<false><<<grid, kShadowBlock, kSimpleSmem, st>>>(S, P);
     return 1;
   }
-  if (count) classify_kernel<true><<<g_classify_grid[1], kClassifyBlock, kClassifySmem, st>>>(S, P);
-  else classify_kernel<false><<<g_classify_grid[0], kClassifyBlock, kClassifySmem, st>>>(S, P);
+  // FAST: the occluder tables are the staged shared-memory ones (SceneView::shadow_fast)
+  if (S.shadow_fast) {
+    if (count) classify_kernel<true, true><<<g_classify_grid[1], kClassifyBlock, kClassifySmem, st>>>(S, P);
+    else classify_kernel<false, true><<<g_classify_grid[0], kClassifyBlock, kClassifySmem, st>>>(S, P);
+  } else {
+    if (count) classify_kernel<true, false><<<g_classify_grid[1], kClassifyBlock, kClassifySmem, st>>>(S, P);
+    else classify_kernel<false, false><<<g_classify_grid[0], kClassifyBlock, kClassifySmem, st>>>(S, P);
+  }
   if (refill) {
     if (count) shadow_refill_kernel<true><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
     else shadow_refill_kernel<false><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -596,6 +597,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   for (uint32_t i = 0; i < d->n_lights; i++)
     if (d->lights[i].kind != RH_LIGHT_DIRECTIONAL && d->lights[i].kind != RH_LIGHT_POINT)
       return rh::set_error(RH_ERR_ARG, "rh_scene_create: unknown light kind");
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+  const clk::time_point t_begin = clk::now();
   std::vector<WideNode> wide;
   std::vector<DObject> objs;
   uint32_t depth = 0;
@@ -722,6 +726,8 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
     }
     n.pad_[0] = n.pad_[1] = 0;
   }
+  S->ms_trees = ms_since(t_begin);
+  clk::time_point t_mark = clk::now();
   if ((rc = upload(S->wide, wide.data(), wide.size()))) return rc;
   if ((rc = upload(S->wide32, wide32.data(), wide32.size()))) return rc;
   if ((rc = upload(S->tris, dtris.data(), dtris.size()))) return rc;
@@ -778,6 +784,8 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   // Light-space tables of the shadow kernels (light_maps.cpp): cube maps of the nearest possible occluder distance, one
   // per (point light, occluder mesh), and lit-triangle flags per (triangle, light of either kind).  Only the
   // shared-memory-table shadow kernels read them; RAYHS_B200_LIGHT_MAPS=0 switches the build off.
+  S->ms_upload = ms_since(t_mark);
+  t_mark = clk::now();
   v.light_maps = nullptr;
   v.lit_flags = nullptr;
   v.light_map_index = nullptr;
@@ -892,6 +900,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       }
     }
   }
+  S->ms_light_tables = ms_since(t_mark);
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
   v.abs_max = abs_max;
@@ -1345,6 +1354,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->shade_fetches = fc->k[0].shade_fetches;
       stats->texel_fetches = fc->k[0].texel_fetches;
       stats->node_visits = fc->k[0].node_visits;
+      stats->node_visits_global = fc->k[0].global_node_visits;
+      stats->shadow_node_visits_global = fc->k[1].global_node_visits;
       stats->shadow_box_tests = fc->k[1].box_tests;
       stats->shadow_tri_tests = fc->k[1].tri_tests;
       stats->shadow_prim_tests = fc->k[1].prim_tests;
@@ -1440,6 +1451,21 @@ int rh_scene_create(const rh_scene_desc* desc, rh_scene** out) {
   return scene_create_on(g_dev.get(), desc, out);
 }
 void rh_scene_destroy(rh_scene* scene) { scene_destroy(scene); }
+int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4) {
+  if (!scene) return rh::set_error(RH_ERR_ARG, "rh_scene_info: null scene");
+  if (setup_ms3) {
+    setup_ms3[0] = scene->ms_trees;
+    setup_ms3[1] = scene->ms_light_tables;
+    setup_ms3[2] = scene->ms_upload;
+  }
+  if (info4) {
+    info4[0] = (int32_t)scene->view.tables_in_smem;
+    info4[1] = (int32_t)scene->view.shadow_fast;
+    info4[2] = (int32_t)scene->max_tree_depth;
+    info4[3] = (int32_t)scene->deep_entries;
+  }
+  return RH_OK;
+}
 
 int rh_render(const rh_scene* scene, const rh_camera* camera, const rh_render_opts* opts, uint8_t* rgb_out,
               int32_t* hit_ids_out, rh_stats* stats) {
@@ -1602,6 +1628,9 @@ int rh_multi_render(const rh_multi_scene* scene, const rh_camera* camera, const 
       stats->shade_fetches += s.shade_fetches; stats->texel_fetches += s.texel_fetches; stats->node_visits += s.node_visits;
       stats->shadow_box_tests += s.shadow_box_tests; stats->shadow_tri_tests += s.shadow_tri_tests;
       stats->shadow_prim_tests += s.shadow_prim_tests; stats->shadow_node_visits += s.shadow_node_visits;
+      stats->node_visits_global += s.node_visits_global; stats->shadow_node_visits_global += s.shadow_node_visits_global;
+      stats->shadow_tasks_queued += s.shadow_tasks_queued; stats->shadow_walk_pairs += s.shadow_walk_pairs;
+      stats->deep_stack_pushes += s.deep_stack_pushes;
       stats->upload_bytes += s.upload_bytes;
       stats->ms_total = std::max(stats->ms_total, s.ms_total);
       stats->ms_trace = std::max(stats->ms_trace, s.ms_trace);

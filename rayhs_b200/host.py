@@ -93,6 +93,15 @@ class Scene:
             check(lib().rh_scene_create(self.flat, C.byref(self._dev)))
         return self._dev
 
+    def _info(self):
+        ms, info = (C.c_double * 3)(), (C.c_int32 * 4)()
+        check(lib().rh_scene_info(self.device, ms, info))
+        return list(ms), list(info)
+
+    @property
+    def tables_in_smem(self) -> bool:
+        return bool(self._info()[1][0])
+
     def close(self) -> None:
         L = lib()
         if self._dev:
@@ -205,6 +214,12 @@ def render(job: Rendering, spp: int = 1, offsets=None, offset_tile: int = 0, wan
     check(L.rh_render(job.scene.device, C.byref(job.camera), C.byref(o), rgb.ctypes.data,
                       ids.ctypes.data if ids is not None else None, C.byref(st)))
     return Image(job.width, rows, rgb, st.as_dict(), ids)
+
+
+def scene_setup_ms(scene: Scene) -> dict:
+    """Milliseconds rh_scene_create spent on its parts (host-side trees, light-space tables, uploads)."""
+    ms, info = scene._info()
+    return {"trees": ms[0], "light_tables": ms[1], "upload": ms[2], "deep_stack_entries_per_thread": info[3], "max_tree_depth": info[2]}
 
 
 def _shadow_flag(shadow: str | None) -> int:
