@@ -1792,12 +1792,23 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __
   const size_t cap = P.q_shadow.capacity;
   const double2* qp = P.q_shadow.plane;
 
+  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kShadowBlock / 32);
+  uint32_t seg_next = 0, seg_end = 0;  // the warp's claimed batches not yet processed
   for (;;) {
-    uint32_t slab = 0;
-    if (lane == 0) slab = atomicAdd(&ctl->shadow_cursor[P.pass], 1u);
-    slab = __shfl_sync(kFull, slab, 0);
-    if (slab >= n_slabs) break;
-    const uint32_t base = slab * kSlab, n_here = min(__ldg(P.q_shadow.fill + slab), kSlab);
+    // a whole slab per claim while plenty of work is left (full pools), smaller pieces near the end of the queue
+    if (seg_next == seg_end) {
+      const uint2 claim = claim_batches(&ctl->shadow_cursor[P.pass], n_batches, total_warps, lane);
+      if (claim.x >= n_batches) break;
+      seg_next = claim.x;
+      seg_end = min(claim.x + claim.y, n_batches);
+    }
+    // the part of the claim that lies in one slab
+    const uint32_t slab = seg_next / kSlabBatches, b_first = seg_next % kSlabBatches;
+    const uint32_t b_count = min(seg_end - seg_next, kSlabBatches - b_first);
+    seg_next += b_count;
+    const uint32_t fill = min(__ldg(P.q_shadow.fill + slab), kSlab);
+    if (b_first * 32 >= fill) continue;
+    const uint32_t base = slab * kSlab + b_first * 32, n_here = min(fill - b_first * 32, b_count * 32);
     uint32_t wm[kShadowT];
 #pragma unroll
     for (int t = 0; t < kShadowT; t++) {
@@ -2102,7 +2113,7 @@ __global__ void __launch_bounds__(kBlock) resolve_kernel(const __grid_constant__
         const double2* a1 = (const double2*)(a + P.accum_stride);
         const double2* a2 = (const double2*)(a + 2 * (size_t)P.accum_stride);
         for (uint32_t s = 0; s < P.spp / 2; s++) {
-          const double2 r2 = __ldcs(a0 + s), g2 = __ldcs(a1 + s), b2 = __ldcs(a2 + s);
+          const double2 r2 = a0[s], g2 = a1[s], b2 = a2[s];
           sr = (sr + r2.x) + r2.y;
           sg = (sg + g2.x) + g2.y;
           sb = (sb + b2.x) + b2.y;

@@ -419,11 +419,19 @@ struct TriBox {
 // own tree and boxes and reaches the permuted triangle records through an index.
 struct SahTree {
   struct Ref { uint32_t slot; float lo[3], hi[3], c[3]; };
+  // One subtree in its own arrays (LOCAL child indices and leaf slots), so that the two halves of a large range can be
+  // built by two threads and spliced in left-to-right order: the result is the array a sequential build writes.
+  struct Sub {
+    std::vector<rh_node> nodes;   // leaves: left = first slot in `order`, right = count
+    std::vector<uint32_t> order;  // new slot -> reference slot
+    uint32_t max_depth = 0;
+  };
   const std::vector<rh_tri>& tris;  // reference (leaf) order
-  std::vector<rh_node> nodes;       // leaves: left = first NEW slot, right = count
+  std::vector<rh_node> nodes;       // all trees built so far; leaves: left = first NEW slot, right = count
   std::vector<uint32_t> order;      // new slot -> reference slot
   uint32_t max_depth = 0;
   std::vector<Ref> refs;
+  std::atomic<bool> failed{false};
 
   explicit SahTree(const std::vector<rh_tri>& t) : tris(t) {}
 
@@ -432,8 +440,23 @@ struct SahTree {
     return x * y + y * z + z * x;
   }
 
-  uint32_t build(size_t b, size_t e, uint32_t depth) {
-    max_depth = std::max(max_depth, depth);
+  static uint32_t append(Sub& out, const Sub& in) {
+    const uint32_t node_off = (uint32_t)out.nodes.size(), slot_off = (uint32_t)out.order.size();
+    for (rh_node nd : in.nodes) {
+      if (nd.is_leaf) nd.left += slot_off;
+      else {
+        nd.left += node_off;
+        nd.right += node_off;
+      }
+      out.nodes.push_back(nd);
+    }
+    out.order.insert(out.order.end(), in.order.begin(), in.order.end());
+    out.max_depth = std::max(out.max_depth, in.max_depth);
+    return node_off;
+  }
+
+  uint32_t build(size_t b, size_t e, uint32_t depth, Sub& out, int fork_levels) {
+    out.max_depth = std::max(out.max_depth, depth);
     const float inf = std::numeric_limits<float>::infinity();
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf}, clo[3] = {inf, inf, inf}, chi[3] = {-inf, -inf, -inf};
     for (size_t i = b; i < e; i++)
@@ -445,14 +468,14 @@ struct SahTree {
       }
     rh_node nd{};
     for (int k = 0; k < 3; k++) { nd.lo[k] = lo[k]; nd.hi[k] = hi[k]; }
-    const uint32_t self = (uint32_t)nodes.size();
-    nodes.push_back(nd);
+    const uint32_t self = (uint32_t)out.nodes.size();
+    out.nodes.push_back(nd);
     const size_t n = e - b;
     if (n <= kSubLeaf) {
-      nodes[self].is_leaf = 1;
-      nodes[self].left = (uint32_t)order.size();
-      nodes[self].right = (uint32_t)n;
-      for (size_t i = b; i < e; i++) order.push_back(refs[i].slot);
+      out.nodes[self].is_leaf = 1;
+      out.nodes[self].left = (uint32_t)out.order.size();
+      out.nodes[self].right = (uint32_t)n;
+      for (size_t i = b; i < e; i++) out.order.push_back(refs[i].slot);
       return self;
     }
     // binned SAH over the three axes; deep or degenerate ranges fall back to the object median of the widest axis
@@ -519,10 +542,31 @@ struct SahTree {
                        [axis](const Ref& x, const Ref& y) { return x.c[axis] < y.c[axis] || (x.c[axis] == y.c[axis] && x.slot < y.slot); });
     }
     if (mid == b || mid == e) mid = b + n / 2;
-    const uint32_t l = build(b, mid, depth + 1);
-    const uint32_t r = build(mid, e, depth + 1);
-    nodes[self].left = l;
-    nodes[self].right = r;
+    uint32_t l, r;
+    if (fork_levels > 0 && n >= (1u << 15) && !failed.load(std::memory_order_relaxed)) {
+      Sub L, R;  // the two halves touch disjoint ranges of `refs`
+      std::thread th([&]() {
+        try {
+          build(b, mid, depth + 1, L, fork_levels - 1);
+        } catch (...) {
+          failed = true;  // (no exception may leave a thread; the caller reports out-of-memory)
+        }
+      });
+      try {
+        build(mid, e, depth + 1, R, fork_levels - 1);
+      } catch (...) {
+        failed = true;
+      }
+      th.join();
+      if (failed) return self;
+      l = append(out, L);
+      r = append(out, R);
+    } else {
+      l = build(b, mid, depth + 1, out, 0);
+      r = build(mid, e, depth + 1, out, 0);
+    }
+    out.nodes[self].left = l;
+    out.nodes[self].right = r;
     return self;
   }
 
@@ -542,7 +586,25 @@ struct SahTree {
         r.c[a] = 0.5f * (r.lo[a] + r.hi[a]);
       }
     }
-    return build(0, count, 0);
+    const unsigned n_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    int fork_levels = 0;
+    while ((1u << fork_levels) < n_threads) fork_levels++;
+    Sub sub;
+    build(0, count, 0, sub, count >= (1u << 16) ? fork_levels + 1 : 0);
+    if (failed) throw std::bad_alloc();
+    // splice into the arrays of all trees
+    const uint32_t node_off = (uint32_t)nodes.size(), slot_off = (uint32_t)order.size();
+    for (rh_node nd : sub.nodes) {
+      if (nd.is_leaf) nd.left += slot_off;
+      else {
+        nd.left += node_off;
+        nd.right += node_off;
+      }
+      nodes.push_back(nd);
+    }
+    order.insert(order.end(), sub.order.begin(), sub.order.end());
+    max_depth = std::max(max_depth, sub.max_depth);
+    return node_off;
   }
 
   // Exact (double, padded) boxes of all nodes from the permuted triangles, bottom-up.
