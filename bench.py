@@ -47,7 +47,7 @@ WORKLOADS = {
                metric="Mrays/s (primary + secondary + shadow), dragon.json full-res at 3840x2160, 16 spp",
                desc="dragon.json + dragon.obj (27228 tris), {w}x{h}, {spp} spp, maxDepth 3, 3 point lights (BASELINE.json configs[3])",
                data="synthetic sample offsets (SplitMix64 seed 24); shipped dragon.obj scene"),
-    "c5": dict(tris=10_000_000, spheres=1000, width=7680, height=4320, spp=64, seed=24, steps=3,
+    "c5": dict(tris=10_000_000, spheres=1000, width=7680, height=4320, spp=64, seed=24, steps=2,
                metric="Mrays/s (primary + secondary + shadow), synthetic stress scene (10 M triangles + 1 k spheres) at 7680x4320, 64 spp",
                desc="synthetic stress scene: {tris} random triangles + {spheres} spheres + checker floor, {w}x{h}, {spp} spp, maxDepth 3, "
                     "3 point lights (BASELINE.json configs[4], SURVEY 8d C5)",
@@ -346,7 +346,10 @@ def main():
         L.rh_sample_offsets_f64(seed, W * H, spp, off_host.data_ptr())
         off_dev = off_host.cuda()
     else:
-        off_host = torch.empty((rows * W, spp, 2), dtype=torch.float64, pin_memory=True)
+        try:
+            off_host = torch.empty((rows * W, spp, 2), dtype=torch.float64, pin_memory=True)
+        except RuntimeError:   # (34 GB of pinned memory at N = 1)
+            off_host = torch.empty((rows * W, spp, 2), dtype=torch.float64)
         for lb in range(rows // bh):
             grow = (lb * G + rank) * bh
             n = max(0, min(bh, H - grow))

@@ -279,7 +279,7 @@ bool build_light_map(const double L[3], const rh_tri* tris, const uint32_t* slot
   // Triangles go in a strided order so that an early look at the fill tells a soup from a shape.
   const size_t stride = n > 4096 ? 4093 : 1;  // prime: a permutation of 0..n-1 whenever n is not a multiple of it
   const bool permute = stride > 1 && n % stride != 0;
-  size_t done = 0, next_check = 200000;
+  size_t done = 0, next_check = 16384, prev_empty = 0;
   for (size_t i = 0; i < n; i++) {
     const size_t at = permute ? (i * stride) % n : i;
     const rh_tri& t = tris[slots[at]];
@@ -303,6 +303,16 @@ bool build_light_map(const double L[3], const rh_tri* tris, const uint32_t* slot
       size_t empty = 0;
       for (size_t q = 0; q < cells; q++) empty += out[q] == inf;
       if ((double)empty < min_empty * (double)cells) return false;
+      // A soup shows early.  The last done/2 triangles (a uniform sample of the mesh: strided order) took the fraction r
+      // of the cells that were still empty before them; triangles scattered at random keep taking that fraction, a
+      // shape's silhouette saturates (r -> 0).  When the empties predicted for all n triangles are far below the useful
+      // minimum the map is given up now (this only decides whether a map is worth having, never what a map says).
+      if (prev_empty > 0 && empty < prev_empty) {
+        const double r = (double)(prev_empty - empty) / (double)prev_empty;
+        const double blocks = (double)(n - done) / (0.5 * (double)done);
+        if ((double)empty / (double)cells * std::pow(1.0 - r, blocks) < 1e-3 * min_empty) return false;
+      }
+      prev_empty = empty;
     }
   }
   size_t empty = 0;
