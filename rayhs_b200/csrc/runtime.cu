@@ -1110,6 +1110,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       // accumulators + (two ray queues + hit queue + half a walk queue) at 2 entries per sample
       const size_t per_sample = 3 * sizeof(double) + 2 * (2 * 4 * sizeof(double2) + (5 * sizeof(double2) + 8) + (5 * sizeof(double2) + 12) / 2);
       want = std::min<size_t>((size_t)(0.45 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
+      // a frame that needs several chunks has two of them in flight, each with its own scratch: half the budget each
+      if (RH_LANES > 1 && (size_t)rows_local * row_samples > want) want /= 2;
       if (host_offsets) want = std::min<size_t>(want, (size_t)RH_STREAM_CHUNK_MI << 20);
       first = host_offsets ? std::min<size_t>(want, (size_t)RH_STREAM_FIRST_MI << 20) : want;
     }
