@@ -110,16 +110,17 @@ class ClockSampler:
 def algorithmic_bytes(st: dict, offset_bytes: int, tables_in_smem: bool, n_pixels: int, spp: int) -> dict:
     """bytes that must LEAVE or ENTER an SM per frame, per kernel, from the instrumented (RH_FLAG_COUNT)
     kernels' own counters.  Only global-memory records count: node records beyond the shared-memory-staged top levels
-    (64 B), triangle records (80 B), winning shading records (128 B), texels (24 B), object records of sphere-tree
+    (64 B) and triangle records (80 B) — both counted once per warp instruction: lanes that read the same record share
+    one fetch —, winning shading records (128 B), texels (24 B), object records of sphere-tree
     leaves when the object table is not staged (96 B), sample offsets, queue entries written and read (ray 64 B, hit
     88 B, queued hit 92 B, + the point re-read per walked pair 32 B), accumulator updates (24 B).  The occluder, light and
     material tables and the top tree levels live in shared memory and are not traffic."""
     prim = 0 if tables_in_smem else 96
-    trace = (64 * st["node_visits_global"] + 80 * st["tri_tests"] + prim * st["prim_tests"] + 128 * st["shade_fetches"]
+    trace = (64 * st["node_visits_global"] + 80 * st["tri_records"] + prim * st["prim_tests"] + 128 * st["shade_fetches"]
              + 24 * st["texel_fetches"] + offset_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 88 * st["shadow_tasks"])
     classify = 88 * st["shadow_tasks"] + 92 * st["shadow_tasks_queued"] + 24 * (st["shadow_tasks"] - st["shadow_tasks_queued"])
     walk = (92 * st["shadow_tasks_queued"] + 32 * st["shadow_walk_pairs"] + 24 * st["shadow_tasks_queued"]
-            + 64 * st["shadow_node_visits_global"] + 80 * st["shadow_tri_tests"] + prim * st["shadow_prim_tests"])
+            + 64 * st["shadow_node_visits_global"] + 80 * st["shadow_tri_records"] + prim * st["shadow_prim_tests"])
     resolve = (24 * spp + 3) * n_pixels
     return {"trace": trace, "classify": classify, "walk": walk, "resolve": resolve}
 
@@ -316,6 +317,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # one-shot use first, while this process holds no device memory: a fresh process renders one frame
+    cold = cold_start(name, wl) if (rank == 0 and world == 1 and not args.no_cold_start) else None
     t0 = time.time()
     rh.init(local_rank)
     t_init = time.time() - t0
@@ -583,10 +586,6 @@ def main():
             parity.update(rows=int(n_par), columns=int(len(ref["cols"])), samples=int(mism.size), id_mismatches=int(mism.sum()),
                           sample_rows_equal_the_timed_frame=rows_equal,
                           against="oracle/oracle.cpp on the same offsets (parity unpinned by reference vectors: none exist, GHC absent)")
-
-    cold = None
-    if rank == 0 and G == 1 and not args.no_cold_start:
-        cold = cold_start(name, wl)
 
     if rank == 0:
         st = stats[-1]

@@ -275,8 +275,11 @@ typedef struct rh_stats {
   uint64_t shadow_tri_tests;
   uint64_t shadow_prim_tests;
   uint64_t shadow_node_visits;
-  uint64_t node_visits_global;        /* of node_visits: records read from global memory (not the staged top levels) */
+  uint64_t node_visits_global;        /* node records fetched from global memory (not the staged top levels), counted once
+                                         per warp instruction: lanes that visit the same node share one fetch          */
   uint64_t shadow_node_visits_global;
+  uint64_t tri_records;               /* triangle records fetched, counted the same way                              */
+  uint64_t shadow_tri_records;
   uint64_t upload_bytes;  /* sample-offset bytes copied host -> device           */
   double ms_total;        /* CUDA events around the whole call's device work (uploads and read-back included) */
   double ms_trace;        /* RH_FLAG_PROFILE only: closest-hit + shade kernels   */

@@ -102,6 +102,7 @@ class rh_stats(C.Structure):
                 ("shade_fetches", C.c_uint64), ("texel_fetches", C.c_uint64), ("node_visits", C.c_uint64),
                 ("shadow_box_tests", C.c_uint64), ("shadow_tri_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
                 ("shadow_node_visits", C.c_uint64), ("node_visits_global", C.c_uint64), ("shadow_node_visits_global", C.c_uint64),
+                ("tri_records", C.c_uint64), ("shadow_tri_records", C.c_uint64),
                 ("upload_bytes", C.c_uint64), ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_resolve", C.c_double), ("trace_launches", C.c_uint32), ("shadow_launches", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("chunks", C.c_uint32), ("negative_channels", C.c_uint32),

@@ -173,7 +173,7 @@ struct ChunkCtl {
 
 // Frame-level counters (zeroed per rh_render).
 struct KernelCounters {  // RH_FLAG_COUNT only
-  unsigned long long box_tests, tri_tests, prim_tests, node_visits, shade_fetches, texel_fetches, global_node_visits;
+  unsigned long long box_tests, tri_tests, prim_tests, node_visits, shade_fetches, texel_fetches, global_node_visits, tri_records;
 };
 struct FrameCounters {
   unsigned long long rays_reflect, rays_probe, rays_exit, negative_channels;

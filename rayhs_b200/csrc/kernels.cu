@@ -245,8 +245,8 @@ __device__ __forceinline__ void stage_walk_tables(WalkTables& sm, const SceneVie
 // ------------------------------------------------------------------ counters
 template <bool COUNT>
 struct Cnt {
-  unsigned long long box, tri, prim, nodes, gnodes, shade, texel, deep;
-  __device__ __forceinline__ void zero() { box = tri = prim = nodes = gnodes = shade = texel = deep = 0; }
+  unsigned long long box, tri, prim, nodes, gnodes, wtri, shade, texel, deep;
+  __device__ __forceinline__ void zero() { box = tri = prim = nodes = gnodes = wtri = shade = texel = deep = 0; }
 };
 template <>
 struct Cnt<false> {
@@ -259,10 +259,10 @@ template <bool COUNT>
 __device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc, int which) {
   if constexpr (COUNT) {
     KernelCounters* kc = &fc->k[which];
-    unsigned long long* src[7] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel, &cnt.gnodes};
-    unsigned long long* dst[7] = {&kc->box_tests, &kc->tri_tests, &kc->prim_tests, &kc->node_visits, &kc->shade_fetches,
-                                  &kc->texel_fetches, &kc->global_node_visits};
-    for (int k = 0; k < 7; k++) {
+    unsigned long long* src[8] = {&cnt.box, &cnt.tri, &cnt.prim, &cnt.nodes, &cnt.shade, &cnt.texel, &cnt.gnodes, &cnt.wtri};
+    unsigned long long* dst[8] = {&kc->box_tests, &kc->tri_tests, &kc->prim_tests, &kc->node_visits, &kc->shade_fetches,
+                                  &kc->texel_fetches, &kc->global_node_visits, &kc->tri_records};
+    for (int k = 0; k < 8; k++) {
       unsigned long long v = *src[k];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
       if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst[k], v);
@@ -463,6 +463,10 @@ __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint3
     const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
     const double e2z = __ldg((const double*)(tp + 4));
     RH_CNT(tri, 1);
+    if constexpr (COUNT) {
+      const unsigned peers = __match_any_sync(__activemask(), slot);
+      if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) cnt.wtri += 1;  // triangle records fetched (once per warp instruction)
+    }
     const V3 p0 = mk(a.x, a.y, b.x), e1 = mk(b.y, c.x, c.y), e2 = mk(d.x, d.y, e2z);
     const V3 p = cross(r.d, e2);
     const double det = dot(e1, p);
@@ -519,7 +523,12 @@ __device__ __forceinline__ bool node_step(const Ctx& cx, uint32_t& ref, const Ra
   const uint2 cw = *(const uint2*)(np + 3);  // child0, child1
   RH_CNT(nodes, 1);
   if constexpr (COUNT) {
-    if (ref >= cx.S->n_smem_nodes) cnt.gnodes += 1;  // a record read from global memory (not one of the staged top levels)
+    // records read from global memory (not the staged top levels), counted once per warp instruction: lanes that
+    // visit the same node share one fetch
+    if (ref >= cx.S->n_smem_nodes) {
+      const unsigned peers = __match_any_sync(__activemask(), ref);
+      if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) cnt.gnodes += 1;
+    }
   }
   bool h0 = false, h1 = false;
   float tm0 = 0, tm1 = 0;

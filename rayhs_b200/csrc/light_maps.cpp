@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <limits>
 #include <new>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -279,26 +281,43 @@ bool build_light_map(const double L[3], const rh_tri* tris, const uint32_t* slot
   // Triangles go in a strided order so that an early look at the fill tells a soup from a shape.
   const size_t stride = n > 4096 ? 4093 : 1;  // prime: a permutation of 0..n-1 whenever n is not a multiple of it
   const bool permute = stride > 1 && n % stride != 0;
-  size_t done = 0, next_check = 16384, prev_empty = 0;
-  for (size_t i = 0; i < n; i++) {
-    const size_t at = permute ? (i * stride) % n : i;
-    const rh_tri& t = tris[slots[at]];
-    const P3 p0 = {t.p0[0], t.p0[1], t.p0[2]};
-    const P3 a = sub(p0, lp);
-    const P3 b = sub(add(p0, P3{t.e1[0], t.e1[1], t.e1[2]}), lp);
-    const P3 c = sub(add(p0, P3{t.e2[0], t.e2[1], t.e2[2]}), lp);
-    double coord = scale_abs;
-    for (int k = 0; k < 3; k++) coord = std::max(coord, std::max(std::fabs(a[k]), std::max(std::fabs(b[k]), std::fabs(c[k]))));
-    if (!std::isfinite(coord)) return false;
-    const double d = dist_origin_triangle(a, b, c);
-    if (!(d > 1e-6 * coord)) return false;
-    const float val = round_down(d * (1.0 - 1e-6) - 1e-9 * coord);
-    const P3 tri[3] = {a, b, c};
-    for (int k = 0; k < 3; k++) {
-      raster_face(out + (size_t)(2 * k) * R * R, R, tri, k, 1.0, val);
-      raster_face(out + (size_t)(2 * k + 1) * R * R, R, tri, k, -1.0, val);
+  std::atomic<bool> unsafe{false};
+  // One cube face per thread (the faces are disjoint parts of `out`): every thread walks the same stretch of the
+  // triangle sequence and rasterises only its own face.
+  auto raster_range = [&](size_t begin, size_t end, int face) {
+    const int k = face / 2;
+    const double sgn = (face & 1) ? -1.0 : 1.0;
+    for (size_t i = begin; i < end; i++) {
+      const size_t at = permute ? (i * stride) % n : i;
+      const rh_tri& t = tris[slots[at]];
+      const P3 p0 = {t.p0[0], t.p0[1], t.p0[2]};
+      const P3 a = sub(p0, lp);
+      const P3 b = sub(add(p0, P3{t.e1[0], t.e1[1], t.e1[2]}), lp);
+      const P3 c = sub(add(p0, P3{t.e2[0], t.e2[1], t.e2[2]}), lp);
+      double coord = scale_abs;
+      for (int q = 0; q < 3; q++) coord = std::max(coord, std::max(std::fabs(a[q]), std::max(std::fabs(b[q]), std::fabs(c[q]))));
+      if (!std::isfinite(coord)) { unsafe = true; return; }
+      const double d = dist_origin_triangle(a, b, c);
+      if (!(d > 1e-6 * coord)) { unsafe = true; return; }
+      const float val = round_down(d * (1.0 - 1e-6) - 1e-9 * coord);
+      const P3 tri[3] = {a, b, c};
+      raster_face(out + (size_t)face * R * R, R, tri, k, sgn, val);
     }
-    if (++done == next_check) {
+  };
+  const bool threaded = n >= 2048 && std::thread::hardware_concurrency() >= 4;
+  size_t done = 0, next_check = 16384, prev_empty = 0;
+  while (done < n) {
+    const size_t end = std::min(n, next_check);
+    if (threaded) {
+      std::thread pool[6];
+      for (int f = 0; f < 6; f++) pool[f] = std::thread(raster_range, done, end, f);
+      for (int f = 0; f < 6; f++) pool[f].join();
+    } else {
+      for (int f = 0; f < 6; f++) raster_range(done, end, f);
+    }
+    if (unsafe) return false;
+    done = end;
+    if (done == next_check && done < n) {
       next_check *= 2;
       size_t empty = 0;
       for (size_t q = 0; q < cells; q++) empty += out[q] == inf;

@@ -881,9 +881,13 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
               else dfs.push_back(w.child[c]);
             }
           }
-          // lit triangles: per triangle and light, can another triangle of this mesh shadow it at all?
-          if (slots.size() * (size_t)d->n_lights <= kLitMaxQueries && !(env_lit && env_lit[0] == '0')) {
-            if (lit.empty()) lit.assign(dtris.size(), 0);
+          // lit triangles: per triangle and light, can another triangle of this mesh shadow it at all?  The queries
+          // run on their own threads while this one builds the mesh's cube maps.
+          const bool want_lit = slots.size() * (size_t)d->n_lights <= kLitMaxQueries && !(env_lit && env_lit[0] == '0');
+          if (want_lit && lit.empty()) lit.assign(dtris.size(), 0);
+          size_t lit_found = 0;
+          bool lit_failed = false;
+          auto lit_job = [&, m]() {
             // one query per (triangle, light), independent of each other: a few host threads share the triangles
             std::atomic<size_t> next{0}, flagged{0};
             std::atomic<bool> failed{false};
@@ -926,25 +930,39 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
               }
               flagged += mine;
             };
-            const unsigned n_threads = slots.size() < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            const unsigned n_threads = slots.size() < 4096 ? 1u : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
             if (n_threads == 1) {
               work();
             } else {
-              std::vector<std::thread> pool;
-              for (unsigned t = 0; t < n_threads; t++) pool.emplace_back(work);
-              for (std::thread& t : pool) t.join();
+              try {
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < n_threads; t++) pool.emplace_back(work);
+                for (std::thread& t : pool) t.join();
+              } catch (...) {
+                failed = true;
+              }
             }
-            if (failed) throw std::bad_alloc();
-            n_lit += flagged.load();
+            lit_failed = failed.load();
+            lit_found = flagged.load();
+          };
+          std::thread lit_thread;
+          if (want_lit) lit_thread = std::thread(lit_job);
+          bool maps_failed = false;
+          try {
+            for (uint32_t li = 0; li < d->n_lights; li++) {
+              if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+              double empty = 0;
+              if (!rh::build_light_map(d->lights[li].vec, dtris.data(), slots.data(), slots.size(), R, one.data(), kLightMapMinEmpty, &empty))
+                continue;
+              index[(size_t)li * kOccMeshes + m] = n_maps++;
+              maps.insert(maps.end(), one.begin(), one.end());
+            }
+          } catch (...) {
+            maps_failed = true;  // (the query threads must be joined before anything unwinds)
           }
-          for (uint32_t li = 0; li < d->n_lights; li++) {
-            if (d->lights[li].kind != RH_LIGHT_POINT) continue;
-            double empty = 0;
-            if (!rh::build_light_map(d->lights[li].vec, dtris.data(), slots.data(), slots.size(), R, one.data(), kLightMapMinEmpty, &empty))
-              continue;
-            index[(size_t)li * kOccMeshes + m] = n_maps++;
-            maps.insert(maps.end(), one.begin(), one.end());
-          }
+          if (lit_thread.joinable()) lit_thread.join();
+          if (lit_failed || maps_failed) throw std::bad_alloc();
+          n_lit += lit_found;
         }
         if (n_lit) {
           if ((rc = upload(S->lit_flags, lit.data(), lit.size()))) return rc;
@@ -1420,6 +1438,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->node_visits = fc->k[0].node_visits;
       stats->node_visits_global = fc->k[0].global_node_visits;
       stats->shadow_node_visits_global = fc->k[1].global_node_visits;
+      stats->tri_records = fc->k[0].tri_records;
+      stats->shadow_tri_records = fc->k[1].tri_records;
       stats->shadow_box_tests = fc->k[1].box_tests;
       stats->shadow_tri_tests = fc->k[1].tri_tests;
       stats->shadow_prim_tests = fc->k[1].prim_tests;
@@ -1693,6 +1713,7 @@ int rh_multi_render(const rh_multi_scene* scene, const rh_camera* camera, const 
       stats->shadow_box_tests += s.shadow_box_tests; stats->shadow_tri_tests += s.shadow_tri_tests;
       stats->shadow_prim_tests += s.shadow_prim_tests; stats->shadow_node_visits += s.shadow_node_visits;
       stats->node_visits_global += s.node_visits_global; stats->shadow_node_visits_global += s.shadow_node_visits_global;
+      stats->tri_records += s.tri_records; stats->shadow_tri_records += s.shadow_tri_records;
       stats->shadow_tasks_queued += s.shadow_tasks_queued; stats->shadow_walk_pairs += s.shadow_walk_pairs;
       stats->deep_stack_pushes += s.deep_stack_pushes;
       stats->upload_bytes += s.upload_bytes;
