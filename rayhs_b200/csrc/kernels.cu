@@ -608,8 +608,8 @@ __device__ __forceinline__ bool traverse(const Ctx& cx, uint32_t root, const Ray
 // included): rays with a zero direction component (centre row/column of the image), far origins, and
 // RH_FLAG_EXACT_BOXES validation runs.  Cold path: kept out of line; its stack is the thread's global column.
 template <bool COUNT, class Sink, bool SPHERES = false>
-__device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, Stack& st,
-                                            Cnt<COUNT>& cnt, bool skip_emitters = false) {
+__device__ __noinline__ bool traverse_exact_impl(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, Stack& st,
+                                                 Cnt<COUNT>& cnt, bool skip_emitters) {
   const V3 inv = mk(1 / r.d.x, 1 / r.d.y, 1 / r.d.z);
   int sp = 0;
   uint32_t ref = root, first = 0;
@@ -665,6 +665,23 @@ __device__ __noinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const 
     ref = e.x;
     first = e.y;
   }
+}
+
+// The out-of-line walk gets COPIES of the ray, the sink, the tables and the stack handle: handing it the caller's own
+// objects by reference would pin those — the hottest values of every kernel — in local memory for the whole kernel
+// (ncu on an earlier build: 57 GB of local stores per pass-0 launch, every one written through to L2).
+template <bool COUNT, class Sink, bool SPHERES = false>
+__device__ __forceinline__ bool traverse_exact(const Ctx& cx, uint32_t root, const Ray& r, double& bound, Sink& sink, Stack& st,
+                                               Cnt<COUNT>& cnt, bool skip_emitters = false) {
+  Ctx cx_copy = cx;
+  Ray r_copy = r;
+  Sink sink_copy = sink;
+  Stack st_copy = st;
+  double bound_copy = bound;
+  const bool stop = traverse_exact_impl<COUNT, Sink, SPHERES>(cx_copy, root, r_copy, bound_copy, sink_copy, st_copy, cnt, skip_emitters);
+  sink = sink_copy;
+  bound = bound_copy;
+  return stop;
 }
 
 // Geometry.hs:70-79 (plane): hit iff |d.n| > 0 and time = n.(p-o) / (d.n) > 0.  The quotient is
@@ -820,15 +837,15 @@ __device__ __forceinline__ long long hs_mod_int(long long a, long long m) {
 
 // ColorMap.hs:18-58
 template <bool COUNT>
-__device__ __noinline__ V3 color_at(const Ctx& cx, const rh_material& m, double u, double v, Cnt<COUNT>& cnt) {
+__device__ __noinline__ V3 color_at(const SceneView& S, const rh_material& m, double u, double v, Cnt<COUNT>& cnt) {
   const V3 c1 = ld3(m.color1);
   if (m.cmap_kind == RH_CMAP_FLAT) return c1;
   if (m.cmap_kind == RH_CMAP_CHECKER) {
     const double s = m.size;
     return ((hs_mod1(u, s) - (0.5 * s)) * (hs_mod1(v, s) - (0.5 * s)) < 0) ? c1 : ld3(m.color2);
   }
-  const rh_texture tx = cx.S->textures[m.texture];
-  const double* px = cx.S->texels + 3 * tx.offset;
+  const rh_texture tx = S.textures[m.texture];
+  const double* px = S.texels + 3 * tx.offset;
   const double uu = hs_mod1(u, 1) * (double)tx.w;  // toPixel / repeatUV
   const double vv = hs_mod1(v, 1) * (double)tx.h;
   const long long ui = (long long)rint(uu);  // round: half to even
@@ -1620,7 +1637,7 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
           n_shaded++;
           task.p = p;
           task.n = n;
-          task.cd = color_at<COUNT>(cx, cx.materials[mat_index], tu, tv, cnt);
+          task.cd = color_at<COUNT>(S, cx.materials[mat_index], tu, tv, cnt);
           task.w = w;
           task.sample = sample | (mkind == RH_MAT_DIFFUSE ? 0x80000000u : 0u);
           // lit-triangle flags of the hit triangle (light_maps.cpp) travel in the `walk` word of the hit queue

@@ -1122,6 +1122,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   // k+1's upload overlaps chunk k's kernels, so the chunks stay moderate (16 Mi samples) and the first one, whose
   // upload nothing can overlap, is small.
   std::vector<int> plan;  // rows per chunk
+  int n_tail = 0;         // chunks at the end of the plan that stay last in the processing order (streamed offsets)
   {
     size_t want = (size_t)o->chunk_samples, first = want;
     if (o->chunk_samples <= 0) {
@@ -1139,6 +1140,21 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       const int n = (int)std::max<size_t>(1, std::min<size_t>(w / row_samples, (size_t)(rows_local - row)));
       plan.push_back(n);
       row += n;
+    }
+    // Streamed offsets: the frame ends with the kernels of the chunk whose upload finishes last, so the frame's last
+    // chunk is cut into halves of halves (down to ~1 Mi samples): what is left to do after the last byte has arrived is
+    // a small chunk's work.
+    if (host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
+      int last = plan.back();
+      plan.pop_back();
+      const int min_rows = (int)std::max<size_t>(1, ((size_t)1 << 20) / row_samples);
+      while (last > 2 * min_rows && n_tail < 4) {
+        plan.push_back(last - last / 2);
+        last /= 2;
+        n_tail++;
+      }
+      plan.push_back(last);
+      n_tail++;
     }
   }
   const int n_chunks = (int)plan.size();
@@ -1274,7 +1290,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     std::vector<int> key = {W, H, spp, G, o->shard_index, bh};
     key.insert(key.end(), plan.begin(), plan.end());
     if (stream_offsets && n_chunks > 2 && scene->cost_key == key && (int)scene->chunk_ms.size() == n_chunks)
-      std::stable_sort(order.begin() + 1, order.end(), [&](int x, int y) {  // the small first chunk stays first
+      std::stable_sort(order.begin() + 1, order.end() - n_tail, [&](int x, int y) {  // the small first chunk stays first, the tail pieces last
         return scene->chunk_ms[x] / plan[x] > scene->chunk_ms[y] / plan[y];
       });
     std::vector<cudaEvent_t> chunk_ev;

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shards", type=int, default=8)
 ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--shadow", default="pooled", choices=["pooled", "split"])
 a = ap.parse_args()
 rh.init(0)
 L = capi.lib()
@@ -34,7 +35,7 @@ for G in (1, a.shards):
     bh = L.rh_default_band_height(H, G)
     rows = L.rh_shard_rows(H, G, bh)
     rgb = torch.empty((rows, W, 3), dtype=torch.uint8, device="cuda")
-    kw = dict(spp=spp, offsets_dev=off_dev, shard_index=0, shard_count=G, band_height=bh, shadow="pooled", chunk_samples=a.chunk)
+    kw = dict(spp=spp, offsets_dev=off_dev, shard_index=0, shard_count=G, band_height=bh, shadow=a.shadow, chunk_samples=a.chunk)
     for _ in range(4):
         rh.render_device(job, rgb, **kw)
     torch.cuda.synchronize()
