@@ -923,16 +923,20 @@ __device__ __forceinline__ void slab_close(const SlabWriter& w, uint32_t lane, u
 // small launches, so that no warp ends up with a long tail — the secondary passes are short launches whose duration
 // is set by their slowest warp.  Returns (first batch, number of batches); first >= n_batches: nothing left.
 constexpr uint32_t kSlabBatches = kSlab / 32;
-__device__ __forceinline__ uint2 claim_batches(uint32_t* cursor, uint32_t n_batches, uint32_t total_warps, uint32_t lane) {
+// `seen`: where the cursor stood after this warp's previous claim (a lower bound of where it stands now; before the
+// first claim: as if every warp ahead of this one had taken a slab) — the estimate of the work left costs no extra
+// round trip to the cursor's cache line.
+__device__ __forceinline__ uint2 claim_batches(uint32_t* cursor, uint32_t n_batches, uint32_t total_warps, uint32_t lane,
+                                               uint32_t& seen) {
   uint2 c = make_uint2(0, 1);
   if (lane == 0) {
-    const uint32_t seen = *(volatile uint32_t*)cursor;
     const uint32_t left = seen < n_batches ? n_batches - seen : 0;
     c.y = min(kSlabBatches, max(1u, left / (2u * total_warps)));
     c.x = atomicAdd(cursor, c.y);
   }
   c.x = __shfl_sync(kFull, c.x, 0);
   c.y = __shfl_sync(kFull, c.y, 0);
+  seen = c.x + c.y;
   return c;
 }
 
@@ -1196,19 +1200,12 @@ __device__ __forceinline__ bool roots_need_walk(const SmemTables& sm, const Scen
   r.o = q.o;
   r.d = q.ld;
   if (exact_boxes || needs_exact_walk(r, S)) return true;
-  if (use_maps && !q.directional) {
-    const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
-    const float dist_up = __double2float_ru(q.dd);
-    if (cell != kEmpty)
-      for (uint32_t m = 0; m < S.n_occ_meshes; m++) {
-        const uint32_t mi = sm.light_map[li][m];
-        if (mi != kEmpty && light_map_clears(S, mi, cell, dist_up)) skip |= 1u << m;
-      }
-  }
+  // the root boxes first (shared memory, ~60 instructions): only a pair whose ray enters a box asks that mesh's cube map
+  // (a dependent L2 load)
   const RayF f = make_rayf(r, S);
   const float ffar = __double2float_ru(q.far);
-  bool need = false;
-  for (uint32_t m = 0; m < n_roots && !need; m++) {
+  uint32_t enters = 0;
+  for (uint32_t m = 0; m < n_roots; m++) {
     if ((skip >> m) & 1u) continue;
     const uint32_t root = sm.mesh_roots[m];
     const float4* np = root < S.n_smem_nodes ? (const float4*)&sm.nodes[root] : (const float4*)&S.wide32[root];
@@ -1216,9 +1213,20 @@ __device__ __forceinline__ bool roots_need_walk(const SmemTables& sm, const Scen
     float tm;
     RH_CNT(nodes, 1);
     RH_CNT(box, 1);
-    need = slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar);
+    if (slab32(f, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, tm) && !(tm > ffar)) enters |= 1u << m;
   }
-  return need;
+  if (!enters) return false;
+  if (use_maps && !q.directional) {
+    const uint32_t cell = light_map_cell(p, q.lp, S.light_map_res);
+    const float dist_up = __double2float_ru(q.dd);
+    if (cell != kEmpty)
+      for (uint32_t m = 0; m < S.n_occ_meshes; m++) {
+        if (!((enters >> m) & 1u)) continue;
+        const uint32_t mi = sm.light_map[li][m];
+        if (mi != kEmpty && light_map_clears(S, mi, cell, dist_up)) enters &= ~(1u << m);
+      }
+  }
+  return enters != 0;
 }
 
 // The lights of one Diffuse / Plastic hit, everything that needs no tree walk: which lights add nothing (`settled`:
@@ -1467,8 +1475,9 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
   __syncwarp();
 
   const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kTraceBlock / 32);
+  uint32_t cursor_seen = (blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * kSlabBatches;  // as if every warp ahead had claimed a slab
   for (;;) {
-    const uint2 claim = claim_batches(&ctl->trace_cursor[P.pass], n_batches, total_warps, lane);
+    const uint2 claim = claim_batches(&ctl->trace_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
     if (claim.x >= n_batches) break;
     const uint32_t claim_end = min(claim.x + claim.y, n_batches);
     for (uint32_t bi = claim.x; bi < claim_end; bi++) {
@@ -1698,8 +1707,9 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
   const double2* qp = P.q_hits.plane;
   uint32_t n_culled = 0, n_walk_pairs = 0;
   const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kClassifyBlock / 32);
+  uint32_t cursor_seen = (blockIdx.x * (kClassifyBlock / 32) + (threadIdx.x >> 5)) * kSlabBatches;
   for (;;) {
-    const uint2 claim = claim_batches(&ctl->hit_cursor[P.pass], n_batches, total_warps, lane);
+    const uint2 claim = claim_batches(&ctl->hit_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
     if (claim.x >= n_batches) break;
     const uint32_t claim_end = min(claim.x + claim.y, n_batches);
     for (uint32_t bi = claim.x; bi < claim_end; bi++) {
@@ -1820,10 +1830,11 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __
 
   const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kShadowBlock / 32);
   uint32_t seg_next = 0, seg_end = 0;  // the warp's claimed batches not yet processed
+  uint32_t cursor_seen = (blockIdx.x * (kShadowBlock / 32) + warp) * kSlabBatches;
   for (;;) {
     // a whole slab per claim while plenty of work is left (full pools), smaller pieces near the end of the queue
     if (seg_next == seg_end) {
-      const uint2 claim = claim_batches(&ctl->shadow_cursor[P.pass], n_batches, total_warps, lane);
+      const uint2 claim = claim_batches(&ctl->shadow_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
       if (claim.x >= n_batches) break;
       seg_next = claim.x;
       seg_end = min(claim.x + claim.y, n_batches);
