@@ -553,8 +553,11 @@ def main():
         if not c5:
             v, sample, ref, prows = c4_oracle_sample(sc, W, H, spp, off_host.numpy(), 15.0, want_ids=True)
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
-            # parity of the frame the timed steps rendered, on every row the oracle just rendered: bytes and hit ids
-            step_device()
+            # parity of the frame the timed steps rendered, on every row the oracle just rendered: bytes and hit ids.
+            # (No collective in here: only rank 0 runs this block.  At N > 1 the complete frame is in this rank's peer
+            # frame since the assembled-frame check above.)
+            if G == 1:
+                step_device()
             torch.cuda.synchronize()
             gpu_rows = frame_dev[torch.from_numpy(prows).cuda()].cpu().numpy()
             ids_dev = torch.empty((H * W * spp, 2), dtype=torch.int32, device="cuda")
@@ -577,7 +580,7 @@ def main():
             rh.render_device(job, rgb16, spp=spp, seed=seed, shard_index=r0, shard_count=rstep, band_height=1, hit_ids_dev=ids16)
             torch.cuda.synchronize()
             ridx = torch.from_numpy(ref["rows"]).cuda()
-            rows_equal = bool(torch.equal(rgb16[:n_par], frame_dev[ridx])) if G == 1 or True else None
+            rows_equal = bool(torch.equal(rgb16[:n_par], frame_dev[ridx]))
             cidx = torch.from_numpy(ref["cols"]).cuda()
             gpu_px = frame_dev[ridx][:, cidx].cpu().numpy()
             gpu_ids = ids16.view(rgb16.shape[0], W, spp, 2)[:n_par][:, cidx].cpu().numpy()

@@ -1144,7 +1144,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     // Streamed offsets: the frame ends with the kernels of the chunk whose upload finishes last, so the frame's last
     // chunk is cut into halves of halves (down to ~1 Mi samples): what is left to do after the last byte has arrived is
     // a small chunk's work.
-    if (host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
+    static const bool tail_shaping = !(getenv("RAYHS_B200_TAIL") && getenv("RAYHS_B200_TAIL")[0] == '0');  // (A/B switch)
+    if (tail_shaping && host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
       int last = plan.back();
       plan.pop_back();
       const int min_rows = (int)std::max<size_t>(1, ((size_t)1 << 20) / row_samples);

@@ -4,7 +4,7 @@ N=${N:-2}
 WORKLOAD=${WORKLOAD:-c4}
 TAG=${TAG:-r2}
 mkdir -p gpurun_out
-timeout ${BENCH_TIMEOUT:-1500} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+timeout ${BENCH_TIMEOUT:-420} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus $N --workload $WORKLOAD $ARGS > gpurun_out/bench_${WORKLOAD}_${N}gpu_${TAG}.json 2> gpurun_out/bench_${WORKLOAD}_${N}gpu_${TAG}.err
 echo "bench rc=$?"
 tail -3 gpurun_out/bench_${WORKLOAD}_${N}gpu_${TAG}.err | cut -c1-300
