@@ -108,21 +108,27 @@ class ClockSampler:
 
 
 def algorithmic_bytes(st: dict, offset_bytes: int, tables_in_smem: bool, n_pixels: int, spp: int) -> dict:
-    """bytes that must LEAVE or ENTER an SM per frame, per kernel, from the instrumented (RH_FLAG_COUNT)
-    kernels' own counters.  Only global-memory records count: node records beyond the shared-memory-staged top levels
-    (64 B) and triangle records (80 B) — both counted once per warp instruction: lanes that read the same record share
-    one fetch —, winning shading records (128 B), texels (24 B), object records of sphere-tree
-    leaves when the object table is not staged (96 B), sample offsets, queue entries written and read (ray 64 B, hit
-    88 B, queued hit 92 B, + the point re-read per walked pair 32 B), accumulator updates (24 B).  The occluder, light and
-    material tables and the top tree levels live in shared memory and are not traffic."""
+    """per kernel and frame, from the instrumented (RH_FLAG_COUNT) kernels' own counters, two kinds of bytes.
+    `stream`: bytes that must cross HBM — sample offsets, queue entries written and read (ray 64 B, hit 88 B, queued
+    hit 92 B, + the point re-read per walked pair 32 B), accumulator updates (24 B): GBs per frame, read or written once.
+    `gather`: record fetches an SM issues — node records beyond the shared-memory-staged top levels (64 B) and triangle
+    records (80 B), both counted once per warp instruction (lanes reading the same record share one fetch), winning
+    shading records (128 B), texels (24 B), object records of sphere-tree leaves when the object table is not staged
+    (96 B).  Gathers are served by L1, L2 or HBM: of them only min(gather, the record set's size per launch) HAS to
+    cross HBM (`hbm_compulsory`, formed by the caller).  The occluder, light and material tables and the top tree
+    levels live in shared memory and are not traffic."""
     prim = 0 if tables_in_smem else 96
-    trace = (64 * st["node_visits_global"] + 80 * st["tri_records"] + prim * st["prim_tests"] + 128 * st["shade_fetches"]
-             + 24 * st["texel_fetches"] + offset_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 88 * st["shadow_tasks"])
-    classify = 88 * st["shadow_tasks"] + 92 * st["shadow_tasks_queued"] + 24 * (st["shadow_tasks"] - st["shadow_tasks_queued"])
-    walk = (92 * st["shadow_tasks_queued"] + 32 * st["shadow_walk_pairs"] + 24 * st["shadow_tasks_queued"]
-            + 64 * st["shadow_node_visits_global"] + 80 * st["shadow_tri_records"] + prim * st["shadow_prim_tests"])
-    resolve = (24 * spp + 3) * n_pixels
-    return {"trace": trace, "classify": classify, "walk": walk, "resolve": resolve}
+    out = {
+        "trace": {"stream": offset_bytes * st["rays_primary"] + 2 * 64 * st["queued_rays"] + 88 * st["shadow_tasks"],
+                  "gather": 64 * st["node_visits_global"] + 80 * st["tri_records"] + prim * st["prim_tests"] + 128 * st["shade_fetches"]
+                            + 24 * st["texel_fetches"]},
+        "classify": {"stream": 88 * st["shadow_tasks"] + 92 * st["shadow_tasks_queued"] + 24 * (st["shadow_tasks"] - st["shadow_tasks_queued"]),
+                     "gather": 0},
+        "walk": {"stream": 92 * st["shadow_tasks_queued"] + 32 * st["shadow_walk_pairs"] + 24 * st["shadow_tasks_queued"],
+                 "gather": 64 * st["shadow_node_visits_global"] + 80 * st["shadow_tri_records"] + prim * st["shadow_prim_tests"]},
+        "resolve": {"stream": (24 * spp + 3) * n_pixels, "gather": 0},
+    }
+    return out
 
 
 def compare_u8(a: np.ndarray, b: np.ndarray) -> dict:
@@ -462,6 +468,18 @@ def main():
         seeded = lambda: rh.render(job, spp=spp, seed=seed, out=rgb_host.numpy()).stats
         seeded()
         ms_seeded, _ = timed(seeded, args.steps)
+    # the floor of e2e: this step's offset bytes over PCIe with nothing else going on (all ranks copy at the same time,
+    # like in the step; on a piece of at most 2 GiB), from the same host buffer
+    up_bytes = int(stats_e2e[-1]["upload_bytes"])
+    piece = min(up_bytes, 2 << 30)
+    src_u8 = off_host.view(torch.uint8).reshape(-1)[:piece]
+    dst_u8 = torch.empty(piece, dtype=torch.uint8, device="cuda")
+    dst_u8.copy_(src_u8, non_blocking=True)
+    ms_copy, _ = timed(lambda: dst_u8.copy_(src_u8, non_blocking=True), 2)
+    h2d_alone = {"GBps_per_rank": piece / (ms_copy * 1e-3) / 1e9, "ms_for_this_step's_bytes": ms_copy * up_bytes / max(piece, 1),
+                 "pinned": bool(off_host.is_pinned()),
+                 "note": "cudaMemcpyAsync of the step's offset slice alone, all ranks at once: no schedule can bring e2e below this"}
+    del dst_u8
     clocks = sampler.stop() if rank == 0 else None
     rays = total_rays(stats[-1])
     value = rays / (ms_dev * 1e-3) / 1e6
@@ -485,8 +503,16 @@ def main():
     shadow_refill = bool(prof.get("shadow_split"))
     walk_kernel = "shadow_refill_kernel" if shadow_refill else "shadow_pooled_kernel"
     kernels_ms = {"trace_kernel": prof["ms_trace"], "classify_kernel+" + walk_kernel: prof["ms_shadow"], "resolve_kernel": prof["ms_resolve"]}
-    kernels_bytes = {"trace_kernel": ab["trace"], "classify_kernel+" + walk_kernel: ab["classify"] + ab["walk"], "resolve_kernel": ab["resolve"]}
     kernels_launches = {"trace_kernel": prof["trace_launches"], "classify_kernel+" + walk_kernel: prof["shadow_launches"], "resolve_kernel": 1}
+    rb = sc.record_bytes
+    record_set = {"trace_kernel": rb["nodes"] + rb["tris"] + rb["shade"] + rb["texels"], "classify_kernel+" + walk_kernel: rb["nodes"] + rb["tris"],
+                  "resolve_kernel": 0}
+    parts = {"trace_kernel": [ab["trace"]], "classify_kernel+" + walk_kernel: [ab["classify"], ab["walk"]], "resolve_kernel": [ab["resolve"]]}
+    kernels_stream = {k: sum(x["stream"] for x in v) for k, v in parts.items()}
+    kernels_gather = {k: sum(x["gather"] for x in v) for k, v in parts.items()}
+    # of the gathers only one pass over the record set per launch has to come from HBM (classify + walk: the walk launches)
+    walk_launches = {k: (n // 2 if "+" in k else n) for k, n in kernels_launches.items()}
+    kernels_bytes = {k: kernels_stream[k] + min(kernels_gather[k], max(1, walk_launches[k]) * record_set[k]) for k in kernels_ms}
     dom = max(kernels_ms, key=kernels_ms.get)
     dom_ms, dom_bytes, dom_n = kernels_ms[dom], kernels_bytes[dom], max(1, kernels_launches[dom])
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -523,14 +549,23 @@ def main():
                 "kernel_share_of_frame": dom_ms / max(prof["ms_total"], 1e-9),
                 "measured_under_ncu": measured,
                 "all_kernels": {k: {"ms_per_frame": kernels_ms[k], "algorithmic_GB_per_frame": kernels_bytes[k] / 1e9,
-                                    "GBps": kernels_bytes[k] / max(kernels_ms[k], 1e-9) / 1e6} for k in kernels_ms},
+                                    "GBps": kernels_bytes[k] / max(kernels_ms[k], 1e-9) / 1e6,
+                                    "stream_GB_per_frame": kernels_stream[k] / 1e9, "gather_requests_GB_per_frame": kernels_gather[k] / 1e9,
+                                    "gather_request_GBps": kernels_gather[k] / max(kernels_ms[k], 1e-9) / 1e6,
+                                    "record_set_GB": record_set[k] / 1e9} for k in kernels_ms},
                 "frame_check": {"algorithmic_GB_per_frame": all_bytes / 1e9, "GBps_over_the_step": all_bytes / (ms_dev * 1e-3) / 1e9,
                                 "below_peak": bool(all_bytes / (ms_dev * 1e-3) / 1e9 <= peaks["hbm_gbs"])},
                 "l2_stream_peak_GBps": stream_l2.value, "gather_peak_l2_resident_GBps": gather_l2.value,
                 "gather_peak_hbm_resident_GBps": gather_hbm.value,
-                "note": "algorithmic bytes = records that leave or enter an SM (queues, offsets, accumulators, triangle / shading records, "
-                        "node records beyond the shared-memory-staged top levels); the kernels are bound by instruction issue and "
-                        "dependent fp64 latency, not by memory — `frac` says how far below the HBM roofline that leaves them"}
+                "gather_request_frac_of_l2_gather_peak": kernels_gather[dom] / max(dom_ms, 1e-9) / 1e6 / max(gather_l2.value, 1e-9),
+                "note": "algorithmic bytes = what has to cross HBM: the streams (offsets, queue entries written and read, accumulator "
+                        "updates) + of the record gathers (nodes beyond the shared-memory-staged top levels, triangle / shading records, "
+                        "texels; counted once per warp instruction) at most one pass over the record set per launch; the gather requests "
+                        "themselves are served by L1 / L2 and are reported beside it (gather_request_GBps, against the measured random-gather "
+                        "rate of an L2-resident set).  " + (
+                            "The kernels are bound by instruction issue and dependent fp64 latency, not by memory — `frac` says how far below "
+                            "the HBM roofline that leaves them" if not c5 else
+                            "With 2.1 GB of records the walks are bound by the L1 / L2 gather path and by lane utilisation, not by HBM streaming")}
 
     # N > 1: the assembled frame must be the frame one GPU renders alone (SURVEY 8e parity gate); checked on rank 0
     # outside the timed region.  (c5 at full size: the 16 parity rows instead — one GPU alone needs ~20 s per frame.)
@@ -599,7 +634,7 @@ def main():
                 "data": wl["data"], "config": config_dict(wl, G, name), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(stats_e2e[-1]["upload_bytes"]), "d2h_bytes_per_step": int((H if G > 1 else rows) * W * 3),
-                        "note": e2e_note},
+                        "h2d_alone": h2d_alone, "note": e2e_note},
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
                 "rays_per_frame": rays, "frame_ms": ms_dev,
                 "rays_by_class_rank0": {k: int(st[k]) for k in ("rays_primary", "rays_reflect", "rays_probe", "rays_exit", "rays_shadow",

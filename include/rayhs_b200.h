@@ -312,6 +312,10 @@ void rh_scene_destroy(rh_scene* scene);
  * maps, lit-triangle flags), uploads}; info4 = {object / material / light tables staged in shared memory, occluder
  * tables staged, deepest tree, deep-stack entries per thread}.  Either pointer may be NULL. */
 int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4);
+/* Bytes of the scene's gathered records in HBM: bytes5 = {cull-tree nodes (float boxes), triangle records, shading
+ * records, texels, light-space tables (cube maps + lit flags)}.  bench.py bounds the HBM-compulsory share of the
+ * gathers with it (a record has to cross HBM at most once per launch while the set fits the L2). */
+int rh_scene_record_bytes(const rh_scene* scene, uint64_t* bytes5);
 
 /* Replaces `rayTrace` (RayHs.hs:161-166) / `distributedRayTrace` (RayHs.hs:190-195).
  * rgb_out: RGB8, row-major.  For shard_count == 1 it is width*height*3 bytes.

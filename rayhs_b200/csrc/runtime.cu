@@ -1568,6 +1568,16 @@ int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4) {
   return RH_OK;
 }
 
+int rh_scene_record_bytes(const rh_scene* scene, uint64_t* bytes5) {
+  if (!scene || !bytes5) return rh::set_error(RH_ERR_ARG, "rh_scene_record_bytes: null argument");
+  bytes5[0] = scene->wide32.bytes;
+  bytes5[1] = scene->tris.bytes;
+  bytes5[2] = scene->shade.bytes;
+  bytes5[3] = scene->texels.bytes;
+  bytes5[4] = scene->light_maps.bytes + scene->lit_flags.bytes;
+  return RH_OK;
+}
+
 int rh_render(const rh_scene* scene, const rh_camera* camera, const rh_render_opts* opts, uint8_t* rgb_out,
               int32_t* hit_ids_out, rh_stats* stats) {
   if (!g_dev) return rh::set_error(RH_ERR_STATE, "rh_render: call rh_init first");

@@ -99,6 +99,13 @@ class Scene:
         return list(ms), list(info)
 
     @property
+    def record_bytes(self) -> dict:
+        """Bytes of the gathered records in HBM (cull-tree nodes, triangle / shading records, texels, light-space tables)."""
+        b = (C.c_uint64 * 5)()
+        check(lib().rh_scene_record_bytes(self.device, b))
+        return dict(zip(("nodes", "tris", "shade", "texels", "light_tables"), (int(x) for x in b)))
+
+    @property
     def tables_in_smem(self) -> bool:
         return bool(self._info()[1][0])
 
