@@ -316,6 +316,11 @@ int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4);
  * records, texels, light-space tables (cube maps + lit flags)}.  bench.py bounds the HBM-compulsory share of the
  * gathers with it (a record has to cross HBM at most once per launch while the set fits the L2). */
 int rh_scene_record_bytes(const rh_scene* scene, uint64_t* bytes5);
+/* The light-space tables rh_scene_create built on the device, copied back (validation: tests compare them with the host
+ * builders rh_light_map_build / rh_lit_triangles).  info4 = {cube maps, cells per face edge, lit flags present (0/1),
+ * triangle slots}.  maps_out: maps * 6 * res * res floats; index_out: n_lights * 8 words (light * 8 + occluder mesh ->
+ * map or 0xFFFFFFFF); lit_out: one uint16 per triangle slot.  Any pointer may be NULL. */
+int rh_scene_light_tables(const rh_scene* scene, uint32_t* info4, float* maps_out, uint32_t* index_out, uint16_t* lit_out);
 
 /* Replaces `rayTrace` (RayHs.hs:161-166) / `distributedRayTrace` (RayHs.hs:190-195).
  * rgb_out: RGB8, row-major.  For shard_count == 1 it is width*height*3 bytes.

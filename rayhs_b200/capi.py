@@ -132,6 +132,7 @@ SIGNATURES = {
     "rh_scene_destroy": (None, [vp]),
     "rh_scene_info": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "rh_scene_record_bytes": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+    "rh_scene_light_tables": (C.c_int, [vp, C.POINTER(C.c_uint32), vp, vp, vp]),
     "rh_render": (C.c_int, [vp, C.POINTER(rh_camera), C.POINTER(rh_render_opts), vp, vp, C.POINTER(rh_stats)]),
     "rh_shard_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rh_default_band_height": (C.c_int, [C.c_int, C.c_int]),

@@ -17,10 +17,7 @@ bool build_light_map(const double L[3], const rh_tri* tris, const unsigned* slot
 // at L?  The query region K is the hull of T0 (widened a little) and L, minus the slab within 1e-8 of T0's plane: a
 // shadow ray from a point p of T0 starts 1e-6 along the unit light direction (rayEps, Geometry.hs:36) and only counts
 // hits at t >= 1e-6 (Mesh.hs:76), i.e. at least 2e-6 |cos| above the plane, and the query is only made for |cos| >= 0.01.
-struct LitQuery {
-  double n[4][3], d[4];  // K = { x : n[i].x + d[i] >= 0 for all i }
-  double lo[3], hi[3];   // bounding box of K
-};
+struct LitQuery;  // light_geom.h: K = { x : n[i].x + d[i] >= 0 for all i } with its bounding box
 bool lit_query_make(const rh_tri& t0, const double L[3], bool directional, LitQuery* q);  // false: grazing light or degenerate triangle
 // (directional: L is the light's vector, K the prism over T0 along it)
 bool lit_query_box_outside(const LitQuery& q, const double* lo, const double* hi);  // the box cannot meet K

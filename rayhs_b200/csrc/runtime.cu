@@ -29,6 +29,7 @@
 
 #include "common.h"
 #include "device_types.cuh"
+#include "light_geom.h"
 
 namespace rh {
 static thread_local std::string g_err;
@@ -163,6 +164,7 @@ struct rh_scene {
   mutable double tune_ns_per_pair[2] = {0, 0};
   // set-up times of rh_scene_create (milliseconds)
   double ms_trees = 0, ms_light_tables = 0, ms_upload = 0;
+  uint32_t n_light_maps = 0;     // cube maps in light_maps
   // Per-chunk kernel time of the last frame that streamed its sample offsets from the host (key: the chunk plan).
   // The next such frame processes its chunks in descending cost per sample, so that the uploads of the cheap chunks
   // hide behind the kernels of the expensive ones instead of the other way round.
@@ -181,6 +183,7 @@ namespace {
 // Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
 constexpr int kLightMapRes = 512;                       // cells per edge of a cube-map face (6.3 MB per map)
 constexpr size_t kLightMapBudget = (size_t)256 << 20;   // all maps of a scene; the resolution halves until they fit
+constexpr size_t kLitMaxQueriesDevice = 48000000;        // the same bound for the GPU builder (~0.05 us per query)
 constexpr size_t kLitMaxQueries = 1200000;              // (triangles x lights) of a mesh beyond which it gets no lit-triangle flags (host time: ~10 us per query)
 constexpr double kLightMapMinEmpty = 0.02;              // a map with fewer empty cells than this is not worth its lookups
 constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
@@ -869,7 +872,74 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
         std::vector<uint16_t> lit;
         uint32_t n_maps = 0;
         size_t n_lit = 0;
-        for (size_t m = 0; m < occ_meshes.size(); m++) {
+        // The tables are built on the GPU (setup_kernels.cu: the triangle records and the cull tree are already in
+        // HBM); RAYHS_B200_SETUP=host keeps the host builders of light_maps.cpp — same geometry code (light_geom.h),
+        // same tables bit for bit (tests/test_round2_gpu.py).
+        const char* env_setup = getenv("RAYHS_B200_SETUP");
+        const bool on_device = !(env_setup && strcmp(env_setup, "host") == 0);
+        std::vector<DevBuf> slot_bufs(on_device ? occ_meshes.size() : 0);
+        DevBuf words;
+        bool any_lit_query = false;
+        if (on_device) {
+          if ((rc = words.reserve(64))) return rc;
+          RH_CUDA(cudaMemsetAsync(words.p, 0, 64, D->stream));
+          if (n_pairs && (rc = S->light_maps.reserve(n_pairs * cells * sizeof(float)))) return rc;
+        }
+        for (size_t m = 0; on_device && m < occ_meshes.size(); m++) {
+          std::vector<uint32_t> slots, dfs{occ_meshes[m]};  // the mesh's triangles: leaves of its cull tree
+          while (!dfs.empty()) {
+            const WideNode& w = cull[dfs.back()];
+            dfs.pop_back();
+            for (int c = 0; c < 2; c++) {
+              if (w.child[c] == kEmpty) continue;
+              if (w.child[c] & kLeafBit)
+                for (uint32_t k = 0; k < (w.child[c] & kCountMask); k++) slots.push_back(w.first[c] + k);
+              else dfs.push_back(w.child[c]);
+            }
+          }
+          if (slots.empty()) continue;
+          if ((rc = upload(slot_bufs[m], slots.data(), slots.size()))) return rc;
+          const uint32_t* d_slots = (const uint32_t*)slot_bufs[m].p;
+          const bool want_lit = slots.size() * (size_t)d->n_lights <= kLitMaxQueriesDevice && !(env_lit && env_lit[0] == '0');
+          if (want_lit) {
+            if (!any_lit_query) {
+              const size_t lit_bytes = ((dtris.size() + 1) / 2) * 4;  // (whole 32-bit words: the kernel sets bits with atomicOr)
+              if ((rc = S->lit_flags.reserve(std::max<size_t>(lit_bytes, 256)))) return rc;
+              RH_CUDA(cudaMemsetAsync(S->lit_flags.p, 0, S->lit_flags.bytes, D->stream));
+              any_lit_query = true;
+            }
+            RH_CUDA((cudaError_t)device_lit_flags((const rh_tri*)S->tris.p, (const WideNode32*)S->wide32.p, center, occ_meshes[m], d_slots,
+                                                  (uint32_t)slots.size(), (const rh_light*)S->lights.p, d->n_lights, (uint32_t)m,
+                                                  (uint16_t*)S->lit_flags.p, (unsigned long long*)words.p + 2, D->stream));
+          }
+          for (uint32_t li = 0; li < d->n_lights; li++) {  // (the lit queries run on the GPU while the host waits for the maps' counts)
+            if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+            int useful = 0;
+            double empty = 0;
+            RH_CUDA((cudaError_t)device_light_map(d->lights[li].vec, (const rh_tri*)S->tris.p, d_slots, slots.size(), R,
+                                                  (float*)S->light_maps.p + (size_t)n_maps * cells, kLightMapMinEmpty,
+                                                  (unsigned long long*)words.p, &useful, &empty, D->stream));
+            if (useful) index[(size_t)li * kOccMeshes + m] = n_maps++;
+          }
+        }
+        if (on_device) {
+          unsigned long long flagged = 0;
+          RH_CUDA(cudaMemcpyAsync(&flagged, (unsigned long long*)words.p + 2, 8, cudaMemcpyDeviceToHost, D->stream));
+          RH_CUDA(cudaStreamSynchronize(D->stream));
+          for (DevBuf& b : slot_bufs) b.release();
+          words.release();
+          if (flagged) v.lit_flags = (const uint16_t*)S->lit_flags.p;
+          else S->lit_flags.release();
+          if (n_maps) {
+            if ((rc = upload(S->light_map_index, index.data(), index.size()))) return rc;
+            v.light_maps = (const float*)S->light_maps.p;
+            v.light_map_index = (const uint32_t*)S->light_map_index.p;
+            v.light_map_res = (uint32_t)R;
+          } else {
+            S->light_maps.release();
+          }
+        }
+        for (size_t m = 0; !on_device && m < occ_meshes.size(); m++) {
           std::vector<uint32_t> slots, dfs{occ_meshes[m]};  // the mesh's triangles: leaves of its cull tree
           while (!dfs.empty()) {
             const WideNode& w = cull[dfs.back()];
@@ -964,11 +1034,11 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
           if (lit_failed || maps_failed) throw std::bad_alloc();
           n_lit += lit_found;
         }
-        if (n_lit) {
+        if (!on_device && n_lit) {
           if ((rc = upload(S->lit_flags, lit.data(), lit.size()))) return rc;
           v.lit_flags = (const uint16_t*)S->lit_flags.p;
         }
-        if (n_maps) {
+        if (!on_device && n_maps) {
           if ((rc = upload(S->light_maps, maps.data(), maps.size()))) return rc;
           if ((rc = upload(S->light_map_index, index.data(), index.size()))) return rc;
           v.light_maps = (const float*)S->light_maps.p;
@@ -981,6 +1051,13 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
     }
   }
   S->ms_light_tables = ms_since(t_mark);
+  S->n_light_maps = 0;
+  if (v.light_map_index) {
+    std::vector<uint32_t> idx((size_t)d->n_lights * kOccMeshes);
+    RH_CUDA(cudaMemcpy(idx.data(), v.light_map_index, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t x : idx)
+      if (x != kEmpty) S->n_light_maps = std::max(S->n_light_maps, x + 1);
+  }
   v.wide = (const WideNode*)S->wide.p;
   v.wide32 = (const WideNode32*)S->wide32.p;
   v.abs_max = abs_max;
@@ -1565,6 +1642,25 @@ int rh_scene_info(const rh_scene* scene, double* setup_ms3, int32_t* info4) {
     info4[2] = (int32_t)scene->max_tree_depth;
     info4[3] = (int32_t)scene->deep_entries;
   }
+  return RH_OK;
+}
+
+int rh_scene_light_tables(const rh_scene* scene, uint32_t* info4, float* maps_out, uint32_t* index_out, uint16_t* lit_out) {
+  if (!scene) return rh::set_error(RH_ERR_ARG, "rh_scene_light_tables: null scene");
+  const SceneView& v = scene->view;
+  RH_CUDA(cudaSetDevice(scene->device->dev));
+  if (info4) {
+    info4[0] = scene->n_light_maps;
+    info4[1] = v.light_map_res;
+    info4[2] = v.lit_flags ? 1u : 0u;
+    info4[3] = v.n_tris;
+  }
+  if (maps_out && scene->n_light_maps)
+    RH_CUDA(cudaMemcpy(maps_out, v.light_maps, (size_t)scene->n_light_maps * 6 * v.light_map_res * v.light_map_res * sizeof(float),
+                       cudaMemcpyDeviceToHost));
+  if (index_out && v.light_map_index)
+    RH_CUDA(cudaMemcpy(index_out, v.light_map_index, (size_t)v.n_lights * kOccMeshes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (lit_out && v.lit_flags) RH_CUDA(cudaMemcpy(lit_out, v.lit_flags, (size_t)v.n_tris * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   return RH_OK;
 }
 

@@ -98,6 +98,20 @@ class Scene:
         check(lib().rh_scene_info(self.device, ms, info))
         return list(ms), list(info)
 
+    def light_tables(self) -> dict:
+        """The light-space tables rh_scene_create built (cube maps, their index, lit-triangle flags), copied back."""
+        import numpy as np
+
+        info = (C.c_uint32 * 4)()
+        check(lib().rh_scene_light_tables(self.device, info, None, None, None))
+        n_maps, res, has_lit, n_tris = (int(x) for x in info)
+        maps = np.empty((n_maps, 6, res, res), dtype=np.float32)
+        index = np.full((int(self.flat.contents.n_lights), 8), 0xFFFFFFFF, dtype=np.uint32)
+        lit = np.zeros(n_tris, dtype=np.uint16)
+        check(lib().rh_scene_light_tables(self.device, info, maps.ctypes.data if n_maps else None, index.ctypes.data if n_maps else None,
+                                          lit.ctypes.data if has_lit else None))
+        return {"maps": maps, "index": index, "lit": lit if has_lit else None, "res": res}
+
     @property
     def record_bytes(self) -> dict:
         """Bytes of the gathered records in HBM (cull-tree nodes, triangle / shading records, texels, light-space tables)."""

@@ -54,3 +54,32 @@ def test_a_shard_of_single_row_bands_picks_arbitrary_rows():
     ys = np.arange(r0, h, step)
     assert np.array_equal(rgb.cpu().numpy()[:len(ys)], full.pixels[ys])
     assert np.array_equal(ids.cpu().numpy().reshape(rows, w, spp, 2)[:len(ys)], full.hit_ids.reshape(h, w, spp, 2)[ys])
+
+
+@pytest.mark.parametrize("name", ["dragon_low", "dragon_full", "transform", "cornellBox"])
+def test_device_built_light_tables_equal_the_host_built_ones(name, monkeypatch):
+    """rh_scene_create builds the cube maps and the lit-triangle flags with CUDA kernels (setup_kernels.cu); the host
+    builders of light_maps.cpp (RAYHS_B200_SETUP=host) run the same geometry code (light_geom.h) and must produce the
+    same tables bit for bit — the host builders are what tests/test_light_maps.py checks against brute force."""
+    import os
+
+    from tests.util import GOLDEN
+
+    path = os.path.join(GOLDEN, name + ".pack")
+    monkeypatch.delenv("RAYHS_B200_SETUP", raising=False)
+    dev = rh.Scene.from_pack(path)
+    t_dev = dev.light_tables()
+    monkeypatch.setenv("RAYHS_B200_SETUP", "host")
+    host = rh.Scene.from_pack(path)
+    t_host = host.light_tables()
+    assert t_dev["res"] == t_host["res"]
+    assert np.array_equal(t_dev["index"], t_host["index"])
+    assert t_dev["maps"].shape == t_host["maps"].shape
+    assert np.array_equal(t_dev["maps"].view(np.uint32), t_host["maps"].view(np.uint32))
+    assert (t_dev["lit"] is None) == (t_host["lit"] is None)
+    if t_dev["lit"] is not None:
+        assert np.array_equal(t_dev["lit"], t_host["lit"])
+        if name.startswith("dragon"):
+            assert (t_dev["lit"] & 0x0fff).astype(bool).mean() > 0.3   # the flags are not trivially empty
+    dev.close()
+    host.close()
