@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--tris", type=int, default=0)
+    ap.add_argument("--band-height", type=int, default=0, help="rows per interleaved band at N > 1 (default: the library's choice)")
     args = ap.parse_args()
     name = args.workload
     wl = dict(WORKLOADS[name])
@@ -343,7 +344,7 @@ def main():
                      "KDTree.hs:68-90 build + flattening a Haskell host would do); rh_scene_create = the library's own set-up"}
     job = rh.renderingFromScene(sc, W, H)
     G = world
-    bh = L.rh_default_band_height(H, G)
+    bh = args.band_height or L.rh_default_band_height(H, G)
     rows = L.rh_shard_rows(H, G, bh)
     row_samples = W * spp
     c5 = name != "c4"

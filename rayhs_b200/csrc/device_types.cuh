@@ -53,7 +53,14 @@ constexpr int kMaxPeers = 16;
 #ifndef RH_TMA_STAGE
 #define RH_TMA_STAGE 0  // trace kernel: the next batch's sample offsets (1) or also the next batch of queued rays (2) arrive by a bulk async copy (cp.async.bulk + mbarrier) while the current batch is traced; 0 = plain loads.  Measured on the bench frame: 0 = 41.3 ms, 1 = 42.4 ms, 2 = 42.8 ms — the loads it replaces are one coalesced LDG.128 per lane whose latency the other warps of the SM already hide, while the tile, the mbarrier handshake and the shared memory taken from L1 cost more than they save: off by default
 #endif
-constexpr int kTraceBlock = RH_TRACE_BLOCK;    // one block per SM, tables staged once per SM
+#ifndef RH_TRACE_PER_SM
+#define RH_TRACE_PER_SM 1   // resident blocks per SM of the trace kernel (block size x this = threads per SM)
+#endif
+#ifndef RH_SHADOW_PER_SM
+#define RH_SHADOW_PER_SM 1  // ... of the pooled shadow kernel
+#endif
+constexpr int kTracePerSm = RH_TRACE_PER_SM, kShadowPerSm = RH_SHADOW_PER_SM;
+constexpr int kTraceBlock = RH_TRACE_BLOCK;    // tables staged once per block
 constexpr int kShadowBlock = RH_SHADOW_BLOCK;
 constexpr int kWalkBlock = RH_WALK_BLOCK;
 
@@ -159,16 +166,20 @@ struct CameraParams {
 // Per-chunk control block in device memory (zeroed before each chunk).
 struct ChunkCtl {
   uint32_t ray_slabs[kMaxPasses + 2];     // slabs reserved in the ray queue that pass k consumes
-  uint32_t hit_slabs[kMaxPasses + 2];     // slabs of shaded Diffuse / Plastic hits produced by pass k (hit queue)
+  // The hit queue is filled front to back by ALL passes of a chunk (one running slab counter): pass k's shaded hits are
+  // the slabs [hit_start[k], hit_start[k + 1]), so that pass k + 1's trace kernel can append while pass k's hits are
+  // still being classified on the other stream.  hit_start[k + 1] is written when pass k's trace kernel has ended.
+  uint32_t hit_start[kMaxPasses + 3];
   uint32_t shadow_slabs[kMaxPasses + 2];  // slabs of hits whose shadow rays have to walk a tree (walk queue)
-  uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors, in slabs
+  uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors, in claim units
   uint32_t hit_cursor[kMaxPasses + 2];
   uint32_t shadow_cursor[kMaxPasses + 2];
   uint32_t ray_items[kMaxPasses + 2];     // entries in those slabs (statistics; one atomic per warp per launch)
   uint32_t hit_items[kMaxPasses + 2];
   uint32_t shadow_items[kMaxPasses + 2];
   uint32_t overflow;
-  uint32_t pad_[3];
+  uint32_t hit_slab_next;                 // the hit queue's slab counter
+  uint32_t pad_[1];
 };
 
 // Frame-level counters (zeroed per rh_render).
@@ -186,6 +197,15 @@ struct FrameCounters {
   unsigned long long max_closest_nodes;
   unsigned long long deep_pushes;    // RH_FLAG_COUNT: stack entries that went beyond the shared-memory short stack
   KernelCounters k[2];  // 0 = trace_kernel, 1 = shadow kernels
+  // RH_FLAG_COUNT: shadow walks by floor(log2(node records visited + 1)), per pass (last row: passes >= 3), and the nodes they visited
+  unsigned long long walk_hist[4][20], walk_hist_nodes[4][20];
+#ifdef RH_WARP_TIMES
+  // diagnostic build (-DRH_WARP_TIMES): per warp of the pooled shadow kernel and pass (row 3: passes >= 3): the low 32 bits of its first
+  // and last globaltimer reading (ns), batches of 32 hits it processed, walk rounds it ran
+  unsigned int warp_begin[4][4096], warp_end[4][4096], warp_batches[4][4096], warp_rounds[4][4096];
+  // ... ns inside the walk rounds, and over its rounds the sums of the longest lane's node steps / triangle tests
+  unsigned int warp_walk_ns[4][4096], warp_max_nodes[4][4096], warp_max_tris[4][4096], warp_pairs[4][4096];
+#endif
 };
 
 // Queues are arrays of slabs of kSlab entries; slab s holds fill[s] <= kSlab valid entries at [s * kSlab ..).  A warp
@@ -247,6 +267,7 @@ struct ChunkParams {
 };
 
 // Launchers (kernels.cu).  `count` selects the instrumented instantiation (box/tri counters).
+// (followed by a one-thread kernel that closes the pass's range of the hit queue, ChunkCtl::hit_start)
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
 // classify_kernel, then the walks of the hits it queued — refill: the per-lane-refill kernel (incoherent rays) instead of
 // the pooled one (coherent rays).  Returns the number of launches.

@@ -250,10 +250,21 @@ struct Cnt {
 };
 template <>
 struct Cnt<false> {
+#ifdef RH_WARP_TIMES
+  unsigned dn, dt;  // diagnostic build: node steps and triangle tests of this lane
+  __device__ __forceinline__ void zero() { dn = dt = 0; }
+#else
   __device__ __forceinline__ void zero() {}
+#endif
 };
 #define RH_CNT(field, n) \
   if constexpr (COUNT) cnt.field += (n)
+#ifdef RH_WARP_TIMES
+#define RH_DBG(field) \
+  if constexpr (!COUNT) cnt.field += 1
+#else
+#define RH_DBG(field)
+#endif
 
 template <bool COUNT>
 __device__ __forceinline__ void flush_counters(Cnt<COUNT>& cnt, FrameCounters* fc, int which) {
@@ -463,6 +474,7 @@ __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint3
     const double2 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
     const double e2z = __ldg((const double*)(tp + 4));
     RH_CNT(tri, 1);
+    RH_DBG(dt);
     if constexpr (COUNT) {
       const unsigned peers = __match_any_sync(__activemask(), slot);
       if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) cnt.wtri += 1;  // triangle records fetched (once per warp instruction)
@@ -522,6 +534,7 @@ __device__ __forceinline__ bool node_step(const Ctx& cx, uint32_t& ref, const Ra
   const float4 b0 = np[0], b1 = np[1], b2 = np[2];
   const uint2 cw = *(const uint2*)(np + 3);  // child0, child1
   RH_CNT(nodes, 1);
+  RH_DBG(dn);
   if constexpr (COUNT) {
     // records read from global memory (not the staged top levels), counted once per warp instruction: lanes that
     // visit the same node share one fetch
@@ -918,26 +931,45 @@ __device__ __forceinline__ void slab_close(const SlabWriter& w, uint32_t lane, u
   }
 }
 
-// Work claim of a persistent warp: consecutive batches of 32 work items (kSlab / 32 per slab).  Guided self-scheduling:
-// whole slabs (one atomic per 128 items) while plenty of work is left, single batches near the end of the queue and for
-// small launches, so that no warp ends up with a long tail — the secondary passes are short launches whose duration
-// is set by their slowest warp.  Returns (first batch, number of batches); first >= n_batches: nothing left.
-constexpr uint32_t kSlabBatches = kSlab / 32;
+// Work claim of a persistent warp: consecutive UNITS of kUnit work items (kSlab / kUnit per slab).  Guided
+// self-scheduling: whole slabs (one atomic per 128 items) while plenty of work is left, then whole 32-item groups, and
+// single units near the end of the queue and in small launches.  The secondary passes are short launches whose duration
+// is set by their slowest warp, and a lone warp is latency-bound: its lanes walk in lock-step (a round lasts as long as
+// its longest walk, ~1 us per node step with nothing to hide the loads behind), so near the end it is faster to spread
+// 32 items over four warps with 8 lanes each than to give them to one (measured per warp with -DRH_WARP_TIMES: on one
+// eighth of the bench frame the last percent of the warps ran 2-3x longer than the median with 32-item claims).
+// Returns (first unit, number of units); first >= n_units: nothing left.
+#ifndef RH_CLAIM_UNIT
+#define RH_CLAIM_UNIT 8
+#endif
+constexpr uint32_t kUnit = RH_CLAIM_UNIT;
+constexpr uint32_t kSlabUnits = kSlab / kUnit, kGroupUnits = 32 / kUnit;
+static_assert(kUnit >= 1 && kUnit <= 32 && 32 % kUnit == 0, "a claim unit divides a warp's 32 lanes");
 // `seen`: where the cursor stood after this warp's previous claim (a lower bound of where it stands now; before the
 // first claim: as if every warp ahead of this one had taken a slab) — the estimate of the work left costs no extra
 // round trip to the cursor's cache line.
-__device__ __forceinline__ uint2 claim_batches(uint32_t* cursor, uint32_t n_batches, uint32_t total_warps, uint32_t lane,
-                                               uint32_t& seen) {
+__device__ __forceinline__ uint2 claim_units(uint32_t* cursor, uint32_t n_units, uint32_t total_warps, uint32_t lane, uint32_t& seen) {
   uint2 c = make_uint2(0, 1);
   if (lane == 0) {
-    const uint32_t left = seen < n_batches ? n_batches - seen : 0;
-    c.y = min(kSlabBatches, max(1u, left / (2u * total_warps)));
+    const uint32_t left = seen < n_units ? n_units - seen : 0;
+    uint32_t want = min(kSlabUnits, max(1u, left / (2u * total_warps)));
+    if (want >= kGroupUnits) want -= want % kGroupUnits;  // whole 32-item groups
+    c.y = want;
     c.x = atomicAdd(cursor, c.y);
   }
   c.x = __shfl_sync(kFull, c.x, 0);
   c.y = __shfl_sync(kFull, c.y, 0);
   seen = c.x + c.y;
   return c;
+}
+// The next piece of a claim [u, end): at most 32 consecutive items of one slab.  Returns the slab, the first item's
+// offset in it and the number of items, and advances u.
+__device__ __forceinline__ void next_piece(uint32_t& u, uint32_t end, uint32_t& slab, uint32_t& off, uint32_t& n) {
+  slab = u / kSlabUnits;
+  const uint32_t uo = u % kSlabUnits, nu = min(min(end - u, kGroupUnits), kSlabUnits - uo);
+  off = uo * kUnit;
+  n = nu * kUnit;
+  u += nu;
 }
 
 __device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint64_t bits, const RayQueue& q, SlabWriter& sw,
@@ -954,6 +986,9 @@ __device__ __forceinline__ void push_ray(bool has, const Ray& r, double w, uint6
   }
 }
 
+// `walk` word of a hit-queue entry: the hit triangle's lit flags (16 bits), or kHitDirect: the entry's colour is a finished
+// term (Emmit / ShowNormal / ShowUV) that is added as it is
+constexpr uint32_t kHitDirect = 0x80000000u;
 struct ShadowTask {
   V3 p, n, cd;
   double w;
@@ -1445,7 +1480,7 @@ static_assert(((size_t)kShortStack * kTraceBlock * sizeof(uint2)) % 128 == 0, "s
 static_assert(kTraceSmem <= 227 * 1024, "trace kernel shared memory");
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_constant__ SceneView S,
+__global__ void __launch_bounds__(kTraceBlock, kTracePerSm) trace_kernel(const __grid_constant__ SceneView S,
                                                                const __grid_constant__ CameraParams cam,
                                                                const __grid_constant__ ChunkParams P) {
   SmemTables& sm = *reinterpret_cast<SmemTables*>(rh_smem);
@@ -1474,18 +1509,20 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
 #endif
   __syncwarp();
 
-  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kTraceBlock / 32);
-  uint32_t cursor_seen = (blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * kSlabBatches;  // as if every warp ahead had claimed a slab
+  const uint32_t n_units = n_slabs * kSlabUnits, total_warps = gridDim.x * (kTraceBlock / 32);
+  uint32_t cursor_seen = (blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * kSlabUnits;  // as if every warp ahead had claimed a slab
   for (;;) {
-    const uint2 claim = claim_batches(&ctl->trace_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
-    if (claim.x >= n_batches) break;
-    const uint32_t claim_end = min(claim.x + claim.y, n_batches);
-    for (uint32_t bi = claim.x; bi < claim_end; bi++) {
-      const uint32_t slab = bi / kSlabBatches, b = (bi % kSlabBatches) * 32, slab_first = slab * kSlab;
+    const uint2 claim = claim_units(&ctl->trace_cursor[P.pass], n_units, total_warps, lane, cursor_seen);
+    if (claim.x >= n_units) break;
+    const uint32_t claim_end = min(claim.x + claim.y, n_units);
+    for (uint32_t u = claim.x; u < claim_end;) {
+      uint32_t slab, b, piece_n;
+      next_piece(u, claim_end, slab, b, piece_n);
+      const uint32_t slab_first = slab * kSlab;
       const uint32_t count = primary ? min(kSlab, P.n_samples - slab_first) : min(__ldg(P.q_in.fill + slab), kSlab);
       if (b >= count) continue;
       const uint32_t item = slab_first + b + lane;
-      bool valid = b + lane < count;
+      bool valid = lane < piece_n && b + lane < count;
       Ray r;
       double w = 1;
       uint32_t sample = item, probe_mat = 0;
@@ -1504,7 +1541,7 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
       // the tile is in registers now: ask for the next batch of this claim (same slab); it lands while this one is traced
       __syncwarp();
       staged.first = kEmpty;
-      if (b + 32 < count && bi + 1 < claim_end) {
+      if (piece_n == 32 && b + 32 < count && u < claim_end && u % kSlabUnits != 0) {
         uint32_t ok = 0;
         const uint32_t dep = (uint32_t)(__double2loint(r.o.x) ^ __double2loint(r.d.x) ^ __double2loint(w));
         if (lane == 0) ok = stage_start(P, primary, slab_first + b + 32, min(32u, count - b - 32), &wsm.tile, &wsm.bar, dep) ? 1u : 0u;
@@ -1631,16 +1668,13 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
         }
         push_ray(has, rb, wb, bits, P.q_out, out_rays, &ctl->ray_slabs[P.pass + 1], &ctl->overflow, lane);
       }
-      // local terms that need no light
-      if (surface) {
-        if (mkind == RH_MAT_EMMIT) accumulate(P, sample, w, ld3(cx.materials[mat_index].color1));
-        else if (mkind == RH_MAT_SHOWNORMAL) accumulate(P, sample, w, n);
-        else if (mkind == RH_MAT_SHOWUV) accumulate(P, sample, w, mk(tu, tv, 0));
-      }
-      // Diffuse / Plastic: ambient + accumDiffuse (RayHs.hs:111-119) — the hit goes to the hit queue with its colour;
-      // classify_kernel folds its lights
+      // Local terms that need no light (Emmit, ShowNormal, ShowUV: RayHs.hs:121-128) and Diffuse / Plastic hits, whose
+      // ambient + accumDiffuse terms (RayHs.hs:111-119) classify_kernel folds: both go to the hit queue.  Every add to a
+      // sample's accumulator is made by the shadow kernels, pass after pass, so the order of a sample's terms does not
+      // depend on how far the next pass's trace kernel — which runs on its own stream — has got.
       {
         const bool lit_surface = surface && (mkind == RH_MAT_DIFFUSE || mkind == RH_MAT_PLASTIC);
+        const bool direct = surface && (mkind == RH_MAT_EMMIT || mkind == RH_MAT_SHOWNORMAL || mkind == RH_MAT_SHOWUV);
         ShadowTask task;
         if (lit_surface) {
           n_shaded++;
@@ -1652,8 +1686,16 @@ __global__ void __launch_bounds__(kTraceBlock, 1) trace_kernel(const __grid_cons
           // lit-triangle flags of the hit triangle (light_maps.cpp) travel in the `walk` word of the hit queue
           task.walk = (okind == RH_OBJ_MESH && S.lit_flags && !P.no_light_maps) ? (uint32_t)__ldg(S.lit_flags + best.slot) : 0u;
           task.settled = 0;
+        } else if (direct) {
+          task.p = p;
+          task.n = n;
+          task.cd = mkind == RH_MAT_EMMIT ? ld3(cx.materials[mat_index].color1) : (mkind == RH_MAT_SHOWNORMAL ? n : mk(tu, tv, 0));
+          task.w = w;
+          task.sample = sample;
+          task.walk = kHitDirect;
+          task.settled = 0;
         }
-        push_shadow(lit_surface, task, P.q_hits, out_shadow, &ctl->hit_slabs[P.pass], &ctl->overflow, lane);
+        push_shadow(lit_surface || direct, task, P.q_hits, out_shadow, &ctl->hit_slab_next, &ctl->overflow, lane);
       }
     }
   }
@@ -1702,22 +1744,25 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
   Cnt<COUNT> cnt;
   cnt.zero();
   ChunkCtl* ctl = P.ctl;
-  const uint32_t n_slabs = min(ctl->hit_slabs[P.pass], P.q_hits.capacity / kSlab);
+  const uint32_t slab0 = min(ctl->hit_start[P.pass], P.q_hits.capacity / kSlab);  // this pass's slabs of the hit queue
+  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1], P.q_hits.capacity / kSlab) - slab0;
   const size_t cap = P.q_hits.capacity;
   const double2* qp = P.q_hits.plane;
   uint32_t n_culled = 0, n_walk_pairs = 0;
-  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kClassifyBlock / 32);
-  uint32_t cursor_seen = (blockIdx.x * (kClassifyBlock / 32) + (threadIdx.x >> 5)) * kSlabBatches;
+  const uint32_t n_units = n_slabs * kSlabUnits, total_warps = gridDim.x * (kClassifyBlock / 32);
+  uint32_t cursor_seen = (blockIdx.x * (kClassifyBlock / 32) + (threadIdx.x >> 5)) * kSlabUnits;
   for (;;) {
-    const uint2 claim = claim_batches(&ctl->hit_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
-    if (claim.x >= n_batches) break;
-    const uint32_t claim_end = min(claim.x + claim.y, n_batches);
-    for (uint32_t bi = claim.x; bi < claim_end; bi++) {
-      const uint32_t slab = bi / kSlabBatches, b = (bi % kSlabBatches) * 32;
+    const uint2 claim = claim_units(&ctl->hit_cursor[P.pass], n_units, total_warps, lane, cursor_seen);
+    if (claim.x >= n_units) break;
+    const uint32_t claim_end = min(claim.x + claim.y, n_units);
+    for (uint32_t u = claim.x; u < claim_end;) {
+      uint32_t slab, b, piece_n;
+      next_piece(u, claim_end, slab, b, piece_n);
+      slab += slab0;
       const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
       if (b >= n_here) continue;
       const uint32_t item = slab * kSlab + b + lane;
-      const bool valid = b + lane < n_here;
+      const bool valid = lane < piece_n && b + lane < n_here;
       ShadowTask task;
       bool queue = false;
       if (valid) {
@@ -1728,7 +1773,13 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
         task.n = mk(bq.y, c.x, c.y);
         task.cd = mk(d.x, d.y, e.x);
         task.w = e.y;
-        const LightFold F = fold_lights<COUNT, FAST>(sm, cx, P, task.p, task.n, task.cd, lit, cnt);
+        LightFold F;
+        if (lit & kHitDirect) {
+          F.walk = F.settled = F.culled = 0;
+          F.acc = task.cd;
+        } else {
+          F = fold_lights<COUNT, FAST>(sm, cx, P, task.p, task.n, task.cd, lit, cnt);
+        }
         n_culled += F.culled;
         if (F.walk) {
           queue = true;
@@ -1786,7 +1837,13 @@ __device__ __forceinline__ bool walk_pair(const Ctx& cx, const ChunkParams& P, c
     hit = exact ? traverse_exact<COUNT, AnyHit, true>(cx, S.sphere_root, r, bound, sink, st, cnt, true)
                 : traverse<COUNT, AnyHit, true>(cx, S.sphere_root, r, f, bound, sink, st, cnt, true);
   }
-  if constexpr (COUNT) atomicMax(&P.counters->max_walk_nodes, cnt.nodes - nodes_before);
+  if constexpr (COUNT) {
+    const unsigned long long nv = cnt.nodes - nodes_before;
+    atomicMax(&P.counters->max_walk_nodes, nv);
+    const int bin = min(19, 63 - __clzll((long long)(nv + 1))), row = min(P.pass, 3);
+    atomicAdd(&P.counters->walk_hist[row][bin], 1ull);
+    atomicAdd(&P.counters->walk_hist_nodes[row][bin], nv);
+  }
   return hit;
 }
 
@@ -1811,7 +1868,7 @@ constexpr size_t kShadowSmem = sizeof(WalkTables) + (kShadowBlock / 32) * sizeof
 static_assert(kShadowSmem <= 227 * 1024, "pooled shadow kernel shared memory");
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __grid_constant__ SceneView S,
+__global__ void __launch_bounds__(kShadowBlock, kShadowPerSm) shadow_pooled_kernel(const __grid_constant__ SceneView S,
                                                                         const __grid_constant__ ChunkParams P) {
   WalkTables& sm = *reinterpret_cast<WalkTables*>(rh_smem);
   Ctx cx;
@@ -1828,24 +1885,32 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __
   const size_t cap = P.q_shadow.capacity;
   const double2* qp = P.q_shadow.plane;
 
-  const uint32_t n_batches = n_slabs * kSlabBatches, total_warps = gridDim.x * (kShadowBlock / 32);
-  uint32_t seg_next = 0, seg_end = 0;  // the warp's claimed batches not yet processed
-  uint32_t cursor_seen = (blockIdx.x * (kShadowBlock / 32) + warp) * kSlabBatches;
+  const uint32_t n_units = n_slabs * kSlabUnits, total_warps = gridDim.x * (kShadowBlock / 32);
+  uint32_t seg_next = 0, seg_end = 0;  // the warp's claimed units not yet processed
+  uint32_t cursor_seen = (blockIdx.x * (kShadowBlock / 32) + warp) * kSlabUnits;
+#ifdef RH_WARP_TIMES
+  unsigned long long dbg_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  uint32_t dbg_batches = 0, dbg_rounds = 0, dbg_walk_ns = 0, dbg_max_nodes = 0, dbg_max_tris = 0, dbg_pairs = 0;
+#endif
   for (;;) {
     // a whole slab per claim while plenty of work is left (full pools), smaller pieces near the end of the queue
     if (seg_next == seg_end) {
-      const uint2 claim = claim_batches(&ctl->shadow_cursor[P.pass], n_batches, total_warps, lane, cursor_seen);
-      if (claim.x >= n_batches) break;
+      const uint2 claim = claim_units(&ctl->shadow_cursor[P.pass], n_units, total_warps, lane, cursor_seen);
+      if (claim.x >= n_units) break;
       seg_next = claim.x;
-      seg_end = min(claim.x + claim.y, n_batches);
+      seg_end = min(claim.x + claim.y, n_units);
     }
     // the part of the claim that lies in one slab
-    const uint32_t slab = seg_next / kSlabBatches, b_first = seg_next % kSlabBatches;
-    const uint32_t b_count = min(seg_end - seg_next, kSlabBatches - b_first);
-    seg_next += b_count;
+    const uint32_t slab = seg_next / kSlabUnits, u_first = seg_next % kSlabUnits;
+    const uint32_t u_count = min(seg_end - seg_next, kSlabUnits - u_first);
+    seg_next += u_count;
     const uint32_t fill = min(__ldg(P.q_shadow.fill + slab), kSlab);
-    if (b_first * 32 >= fill) continue;
-    const uint32_t base = slab * kSlab + b_first * 32, n_here = min(fill - b_first * 32, b_count * 32);
+    if (u_first * kUnit >= fill) continue;
+    const uint32_t base = slab * kSlab + u_first * kUnit, n_here = min(fill - u_first * kUnit, u_count * kUnit);
+#ifdef RH_WARP_TIMES
+    dbg_batches += (n_here + 31) / 32;
+#endif
     uint32_t wm[kShadowT];
 #pragma unroll
     for (int t = 0; t < kShadowT; t++) {
@@ -1871,11 +1936,41 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __
       // ---- phase 2: tree walks in full rounds; the last light also drains the remainder
       const bool last = (li + 1 == n_lights);
       const uint32_t n_full = last ? pool_n : (pool_n & ~31u);
+#ifdef RH_WARP_TIMES
+      dbg_rounds += (n_full + 31) / 32;
+      dbg_pairs += n_full;
+      unsigned long long dbg_w0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_w0));
+#endif
       for (uint32_t i = lane; i < n_full; i += 32) {
         const uint32_t e = ws.pool[i], j = e & 0xff, lw = e >> 8;
         const double2 a = qp[base + j], b = qp[cap + base + j];
+#ifdef RH_WARP_TIMES
+        unsigned dn0 = 0, dt0 = 0;
+        if constexpr (!COUNT) { dn0 = cnt.dn; dt0 = cnt.dt; }
+#endif
         if (walk_pair<COUNT>(cx, P, mesh_roots, n_meshes, cx.lights[lw], mk(a.x, a.y, b.x), st, cnt)) atomicOr(&ws.vis[j], 1u << lw);
+#ifdef RH_WARP_TIMES
+        if constexpr (!COUNT) {
+          unsigned dn1 = cnt.dn - dn0, dt1 = cnt.dt - dt0;
+          const unsigned act = __activemask();
+          for (int o = 16; o; o >>= 1) {
+            dn1 = max(dn1, __shfl_xor_sync(act, dn1, o));
+            dt1 = max(dt1, __shfl_xor_sync(act, dt1, o));
+          }
+          dbg_max_nodes += dn1;
+          dbg_max_tris += dt1;
+        }
+#endif
       }
+#ifdef RH_WARP_TIMES
+      __syncwarp();
+      {
+        unsigned long long dbg_w1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_w1));
+        dbg_walk_ns += (uint32_t)(dbg_w1 - dbg_w0);
+      }
+#endif
       __syncwarp();
       const uint32_t rem = pool_n - n_full;
       uint16_t keep = 0;
@@ -1900,6 +1995,23 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_pooled_kernel(const __
     }
     __syncwarp();
   }
+#ifdef RH_WARP_TIMES
+  {
+    const uint32_t wi = blockIdx.x * (kShadowBlock / 32) + warp, row = min(P.pass, 3);
+    if (lane == 0 && wi < 4096) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      P.counters->warp_begin[row][wi] = (unsigned int)dbg_t0;
+      P.counters->warp_end[row][wi] = (unsigned int)t1 | 1u;
+      P.counters->warp_batches[row][wi] = dbg_batches;
+      P.counters->warp_rounds[row][wi] = dbg_rounds;
+      P.counters->warp_walk_ns[row][wi] = dbg_walk_ns;
+      P.counters->warp_max_nodes[row][wi] = dbg_max_nodes;
+      P.counters->warp_max_tris[row][wi] = dbg_max_tris;
+      P.counters->warp_pairs[row][wi] = dbg_pairs;
+    }
+  }
+#endif
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
 
@@ -2080,7 +2192,8 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
   cnt.zero();
   const uint32_t lane = threadIdx.x & 31;
   ChunkCtl* ctl = P.ctl;
-  const uint32_t n_slabs = min(ctl->hit_slabs[P.pass], P.q_hits.capacity / kSlab);
+  const uint32_t slab0 = min(ctl->hit_start[P.pass], P.q_hits.capacity / kSlab);  // this pass's slabs of the hit queue
+  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1], P.q_hits.capacity / kSlab) - slab0;
   const size_t cap = P.q_hits.capacity;
   unsigned long long n_culled = 0;
   for (;;) {
@@ -2088,6 +2201,7 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
     if (lane == 0) slab = atomicAdd(&ctl->hit_cursor[P.pass], 1u);
     slab = __shfl_sync(kFull, slab, 0);
     if (slab >= n_slabs) break;
+    slab += slab0;
     const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
     for (uint32_t j = lane; j < n_here; j += 32) {
       const uint32_t item = slab * kSlab + j;
@@ -2096,6 +2210,10 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
       const uint32_t sbits = P.q_hits.sample[item];
       const V3 p = mk(a.x, a.y, b.x), n = mk(b.y, c.x, c.y), cd = mk(d.x, d.y, e.x);
       const double w = e.y;
+      if (P.q_hits.walk[item] & kHitDirect) {  // a finished term (Emmit / ShowNormal / ShowUV)
+        accumulate(P, sbits & 0x7fffffffu, w, cd);
+        continue;
+      }
       const bool cd_finite = isfinite(cd.x) && isfinite(cd.y) && isfinite(cd.z);
       V3 acc = mk(0, 0, 0);  // foldl ... black lts
       for (uint32_t li = 0; li < S.n_lights; li++) {
@@ -2121,6 +2239,9 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
   if (lane == 0 && n_culled) atomicAdd(&P.counters->shadow_culled, n_culled);
   flush_counters<COUNT>(cnt, P.counters, 1);
 }
+
+// After pass k's trace kernel: its shaded hits are the slabs [hit_start[k], hit_start[k + 1]) of the hit queue.
+__global__ void close_hit_range_kernel(ChunkCtl* ctl, int pass) { ctl->hit_start[pass + 1] = ctl->hit_slab_next; }
 
 // ------------------------------------------------------------------ K6: average + toIntC (RayHs.hs:169-171, Image.hs:54-55)
 __device__ __forceinline__ int to_int_c(double c, bool& negative) {
@@ -2317,14 +2438,15 @@ int configure_kernels() {
   return (int)e;
 }
 int max_threads_per_launch(int n_sms) {
-  const int b = kTraceBlock > kShadowBlock ? (kTraceBlock > kWalkBlock ? kTraceBlock : kWalkBlock)
-                                           : (kShadowBlock > kWalkBlock ? kShadowBlock : kWalkBlock);
-  return n_sms * b;  // every traversal kernel runs one block per SM
+  const int t = kTraceBlock * kTracePerSm, s = kShadowBlock * (kShadowPerSm > 1 ? kShadowPerSm : 1);  // (the simple kernel: one block)
+  const int b = t > s ? (t > kWalkBlock ? t : kWalkBlock) : (s > kWalkBlock ? s : kWalkBlock);
+  return n_sms * b;  // threads per SM of the largest traversal kernel
 }
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (count) trace_kernel<true><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
-  else trace_kernel<false><<<grid, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  if (count) trace_kernel<true><<<grid * kTracePerSm, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  else trace_kernel<false><<<grid * kTracePerSm, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
+  close_hit_range_kernel<<<1, 1, 0, st>>>(P.ctl, P.pass);
 }
 int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -2345,8 +2467,8 @@ int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool ref
     if (count) shadow_refill_kernel<true><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
     else shadow_refill_kernel<false><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
   } else {
-    if (count) shadow_pooled_kernel<true><<<grid, kShadowBlock, kShadowSmem, st>>>(S, P);
-    else shadow_pooled_kernel<false><<<grid, kShadowBlock, kShadowSmem, st>>>(S, P);
+    if (count) shadow_pooled_kernel<true><<<grid * kShadowPerSm, kShadowBlock, kShadowSmem, st>>>(S, P);
+    else shadow_pooled_kernel<false><<<grid * kShadowPerSm, kShadowBlock, kShadowSmem, st>>>(S, P);
   }
   return 2;
 }

@@ -82,12 +82,16 @@ struct Device {
   cudaStream_t stream = nullptr;       // kernels (lane 0)
   cudaStream_t stream2 = nullptr;      // kernels of every second chunk when two chunks are in flight (lane 1)
   cudaStream_t copy_stream = nullptr;  // sample-offset uploads
+  // Per lane: the stream of the shadow kernels (classify + walks) when a chunk's passes are pipelined — the trace kernel of
+  // pass k + 1 runs beside the shadow kernels of pass k — with an event per pass (trace done) and one per chunk (shadows done)
+  cudaStream_t shadow_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_trace[2][kMaxPasses + 2] = {}, ev_shadows[2] = {nullptr, nullptr};
   cudaEvent_t ev_lane = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
   // per-lane scratch: a chunk's accumulators and queues
   struct Scratch {
-    DevBuf accum, rayq[2], rayq_fill[2], hitq, hitq_words, shq, shq_words, deep;
+    DevBuf accum, rayq[2], rayq_fill[2], hitq, hitq_words, shq, shq_words, deep, deep_shadow;
   } lane[2];
   DevBuf ctl, counters, offsets, rgb, ids;
   void* pinned = nullptr;  // ctl + counters read-back
@@ -107,6 +111,11 @@ struct Device {
     RH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     RH_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     RH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int l = 0; l < 2; l++) {
+      RH_CUDA(cudaStreamCreateWithFlags(&shadow_stream[l], cudaStreamNonBlocking));
+      RH_CUDA(cudaEventCreateWithFlags(&ev_shadows[l], cudaEventDisableTiming));
+      for (cudaEvent_t& e : ev_trace[l]) RH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     RH_CUDA(cudaEventCreateWithFlags(&ev_lane, cudaEventDisableTiming));
     RH_CUDA(cudaEventCreate(&ev_begin));
     RH_CUDA(cudaEventCreate(&ev_end));
@@ -119,8 +128,18 @@ struct Device {
     if (dev < 0) return;
     cudaSetDevice(dev);
     for (Scratch& sc : lane)
-      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.rayq_fill[0], &sc.rayq_fill[1], &sc.hitq, &sc.hitq_words, &sc.shq, &sc.shq_words, &sc.deep})
+      for (DevBuf* b : {&sc.accum, &sc.rayq[0], &sc.rayq[1], &sc.rayq_fill[0], &sc.rayq_fill[1], &sc.hitq, &sc.hitq_words, &sc.shq, &sc.shq_words, &sc.deep, &sc.deep_shadow})
         b->release();
+    for (int l = 0; l < 2; l++) {
+      if (shadow_stream[l]) cudaStreamDestroy(shadow_stream[l]);
+      shadow_stream[l] = nullptr;
+      if (ev_shadows[l]) cudaEventDestroy(ev_shadows[l]);
+      ev_shadows[l] = nullptr;
+      for (cudaEvent_t& e : ev_trace[l]) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+      }
+    }
     for (DevBuf* b : {&ctl, &counters, &offsets, &rgb, &ids})
       b->release();
     if (pinned) cudaFreeHost(pinned);
@@ -168,8 +187,9 @@ struct rh_scene {
   // Per-chunk kernel time of the last frame that streamed its sample offsets from the host (key: the chunk plan).
   // The next such frame processes its chunks in descending cost per sample, so that the uploads of the cheap chunks
   // hide behind the kernels of the expensive ones instead of the other way round.
-  mutable std::vector<int> cost_key;
-  mutable std::vector<float> chunk_ms;
+  mutable std::vector<int> cost_key;      // {W, H, spp, shards, shard, band height} the row costs belong to
+  mutable std::vector<float> row_cost;    // kernel ms per local row (its chunk's time / its chunk's rows)
+  mutable bool stream_compute_bound = false;  // ... and in that frame the kernels, not the upload, finished last
 };
 
 namespace {
@@ -665,6 +685,12 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   using clk = std::chrono::steady_clock;
   auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
   const clk::time_point t_begin = clk::now();
+  static const bool debug_setup = getenv("RAYHS_B200_DEBUG") && strchr(getenv("RAYHS_B200_DEBUG"), 's');
+  clk::time_point t_stage = t_begin;
+  auto stage = [&](const char* what) {
+    if (debug_setup) fprintf(stderr, "rayhs_b200: scene_create %-28s %8.1f ms\n", what, ms_since(t_stage));
+    t_stage = clk::now();
+  };
   std::vector<WideNode> wide;
   std::vector<DObject> objs;
   uint32_t depth = 0;
@@ -678,12 +704,14 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   try {
     int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
     if (rc) return rc;
+    stage("reference tree -> wide nodes");
     dtris.assign(d->tris, d->tris + d->n_tris);
     dshade.assign(d->tri_shade, d->tri_shade + d->n_tris);
     // order key of the tie rule: the first slot of a triangle's reference leaf (leaves are numbered left to right by it)
     for (uint32_t ni = 0; ni < d->n_nodes; ni++)
       if (d->nodes[ni].is_leaf)
         for (uint32_t k = 0; k < d->nodes[ni].right; k++) dtris[d->nodes[ni].left + k].pad_ = d->nodes[ni].left;
+    stage("copies, leaf keys");
     {
       SahTree sah(dtris);
       std::vector<rh_object> objects2(d->objects, d->objects + d->n_objects);
@@ -702,6 +730,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
         }
         objects2[i].root = sah.run(slots);
       }
+      stage("cull tree (binned SAH)");
       // permute the records into the cull tree's leaf order
       std::vector<rh_tri> ptris(sah.order.size());
       std::vector<rh_tri_shade> pshade(sah.order.size());
@@ -711,7 +740,9 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
         pshade[k] = dshade[sah.order[k]];
         exact_index[sah.order[k]] = (uint32_t)k;
       }
+      stage("permutation");
       sah.refit(ptris);
+      stage("refit");
       dtris.swap(ptris);
       dshade.swap(pshade);
       rh_scene_desc d2 = *d;
@@ -724,6 +755,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       uint32_t depth2 = 0, sroot2 = kEmpty;
       rc = build_wide(d2, wide_cull, objs2, &depth2, lin2, refs2, &sroot2);
       if (rc) return rc;
+      stage("cull tree -> wide nodes");
       for (size_t i = 0; i < objs.size(); i++)
         if (objs[i].root != objs2[i].root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: cull tree roots out of step");
       if (sroot2 != sphere_root) return rh::set_error(RH_ERR_STATE, "rh_scene_create: sphere tree roots out of step");
@@ -791,6 +823,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
     }
     n.pad_[0] = n.pad_[1] = 0;
   }
+  stage("float boxes");
   S->ms_trees = ms_since(t_begin);
   clk::time_point t_mark = clk::now();
   if ((rc = upload(S->wide, wide.data(), wide.size()))) return rc;
@@ -1200,6 +1233,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   // upload nothing can overlap, is small.
   std::vector<int> plan;  // rows per chunk
   int n_tail = 0;         // chunks at the end of the plan that stay last in the processing order (streamed offsets)
+  bool know_cost = false, ramped = false;  // the rows' measured costs are known; the plan is the compute-bound one
+  int ramp_first = 0, ramp_pieces = 1;     // ... whose most expensive chunk starts at plan[ramp_first], in ramp_pieces pieces
   {
     size_t want = (size_t)o->chunk_samples, first = want;
     if (o->chunk_samples <= 0) {
@@ -1208,9 +1243,51 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       want = std::min<size_t>((size_t)(0.45 * (double)D->total_mem) / per_sample, (size_t)0x3ffffff0u);
       // a frame that needs several chunks has two of them in flight, each with its own scratch: half the budget each
       if (RH_LANES > 1 && (size_t)rows_local * row_samples > want) want /= 2;
-      if (host_offsets) want = std::min<size_t>(want, (size_t)RH_STREAM_CHUNK_MI << 20);
-      first = host_offsets ? std::min<size_t>(want, (size_t)RH_STREAM_FIRST_MI << 20) : want;
+      // (RAYHS_B200_STREAM_CHUNK_MI / RAYHS_B200_STREAM_FIRST_MI: A/B switches of the two sizes)
+      static const size_t stream_chunk = (size_t)(getenv("RAYHS_B200_STREAM_CHUNK_MI") ? std::max(1, atoi(getenv("RAYHS_B200_STREAM_CHUNK_MI"))) : RH_STREAM_CHUNK_MI) << 20;
+      static const size_t stream_first = (size_t)(getenv("RAYHS_B200_STREAM_FIRST_MI") ? std::max(1, atoi(getenv("RAYHS_B200_STREAM_FIRST_MI"))) : RH_STREAM_FIRST_MI) << 20;
+      if (host_offsets) want = std::min<size_t>(want, stream_chunk);
+      first = host_offsets ? std::min<size_t>(want, stream_first) : want;
     }
+    // What the last streamed frame of this shape measured: kernel time per row, and whether the kernels or the upload
+    // finished last.
+    const std::vector<int> shape_key = {W, H, spp, G, o->shard_index, bh};
+    know_cost = host_offsets && o->chunk_samples <= 0 && scene->cost_key == shape_key && (int)scene->row_cost.size() == rows_local;
+    auto density = [&](int row0, int n) {
+      double c = 0;
+      for (int r = row0; r < row0 + n; r++) c += scene->row_cost[r];
+      return c / std::max(1, n);
+    };
+    static const bool tail_shaping = !(getenv("RAYHS_B200_TAIL") && getenv("RAYHS_B200_TAIL")[0] == '0');  // (A/B switch)
+    static const bool ramp_plan = !(getenv("RAYHS_B200_RAMP") && getenv("RAYHS_B200_RAMP")[0] == '0');     // (A/B switch)
+    if (know_cost && scene->stream_compute_bound && ramp_plan && (size_t)rows_local * row_samples > 2 * want) {
+      // Compute-bound streaming (the kernels finish after the last byte has arrived): what counts is that the GPU never
+      // waits for data once the first bytes are there.  Equal chunks, the expensive rows first (their kernels keep the GPU
+      // busy while the cheap rows arrive), and the very first chunk processed — the most expensive one — cut into
+      // 1/8, 1/8, 1/4, 1/2 so that its first piece is uploaded quickly and each piece's kernels cover the next piece's
+      // upload.  No small pieces at the end: they only help when the upload finishes last.
+      const int rows_per = (int)std::max<size_t>(1, want / row_samples);
+      for (int row = 0; row < rows_local; row += rows_per) plan.push_back(std::min(rows_per, rows_local - row));
+      if (plan.size() >= 2 && plan.back() * 4 < rows_per) {
+        plan[plan.size() - 2] += plan.back();
+        plan.pop_back();
+      }
+      size_t best = 0;
+      double best_d = -1;
+      for (size_t k = 0, row = 0; k < plan.size(); row += plan[k], k++) {
+        const double dk = density((int)row, plan[k]);
+        if (dk > best_d) { best_d = dk; best = k; }
+      }
+      const int n = plan[best];
+      ramp_first = (int)best;
+      if (n >= 16) {
+        const int e = n / 8;
+        plan[best] = e;
+        plan.insert(plan.begin() + best + 1, {e, 2 * e, n - 4 * e});
+        ramp_pieces = 4;
+      }
+      ramped = true;
+    } else {
     int row = 0;
     while (row < rows_local) {
       const size_t w = plan.empty() ? first : want;
@@ -1221,7 +1298,6 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     // Streamed offsets: the frame ends with the kernels of the chunk whose upload finishes last, so the frame's last
     // chunk is cut into halves of halves (down to ~1 Mi samples): what is left to do after the last byte has arrived is
     // a small chunk's work.
-    static const bool tail_shaping = !(getenv("RAYHS_B200_TAIL") && getenv("RAYHS_B200_TAIL")[0] == '0');  // (A/B switch)
     if (tail_shaping && host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
       int last = plan.back();
       plan.pop_back();
@@ -1233,6 +1309,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       }
       plan.push_back(last);
       n_tail++;
+    }
     }
   }
   const int n_chunks = (int)plan.size();
@@ -1261,6 +1338,13 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   // fill the GPU, so a chunk's next kernel starts on the SMs the other chunk's kernel frees as its warps run out of
   // work — the tail of every launch is filled instead of idle.  One lane when every launch is timed on its own.
   const int n_lanes = (RH_LANES > 1 && n_chunks >= 2 && !profile && !counting) ? 2 : 1;
+  // Passes pipelined over two streams per lane: trace(k + 1) needs only trace(k)'s ray queue, the shadow kernels of pass k
+  // only its hits, so trace(0) trace(1) ... run on one stream and classify(0) walk(0) classify(1) ... on the other.  Every
+  // kernel is persistent and fills the GPU; what the second stream buys is that the SMs a kernel's last warps leave idle
+  // (a lone warp walks a tree at ~1 us per node: the tail of a small launch is most of it) start the other stream's
+  // next kernel.  All adds to the accumulators are made by the shadow stream in pass order: same bits as one stream.
+  static const bool pipeline_on = !(getenv("RAYHS_B200_PIPELINE") && getenv("RAYHS_B200_PIPELINE")[0] == '0');  // (A/B switch)
+  const bool pipelined = pipeline_on && !profile && !counting && n_passes >= 2;
   for (int l = 0; l < n_lanes; l++)
     if ((rc = D->lane[l].accum.reserve(chunk_samples * 3 * sizeof(double)))) return rc;
   if ((rc = D->ctl.reserve((size_t)n_chunks * sizeof(ChunkCtl)))) return rc;
@@ -1332,6 +1416,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       if ((rc = sc.shq.reserve(walk_cap * 5 * sizeof(double2)))) return rc;
       if ((rc = sc.shq_words.reserve((3 * walk_cap + walk_cap / kSlab) * sizeof(uint32_t)))) return rc;  // sample ids, walk masks, settled masks, slab fills
       if ((rc = sc.deep.reserve(deep_bytes))) return rc;
+      if (pipelined && (rc = sc.deep_shadow.reserve(deep_bytes))) return rc;  // (kernels of both streams run side by side)
     }
 
     size_t ev_used = 0;
@@ -1365,13 +1450,25 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     // processing order of the chunks (rows are independent, Image.hs:34-36)
     std::vector<int> first_rows(n_chunks), order(n_chunks);
     for (int ck = 0, row = 0; ck < n_chunks; row += plan[ck], ck++) { first_rows[ck] = row; order[ck] = ck; }
-    std::vector<int> key = {W, H, spp, G, o->shard_index, bh};
-    key.insert(key.end(), plan.begin(), plan.end());
-    if (stream_offsets && n_chunks > 2 && scene->cost_key == key && (int)scene->chunk_ms.size() == n_chunks)
-      std::stable_sort(order.begin() + 1, order.end() - n_tail, [&](int x, int y) {  // the small first chunk stays first, the tail pieces last
-        return scene->chunk_ms[x] / plan[x] > scene->chunk_ms[y] / plan[y];
-      });
-    std::vector<cudaEvent_t> chunk_ev;
+    if (stream_offsets && n_chunks > 2 && know_cost) {
+      std::vector<double> dens(n_chunks);
+      for (int ck = 0; ck < n_chunks; ck++) {
+        double c = 0;
+        for (int r = first_rows[ck]; r < first_rows[ck] + plan[ck]; r++) c += scene->row_cost[r];
+        dens[ck] = c / std::max(1, plan[ck]);
+      }
+      // the compute-bound plan: the pieces of the most expensive chunk first, in row order, then everything in descending
+      // cost per row; else the small first chunk stays first and the tail pieces last
+      if (ramped) {
+        order.clear();
+        for (int k = 0; k < ramp_pieces; k++) order.push_back(ramp_first + k);
+        for (int ck = 0; ck < n_chunks; ck++)
+          if (ck < ramp_first || ck >= ramp_first + ramp_pieces) order.push_back(ck);
+      }
+      std::stable_sort(order.begin() + (ramped ? ramp_pieces : 1), order.end() - n_tail, [&](int x, int y) { return dens[x] > dens[y]; });
+    }
+    std::vector<cudaEvent_t> chunk_ev, copy_ev;
+    static const bool debug_timeline = getenv("RAYHS_B200_DEBUG") && strchr(getenv("RAYHS_B200_DEBUG"), 't');
     for (int i = 0; i < n_chunks; i++) {
       const int ck = order[i];
       const int first_row = first_rows[ck];
@@ -1443,6 +1540,12 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
           lr += run;
         }
         RH_CUDA(cudaEventRecord(D->ev_up[b], D->copy_stream));
+        {  // (timing events on the copy stream: when each chunk's upload ended)
+          cudaStream_t keep = lane_stream;
+          lane_stream = D->copy_stream;
+          copy_ev.push_back(prof_event());
+          lane_stream = keep;
+        }
         RH_CUDA(cudaStreamWaitEvent(lane_stream, D->ev_up[b], 0));
         P.offsets = slot;
         chunk_ev.push_back(prof_event());  // after the wait: the span holds kernel time only
@@ -1454,6 +1557,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       P.offset_base = (P.offset_index == kOffIndexLocal) ? 0ull : (unsigned long long)first_row * row_samples;
       for (int plane = 0; plane < 3; plane++)  // (three 1-D memsets: a 2-D one is limited to 2 GB of pitch)
         RH_CUDA(cudaMemsetAsync((double*)sc.accum.p + (size_t)plane * chunk_samples, 0, (size_t)P.n_samples * sizeof(double), lane_stream));
+      const int ln = i % n_lanes;
+      cudaStream_t shadow_stream = pipelined ? D->shadow_stream[ln] : lane_stream;
       for (int pass = 0; pass < n_passes; pass++) {
         P.pass = pass;
         P.q_in.plane = (double2*)sc.rayq[(pass + 1) & 1].p;
@@ -1464,11 +1569,21 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         P.q_out.capacity = (uint32_t)cap;  // (the last pass cannot emit: every ray in it has depth == maxDepth)
         cudaEvent_t a = nullptr;
         if (profile) a = prof_event();
+        P.deep_stack = (uint2*)sc.deep.p;
         launch_trace(scene->view, cam, P, counting, D->n_sms, lane_stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
-        const int n_shadow = launch_shadow(scene->view, P, counting, use_refill, D->n_sms, lane_stream);
+        if (pipelined) {
+          RH_CUDA(cudaEventRecord(D->ev_trace[ln][pass], lane_stream));
+          RH_CUDA(cudaStreamWaitEvent(shadow_stream, D->ev_trace[ln][pass], 0));
+          P.deep_stack = (uint2*)sc.deep_shadow.p;
+        }
+        const int n_shadow = launch_shadow(scene->view, P, counting, use_refill, D->n_sms, shadow_stream);
         if (profile) spans.push_back({a, prof_event(), 1});
-        launches += 1 + n_shadow;
+        launches += 2 + n_shadow;  // (trace, the one-thread kernel that closes its hit range, classify, walk)
+      }
+      if (pipelined) {  // the resolve kernel needs every pass's shadow terms
+        RH_CUDA(cudaEventRecord(D->ev_shadows[ln], shadow_stream));
+        RH_CUDA(cudaStreamWaitEvent(lane_stream, D->ev_shadows[ln], 0));
       }
       cudaEvent_t a = nullptr;
       if (profile) a = prof_event();
@@ -1549,6 +1664,57 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         fprintf(stderr, "rayhs_b200: exact shadow walks %llu, most nodes visited by one shadow ray %llu; exact closest-hit walks %llu, "
                 "most nodes visited by one closest-hit ray %llu\n", fc->exact_walks, fc->max_walk_nodes, fc->exact_closest,
                 fc->max_closest_nodes);
+      if (counting && getenv("RAYHS_B200_DEBUG"))
+        for (int row = 0; row < 4; row++) {
+          fprintf(stderr, "rayhs_b200: shadow walks of pass %d%s by log2(nodes + 1) [walks / nodes]:", row, row == 3 ? "+" : "");
+          for (int b = 0; b < 20; b++)
+            if (fc->walk_hist[row][b]) fprintf(stderr, " %d:%llu/%llu", b, fc->walk_hist[row][b], fc->walk_hist_nodes[row][b]);
+          fprintf(stderr, "\n");
+        }
+#ifdef RH_WARP_TIMES
+      if (getenv("RAYHS_B200_DEBUG"))
+        for (int row = 0; row < 4; row++) {
+          std::vector<int> b, e;
+          unsigned long long tot_b = 0, tot_r = 0;
+          int slow = -1, slow_end = 0;
+          unsigned ref = 0;
+          for (int i = 0; i < 4096; i++)
+            if (fc->warp_end[row][i]) {
+              if (b.empty()) ref = fc->warp_begin[row][i];
+              b.push_back((int)(fc->warp_begin[row][i] - ref));
+              e.push_back((int)(fc->warp_end[row][i] - ref));
+              tot_b += fc->warp_batches[row][i];
+              tot_r += fc->warp_rounds[row][i];
+              if (slow < 0 || e.back() > slow_end) { slow = i; slow_end = e.back(); }
+            }
+          if (b.empty()) continue;
+          std::sort(b.begin(), b.end());
+          std::sort(e.begin(), e.end());
+          const int t0 = b.front();
+          fprintf(stderr, "rayhs_b200: pooled pass %d: %zu warps, %llu batches, %llu rounds; warp start (us after the first) p50 %.1f p99 %.1f max %.1f; "
+                  "warp end p1 %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f; slowest warp: %u batches %u rounds\n", row, b.size(), tot_b, tot_r,
+                  (b[b.size() / 2] - t0) / 1e3, (b[b.size() * 99 / 100] - t0) / 1e3, (b.back() - t0) / 1e3, (e[e.size() / 100] - t0) / 1e3,
+                  (e[e.size() / 10] - t0) / 1e3, (e[e.size() / 2] - t0) / 1e3, (e[e.size() * 9 / 10] - t0) / 1e3, (e[e.size() * 99 / 100] - t0) / 1e3,
+                  (e.back() - t0) / 1e3, fc->warp_batches[row][slow], fc->warp_rounds[row][slow]);
+          std::vector<std::pair<int, int>> by_end;
+          for (int i = 0; i < 4096; i++)
+            if (fc->warp_end[row][i]) by_end.push_back({(int)(fc->warp_end[row][i] - ref) - t0, i});
+          std::sort(by_end.rbegin(), by_end.rend());
+          fprintf(stderr, "rayhs_b200:   slowest warps (block.warp end-us batches rounds pairs walk-us sum-of-longest-lane nodes tris):");
+          for (size_t k = 0; k < 10 && k < by_end.size(); k++) {
+            const int i = by_end[k].second;
+            fprintf(stderr, " %d.%d %.0f %u %u %u %.0f %u %u |", i / 24, i % 24, by_end[k].first / 1e3, fc->warp_batches[row][i], fc->warp_rounds[row][i],
+                    fc->warp_pairs[row][i], fc->warp_walk_ns[row][i] / 1e3, fc->warp_max_nodes[row][i], fc->warp_max_tris[row][i]);
+          }
+          fprintf(stderr, "\n");
+          {
+            const int i = by_end[by_end.size() / 2].second;
+            fprintf(stderr, "rayhs_b200:   median warp: %d.%d %.0f %u %u %u %.0f %u %u\n", i / 24, i % 24, by_end[by_end.size() / 2].first / 1e3,
+                    fc->warp_batches[row][i], fc->warp_rounds[row][i], fc->warp_pairs[row][i], fc->warp_walk_ns[row][i] / 1e3,
+                    fc->warp_max_nodes[row][i], fc->warp_max_tris[row][i]);
+          }
+        }
+#endif
       stats->upload_bytes = upload_bytes;
       float ms = 0;
       cudaEventElapsedTime(&ms, D->ev_begin, D->ev_end);
@@ -1566,10 +1732,33 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       stats->queue_factor = factor;
       stats->shadow_split = use_refill ? 1 : 0;
     }
-    if (stream_offsets && (int)chunk_ev.size() == 2 * n_chunks) {
-      scene->chunk_ms.assign(n_chunks, 0.f);
-      for (int i = 0; i < n_chunks; i++) cudaEventElapsedTime(&scene->chunk_ms[order[i]], chunk_ev[2 * i], chunk_ev[2 * i + 1]);
-      scene->cost_key = key;
+    if (debug_timeline && (int)copy_ev.size() == n_chunks && (int)chunk_ev.size() == 2 * n_chunks) {
+      float end_ms = 0;
+      cudaEventElapsedTime(&end_ms, D->ev_begin, D->ev_end);
+      fprintf(stderr, "rayhs_b200: streamed frame, %d chunks, %.2f ms; per chunk in processing order: rows, upload done, kernels begin, kernels end (ms)\n", n_chunks, end_ms);
+      for (int i = 0; i < n_chunks; i++) {
+        float up = 0, kb = 0, ke = 0;
+        cudaEventElapsedTime(&up, D->ev_begin, copy_ev[i]);
+        cudaEventElapsedTime(&kb, D->ev_begin, chunk_ev[2 * i]);
+        cudaEventElapsedTime(&ke, D->ev_begin, chunk_ev[2 * i + 1]);
+        fprintf(stderr, "rayhs_b200:   chunk %2d lane %d rows %4d  up %6.2f  begin %6.2f  end %6.2f\n", order[i], i % n_lanes, plan[order[i]], up, kb, ke);
+      }
+    }
+    if (stream_offsets && o->chunk_samples <= 0 && (int)chunk_ev.size() == 2 * n_chunks && (int)copy_ev.size() == n_chunks) {
+      scene->row_cost.assign(rows_local, 0.f);
+      for (int i = 0; i < n_chunks; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, chunk_ev[2 * i], chunk_ev[2 * i + 1]);
+        const int ck = order[i];
+        for (int r = first_rows[ck]; r < first_rows[ck] + plan[ck]; r++) scene->row_cost[r] = ms / (float)std::max(1, plan[ck]);
+      }
+      // Did the last chunk's kernels have to wait for its upload, or the other way round?  Once the compute-bound plan is
+      // in use it stays until BOTH lanes were waiting for data at the end of a frame.
+      float lag = 0, lag2 = 0;
+      cudaEventElapsedTime(&lag, copy_ev[n_chunks - 1], chunk_ev[2 * (n_chunks - 1)]);
+      if (n_chunks >= 2) cudaEventElapsedTime(&lag2, copy_ev[n_chunks - 2], chunk_ev[2 * (n_chunks - 2)]);
+      scene->stream_compute_bound = ramped ? !(lag < 0.05f && lag2 < 0.05f) : lag > 0.5f;
+      scene->cost_key = {W, H, spp, G, o->shard_index, bh};
     }
     if (tuning) {
       // only frames with enough walks to time say anything (256 Ki pairs ~ 0.2 ms)

@@ -1,5 +1,7 @@
 #!/bin/bash
-FMT="import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('  total %.2f trace %.2f shadow %.2f resolve %.2f chunks %d' % (d['ms_total'], d['ms_trace'], d['ms_shadow'], d['ms_resolve'], d['chunks']))"
-for c in 0 4194304 16777216 33554432 67108864 134217728; do
-  echo "chunk $c"; python scripts/profile_frame.py --frames 4 --chunk $c | python -c "$FMT"
+# The bench frame with the offsets already in HBM, rendered in chunks of N Mi samples (two chunks in flight): what the
+# chunking itself costs, without the upload.
+for c in ${CHUNKS:-0 8 16 32}; do
+  echo -n "chunk $c Mi: "
+  python scripts/profile_frame.py --frames 6 --no-profile --chunk $((c << 20)) 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('total %.2f ms, %d chunks' % (d['ms_total'], d['chunks']))"
 done

@@ -20,6 +20,7 @@ ap.add_argument("--shards", type=int, default=8)
 ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--shadow", default="pooled", choices=["pooled", "split"])
+ap.add_argument("--count", action="store_true", help="one instrumented frame per shard count at the end (RAYHS_B200_DEBUG=1 prints the histograms)")
 a = ap.parse_args()
 rh.init(0)
 L = capi.lib()
@@ -46,6 +47,9 @@ for G in (1, a.shards):
     torch.cuda.synchronize()
     wall = 1e3 * (time.time() - t0) / a.frames
     st = rh.render_device(job, rgb, profile=True, **kw)
+    if a.count:
+        print(f"--- counted frame, {G} shard(s)", file=sys.stderr, flush=True)
+        rh.render_device(job, rgb, count=True, **kw)
     out[f"shards_{G}"] = {"wall_ms_per_call": wall, "device_ms_per_call": dev / a.frames, "kernels_ms": st["ms_trace"] + st["ms_shadow"] + st["ms_resolve"],
                           "trace": st["ms_trace"], "shadow": st["ms_shadow"], "resolve": st["ms_resolve"], "chunks": st["chunks"]}
 one, many = out["shards_1"], out[f"shards_{a.shards}"]
