@@ -457,6 +457,14 @@ struct AnyHit {
   __device__ __forceinline__ bool offer_object(const Ray& r, double tt, int, double&) const { return in_front(r, tt); }
 };
 
+// Prefetches (RH_PREFETCH bit 0: the lines of a leaf's triangle records beyond the first when the leaf is entered; bit 1:
+// the node record of a child that is stacked for later).  A lone warp walks at the latency of its loads — an L2 hit is
+// ~250 cycles, an L1 hit ~32 — and the records a walk will need next are known one step ahead.
+#ifndef RH_PREFETCH
+#define RH_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Mesh.hs:59-82 triangleIntersection over the `count` triangles of one leaf (Geometry.hs:54-57).
 // The accept/reject decision is the reference's expression evaluated on the reference's values
 // of det, u, v, t.  Before the division, a triangle is dropped early only when that expression is
@@ -468,6 +476,12 @@ struct AnyHit {
 template <bool COUNT, class Sink>
 __device__ __forceinline__ bool test_leaf(const rh_tri* __restrict__ tris, uint32_t first, uint32_t count, const Ray& r,
                                           Sink& sink, double& bound, Cnt<COUNT>& cnt, const uint32_t* __restrict__ index = nullptr) {
+#if RH_PREFETCH & 1
+  if (!index && count > 1) {  // the records are consecutive: first .. first + count - 1, 80 bytes each
+    const char* base = (const char*)(tris + first);
+    for (uint32_t off = 128; off < count * (uint32_t)sizeof(rh_tri) + 127u; off += 128) prefetch_l1(base + off);
+  }
+#endif
   for (uint32_t k = 0; k < count; k++) {
     const uint32_t slot = index ? __ldg(index + first + k) : first + k;  // (exact walk over the reference tree's leaves)
     const double2* tp = (const double2*)(tris + slot);
@@ -564,6 +578,16 @@ __device__ __forceinline__ bool node_step(const Ctx& cx, uint32_t& ref, const Ra
       st.push(sp, cw.y, tm1);
       ref = cw.x;
     }
+#if RH_PREFETCH & 2
+    {
+      const uint32_t far = (tm1 < tm0) ? cw.x : cw.y;  // popped later: its record (or its first triangle) can be on its way
+      if (far & kLeafBit) {
+        if (!(far & kSphereLeafBit)) prefetch_l1(cx.S->tris + (far & kLeafFirstMask));
+      } else if (far >= cx.S->n_smem_nodes) {
+        prefetch_l1(&cx.S->wide32[far]);
+      }
+    }
+#endif
     return true;
   }
   if (h0) {
@@ -942,6 +966,9 @@ __device__ __forceinline__ void slab_close(const SlabWriter& w, uint32_t lane, u
 #ifndef RH_CLAIM_UNIT
 #define RH_CLAIM_UNIT 8
 #endif
+#ifndef RH_CLAIM_DIV
+#define RH_CLAIM_DIV 4  // a claim takes 1 / (RH_CLAIM_DIV x warps) of what is left (bench frame / one eighth of it: 2: 38.43 / 6.00 ms, 4: 38.31 / 5.91, 8: 39.39 / 6.22, 16: 42.09 / 7.35)
+#endif
 constexpr uint32_t kUnit = RH_CLAIM_UNIT;
 constexpr uint32_t kSlabUnits = kSlab / kUnit, kGroupUnits = 32 / kUnit;
 static_assert(kUnit >= 1 && kUnit <= 32 && 32 % kUnit == 0, "a claim unit divides a warp's 32 lanes");
@@ -952,7 +979,7 @@ __device__ __forceinline__ uint2 claim_units(uint32_t* cursor, uint32_t n_units,
   uint2 c = make_uint2(0, 1);
   if (lane == 0) {
     const uint32_t left = seen < n_units ? n_units - seen : 0;
-    uint32_t want = min(kSlabUnits, max(1u, left / (2u * total_warps)));
+    uint32_t want = min(kSlabUnits, max(1u, left / ((uint32_t)RH_CLAIM_DIV * total_warps)));
     if (want >= kGroupUnits) want -= want % kGroupUnits;  // whole 32-item groups
     c.y = want;
     c.x = atomicAdd(cursor, c.y);

@@ -203,7 +203,7 @@ namespace {
 // Boxes are padded so that a ray the reference's rounded discriminant accepts cannot miss the box.
 constexpr int kLightMapRes = 512;                       // cells per edge of a cube-map face (6.3 MB per map)
 constexpr size_t kLightMapBudget = (size_t)256 << 20;   // all maps of a scene; the resolution halves until they fit
-constexpr size_t kLitMaxQueriesDevice = 48000000;        // the same bound for the GPU builder (~0.05 us per query)
+constexpr size_t kLitMaxQueriesDevice = 48000000;        // the same bound for the GPU builder (dragon: 82 k queries in ~2 ms)
 constexpr size_t kLitMaxQueries = 1200000;              // (triangles x lights) of a mesh beyond which it gets no lit-triangle flags (host time: ~10 us per query)
 constexpr double kLightMapMinEmpty = 0.02;              // a map with fewer empty cells than this is not worth its lookups
 constexpr uint32_t kSphereTreeMin = 16;  // fewer spheres than this stay in the linear object list
@@ -420,6 +420,43 @@ int build_wide(const rh_scene_desc& d, std::vector<WideNode>& wide, std::vector<
   return RH_OK;
 }
 
+// Allocator that leaves trivially constructible elements uninitialised: `std::vector<T, NoInit<T>> v(n)` does not spend a
+// single-threaded pass zeroing gigabytes that the next (multi-threaded) loop overwrites.
+template <class T>
+struct NoInit : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInit<U>; };
+  template <class U, class... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+using TriVec = std::vector<rh_tri, NoInit<rh_tri>>;
+using ShadeVec = std::vector<rh_tri_shade, NoInit<rh_tri_shade>>;
+
+// f(begin, end, thread) over [0, n) on up to 32 host threads (one call when n is small).  f must not throw.
+template <class F>
+void parallel_for(size_t n, size_t min_per_thread, F f) {
+  const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(hw, n / std::max<size_t>(1, min_per_thread)));
+  if (nt <= 1) {
+    f((size_t)0, n, 0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (n + nt - 1) / nt;
+  try {
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back([=]() { f(std::min(n, t * per), std::min(n, (t + 1) * per), t); });
+  } catch (...) {  // (could not start a thread: the caller's thread does the rest)
+    const size_t done = pool.size() + 1;
+    f((size_t)0, per, 0u);
+    for (size_t t = done; t < nt; t++) f(std::min(n, t * per), std::min(n, (t + 1) * per), (unsigned)t);
+    for (std::thread& th : pool) th.join();
+    return;
+  }
+  f((size_t)0, std::min(n, per), 0u);
+  for (std::thread& th : pool) th.join();
+}
+
 // Bounding box of one triangle record, padded for p0 + e != p exactly.
 struct TriBox {
   static void tri_box(const rh_tri& t, double* lo, double* hi) {
@@ -449,14 +486,14 @@ struct SahTree {
     std::vector<uint32_t> order;  // new slot -> reference slot
     uint32_t max_depth = 0;
   };
-  const std::vector<rh_tri>& tris;  // reference (leaf) order
+  const rh_tri* tris;               // reference (leaf) order
   std::vector<rh_node> nodes;       // all trees built so far; leaves: left = first NEW slot, right = count
   std::vector<uint32_t> order;      // new slot -> reference slot
   uint32_t max_depth = 0;
   std::vector<Ref> refs;
   std::atomic<bool> failed{false};
 
-  explicit SahTree(const std::vector<rh_tri>& t) : tris(t) {}
+  explicit SahTree(const rh_tri* t) : tris(t) {}
 
   static float area(const float* lo, const float* hi) {
     const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
@@ -481,19 +518,45 @@ struct SahTree {
   uint32_t build(size_t b, size_t e, uint32_t depth, Sub& out, int fork_levels) {
     out.max_depth = std::max(out.max_depth, depth);
     const float inf = std::numeric_limits<float>::infinity();
-    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf}, clo[3] = {inf, inf, inf}, chi[3] = {-inf, -inf, -inf};
-    for (size_t i = b; i < e; i++)
-      for (int k = 0; k < 3; k++) {
-        lo[k] = std::min(lo[k], refs[i].lo[k]);
-        hi[k] = std::max(hi[k], refs[i].hi[k]);
-        clo[k] = std::min(clo[k], refs[i].c[k]);
-        chi[k] = std::max(chi[k], refs[i].c[k]);
-      }
+    constexpr int kBins = 16;
+    // Bounds, then the bins of all three axes in one pass over the range.  The large ranges near the root are cut into
+    // pieces for several threads; min / max and the counts merge exactly, so the tree does not depend on the thread count.
+    struct Bounds { float lo[3], hi[3], clo[3], chi[3]; };
+    struct Bins { float blo[3][kBins][3], bhi[3][kBins][3]; uint32_t cnt[3][kBins]; };
+    auto bounds_of = [&](size_t kb, size_t ke, Bounds& o) {
+      for (int k = 0; k < 3; k++) { o.lo[k] = o.clo[k] = inf; o.hi[k] = o.chi[k] = -inf; }
+      for (size_t i = kb; i < ke; i++)
+        for (int k = 0; k < 3; k++) {
+          o.lo[k] = std::min(o.lo[k], refs[i].lo[k]);
+          o.hi[k] = std::max(o.hi[k], refs[i].hi[k]);
+          o.clo[k] = std::min(o.clo[k], refs[i].c[k]);
+          o.chi[k] = std::max(o.chi[k], refs[i].c[k]);
+        }
+    };
+    const size_t n = e - b;
+    const bool wide_range = fork_levels > 0 && n >= (1u << 20);
+    const unsigned pieces = wide_range ? std::max(1u, std::min(32u, std::thread::hardware_concurrency())) : 1u;
+    Bounds bd;
+    if (pieces > 1) {
+      std::vector<Bounds> part(pieces);
+      for (Bounds& q : part) bounds_of(0, 0, q);
+      parallel_for(n, 1u << 16, [&](size_t kb, size_t ke, unsigned t) { bounds_of(b + kb, b + ke, part[t % pieces]); });
+      bounds_of(0, 0, bd);
+      for (const Bounds& q : part)
+        for (int k = 0; k < 3; k++) {
+          bd.lo[k] = std::min(bd.lo[k], q.lo[k]);
+          bd.hi[k] = std::max(bd.hi[k], q.hi[k]);
+          bd.clo[k] = std::min(bd.clo[k], q.clo[k]);
+          bd.chi[k] = std::max(bd.chi[k], q.chi[k]);
+        }
+    } else {
+      bounds_of(b, e, bd);
+    }
+    const float *lo = bd.lo, *hi = bd.hi, *clo = bd.clo, *chi = bd.chi;
     rh_node nd{};
     for (int k = 0; k < 3; k++) { nd.lo[k] = lo[k]; nd.hi[k] = hi[k]; }
     const uint32_t self = (uint32_t)out.nodes.size();
     out.nodes.push_back(nd);
-    const size_t n = e - b;
     if (n <= kSubLeaf) {
       out.nodes[self].is_leaf = 1;
       out.nodes[self].left = (uint32_t)out.order.size();
@@ -502,29 +565,55 @@ struct SahTree {
       return self;
     }
     // binned SAH over the three axes; deep or degenerate ranges fall back to the object median of the widest axis
-    constexpr int kBins = 16;
     int best_axis = -1, best_bin = 0;
     float best_cost = inf;
     if (depth < 48) {
-      for (int axis = 0; axis < 3; axis++) {
-        const float ext = chi[axis] - clo[axis];
-        if (!(ext > 0)) continue;
-        const float scale = (float)kBins / ext;
-        float blo[kBins][3], bhi[kBins][3];
-        uint32_t cnt[kBins];
-        for (int i = 0; i < kBins; i++) {
-          cnt[i] = 0;
-          for (int k = 0; k < 3; k++) { blo[i][k] = inf; bhi[i][k] = -inf; }
-        }
-        for (size_t i = b; i < e; i++) {
-          int bi = (int)((refs[i].c[axis] - clo[axis]) * scale);
-          bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-          cnt[bi]++;
-          for (int k = 0; k < 3; k++) {
-            blo[bi][k] = std::min(blo[bi][k], refs[i].lo[k]);
-            bhi[bi][k] = std::max(bhi[bi][k], refs[i].hi[k]);
+      float scale[3];
+      for (int axis = 0; axis < 3; axis++) scale[axis] = (chi[axis] - clo[axis] > 0) ? (float)kBins / (chi[axis] - clo[axis]) : 0.f;
+      auto clear_bins = [&](Bins& q) {
+        for (int a = 0; a < 3; a++)
+          for (int i = 0; i < kBins; i++) {
+            q.cnt[a][i] = 0;
+            for (int k = 0; k < 3; k++) { q.blo[a][i][k] = inf; q.bhi[a][i][k] = -inf; }
           }
-        }
+      };
+      auto bin_range = [&](size_t kb, size_t ke, Bins& q) {
+        for (size_t i = kb; i < ke; i++)
+          for (int axis = 0; axis < 3; axis++) {
+            if (!(scale[axis] > 0)) continue;
+            int bi = (int)((refs[i].c[axis] - clo[axis]) * scale[axis]);
+            bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
+            q.cnt[axis][bi]++;
+            for (int k = 0; k < 3; k++) {
+              q.blo[axis][bi][k] = std::min(q.blo[axis][bi][k], refs[i].lo[k]);
+              q.bhi[axis][bi][k] = std::max(q.bhi[axis][bi][k], refs[i].hi[k]);
+            }
+          }
+      };
+      Bins bins_store;  // (1.3 KB on the stack per level)
+      Bins* bins = &bins_store;
+      clear_bins(*bins);
+      if (pieces > 1) {
+        std::vector<Bins> part(pieces);
+        for (Bins& q : part) clear_bins(q);
+        parallel_for(n, 1u << 16, [&](size_t kb, size_t ke, unsigned t) { bin_range(b + kb, b + ke, part[t % pieces]); });
+        for (const Bins& q : part)
+          for (int a = 0; a < 3; a++)
+            for (int i = 0; i < kBins; i++) {
+              bins->cnt[a][i] += q.cnt[a][i];
+              for (int k = 0; k < 3; k++) {
+                bins->blo[a][i][k] = std::min(bins->blo[a][i][k], q.blo[a][i][k]);
+                bins->bhi[a][i][k] = std::max(bins->bhi[a][i][k], q.bhi[a][i][k]);
+              }
+            }
+      } else {
+        bin_range(b, e, *bins);
+      }
+      for (int axis = 0; axis < 3; axis++) {
+        if (!(scale[axis] > 0)) continue;
+        const auto& blo = bins->blo[axis];
+        const auto& bhi = bins->bhi[axis];
+        const uint32_t* cnt = bins->cnt[axis];
         float rarea[kBins];
         uint32_t rcnt[kBins];
         float alo[3] = {inf, inf, inf}, ahi[3] = {-inf, -inf, -inf};
@@ -598,17 +687,19 @@ struct SahTree {
     if (slots.empty()) return RH_NO_NODE;
     const uint32_t count = (uint32_t)slots.size();
     refs.resize(count);
-    for (uint32_t k = 0; k < count; k++) {
-      Ref& r = refs[k];
-      r.slot = slots[k];
-      double lo[3], hi[3];
-      TriBox::tri_box(tris[slots[k]], lo, hi);
-      for (int a = 0; a < 3; a++) {  // float is enough to choose splits; the stored boxes are recomputed in double
-        r.lo[a] = (float)lo[a];
-        r.hi[a] = (float)hi[a];
-        r.c[a] = 0.5f * (r.lo[a] + r.hi[a]);
+    parallel_for(count, 1u << 16, [&](size_t kb, size_t ke, unsigned) {
+      for (size_t k = kb; k < ke; k++) {
+        Ref& r = refs[k];
+        r.slot = slots[k];
+        double lo[3], hi[3];
+        TriBox::tri_box(tris[slots[k]], lo, hi);
+        for (int a = 0; a < 3; a++) {  // float is enough to choose splits; the stored boxes are recomputed in double
+          r.lo[a] = (float)lo[a];
+          r.hi[a] = (float)hi[a];
+          r.c[a] = 0.5f * (r.lo[a] + r.hi[a]);
+        }
       }
-    }
+    });
     const unsigned n_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     int fork_levels = 0;
     while ((1u << fork_levels) < n_threads) fork_levels++;
@@ -631,21 +722,26 @@ struct SahTree {
   }
 
   // Exact (double, padded) boxes of all nodes from the permuted triangles, bottom-up.
-  void refit(const std::vector<rh_tri>& new_tris) {
+  void refit(const TriVec& new_tris) {
     const double inf = std::numeric_limits<double>::infinity();
-    for (size_t i = nodes.size(); i-- > 0;) {  // children always follow their parent in `nodes`
-      rh_node& nd = nodes[i];
-      for (int k = 0; k < 3; k++) { nd.lo[k] = inf; nd.hi[k] = -inf; }
-      if (nd.is_leaf) {
+    parallel_for(nodes.size(), 1u << 16, [&](size_t ib, size_t ie, unsigned) {  // the leaves (independent of each other)
+      for (size_t i = ib; i < ie; i++) {
+        rh_node& nd = nodes[i];
+        if (!nd.is_leaf) continue;
+        for (int k = 0; k < 3; k++) { nd.lo[k] = inf; nd.hi[k] = -inf; }
         for (uint32_t t = 0; t < nd.right; t++) {
           double lo[3], hi[3];
           TriBox::tri_box(new_tris[nd.left + t], lo, hi);
           for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], lo[k]); nd.hi[k] = std::max(nd.hi[k], hi[k]); }
         }
-      } else {
-        for (uint32_t c : {nd.left, nd.right})
-          for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], nodes[c].lo[k]); nd.hi[k] = std::max(nd.hi[k], nodes[c].hi[k]); }
       }
+    });
+    for (size_t i = nodes.size(); i-- > 0;) {  // children always follow their parent in `nodes`
+      rh_node& nd = nodes[i];
+      if (nd.is_leaf) continue;
+      for (int k = 0; k < 3; k++) { nd.lo[k] = inf; nd.hi[k] = -inf; }
+      for (uint32_t c : {nd.left, nd.right})
+        for (int k = 0; k < 3; k++) { nd.lo[k] = std::min(nd.lo[k], nodes[c].lo[k]); nd.hi[k] = std::max(nd.hi[k], nodes[c].hi[k]); }
     }
   }
 };
@@ -694,26 +790,35 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   std::vector<WideNode> wide;
   std::vector<DObject> objs;
   uint32_t depth = 0;
-  std::vector<rh_tri> dtris;
-  std::vector<rh_tri_shade> dshade;
+  TriVec dtris;
+  ShadeVec dshade;
   std::vector<uint32_t> lin_objs, sphere_refs;
   uint32_t sphere_root = kEmpty;
   std::vector<WideNode> wide_cull;      // the float path's own tree (same super-root indices as `wide`)
   uint32_t cull_depth = 0;              // its depth (the reference tree's is `depth`)
   std::vector<uint32_t> exact_index;    // reference slot -> slot in the permuted triangle arrays
   try {
-    int rc = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
-    if (rc) return rc;
-    stage("reference tree -> wide nodes");
-    dtris.assign(d->tris, d->tris + d->n_tris);
-    dshade.assign(d->tri_shade, d->tri_shade + d->n_tris);
+    // the reference tree's wide records (exact walk) are built on their own thread beside the cull tree
+    int rc = RH_OK, rc_ref = RH_OK;
+    std::string ref_error;
+    bool ref_threw = false;
+    std::thread ref_thread([&]() {
+      try {
+        rc_ref = build_wide(*d, wide, objs, &depth, lin_objs, sphere_refs, &sphere_root);
+        if (rc_ref) ref_error = rh::g_err;  // (the message is thread-local)
+      } catch (...) {
+        ref_threw = true;
+      }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } ref_join{ref_thread};
     // order key of the tie rule: the first slot of a triangle's reference leaf (leaves are numbered left to right by it)
+    std::vector<uint32_t> leaf_key(d->n_tris, 0);
     for (uint32_t ni = 0; ni < d->n_nodes; ni++)
       if (d->nodes[ni].is_leaf)
-        for (uint32_t k = 0; k < d->nodes[ni].right; k++) dtris[d->nodes[ni].left + k].pad_ = d->nodes[ni].left;
-    stage("copies, leaf keys");
+        for (uint32_t k = 0; k < d->nodes[ni].right; k++) leaf_key[d->nodes[ni].left + k] = d->nodes[ni].left;
+    stage("leaf keys");
     {
-      SahTree sah(dtris);
+      SahTree sah(d->tris);
       std::vector<rh_object> objects2(d->objects, d->objects + d->n_objects);
       for (uint32_t i = 0; i < d->n_objects; i++) {
         if (objects2[i].kind != RH_OBJ_MESH || objects2[i].root == RH_NO_NODE) continue;
@@ -731,15 +836,23 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
         objects2[i].root = sah.run(slots);
       }
       stage("cull tree (binned SAH)");
+      ref_thread.join();
+      if (ref_threw) throw std::bad_alloc();
+      if (rc_ref) return rh::set_error(rc_ref, ref_error);
+      stage("reference tree -> wide nodes (rest)");
       // permute the records into the cull tree's leaf order
-      std::vector<rh_tri> ptris(sah.order.size());
-      std::vector<rh_tri_shade> pshade(sah.order.size());
+      TriVec ptris(sah.order.size());
+      ShadeVec pshade(sah.order.size());
       exact_index.assign(d->n_tris, 0);
-      for (size_t k = 0; k < sah.order.size(); k++) {
-        ptris[k] = dtris[sah.order[k]];
-        pshade[k] = dshade[sah.order[k]];
-        exact_index[sah.order[k]] = (uint32_t)k;
-      }
+      parallel_for(sah.order.size(), 1u << 16, [&](size_t kb, size_t ke, unsigned) {  // (the caller's records are copied once)
+        for (size_t k = kb; k < ke; k++) {
+          const uint32_t from = sah.order[k];
+          ptris[k] = d->tris[from];
+          ptris[k].pad_ = leaf_key[from];
+          pshade[k] = d->tri_shade[from];
+          exact_index[from] = (uint32_t)k;
+        }
+      });
       stage("permutation");
       sah.refit(ptris);
       stage("refit");
@@ -796,32 +909,45 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
       if (blo[k] <= bhi[k]) center[k] = 0.5 * (blo[k] + bhi[k]);
   }
   const float finf = std::numeric_limits<float>::infinity();
-  for (size_t i = 0; i < cull.size(); i++) {
-    const WideNode& w = cull[i];
-    WideNode32& n = wide32[i];
-    for (int c = 0; c < 2; c++) {
-      for (int k = 0; k < 3; k++) {
-        const double lo = w.box[6 * c + k] - center[k], hi = w.box[6 * c + 3 + k] - center[k];
-        float flo = (float)lo, fhi = (float)hi;
-        if ((double)flo > lo) flo = std::nextafterf(flo, -finf);
-        if ((double)fhi < hi) fhi = std::nextafterf(fhi, finf);
-        if (std::isfinite(flo)) flo = std::nextafterf(flo, -finf);
-        if (std::isfinite(fhi)) fhi = std::nextafterf(fhi, finf);
-        n.box[6 * c + k] = flo;
-        n.box[6 * c + 3 + k] = fhi;
-        if (w.child[c] != kEmpty) abs_max = std::max(abs_max, std::max(std::fabs(flo), std::fabs(fhi)));
+  {
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<float> abs_max_of(hw + 1, 0.f);
+    std::atomic<bool> bad_leaf{false};
+    parallel_for(cull.size(), 1u << 15, [&](size_t ib, size_t ie, unsigned t) {
+      float amax = 0.f;
+      for (size_t i = ib; i < ie; i++) {
+        const WideNode& w = cull[i];
+        WideNode32& n = wide32[i];
+        for (int c = 0; c < 2; c++) {
+          for (int k = 0; k < 3; k++) {
+            const double lo = w.box[6 * c + k] - center[k], hi = w.box[6 * c + 3 + k] - center[k];
+            float flo = (float)lo, fhi = (float)hi;
+            if ((double)flo > lo) flo = std::nextafterf(flo, -finf);
+            if ((double)fhi < hi) fhi = std::nextafterf(fhi, finf);
+            if (std::isfinite(flo)) flo = std::nextafterf(flo, -finf);
+            if (std::isfinite(fhi)) fhi = std::nextafterf(fhi, finf);
+            n.box[6 * c + k] = flo;
+            n.box[6 * c + 3 + k] = fhi;
+            if (w.child[c] != kEmpty) amax = std::max(amax, std::max(std::fabs(flo), std::fabs(fhi)));
+          }
+          // leaf references of the cull tree carry their slot range (see kLeafCountShift): a stacked subtree is one word
+          uint32_t ch = w.child[c];
+          if (ch != kEmpty && (ch & kLeafBit)) {
+            const uint32_t count = ch & kCountMask;
+            if (count == 0 || count > kLeafMaxCount || w.first[c] > kLeafFirstMask) {
+              bad_leaf = true;
+              continue;
+            }
+            ch = (ch & (kLeafBit | kSphereLeafBit)) | ((count - 1) << kLeafCountShift) | w.first[c];
+          }
+          n.child[c] = ch;
+        }
+        n.pad_[0] = n.pad_[1] = 0;
       }
-      // leaf references of the cull tree carry their slot range (see kLeafCountShift): a stacked subtree is one word
-      uint32_t ch = w.child[c];
-      if (ch != kEmpty && (ch & kLeafBit)) {
-        const uint32_t count = ch & kCountMask;
-        if (count == 0 || count > kLeafMaxCount || w.first[c] > kLeafFirstMask)
-          return rh::set_error(RH_ERR_ARG, "rh_scene_create: more than 134 M triangle slots, or a cull-tree leaf out of range");
-        ch = (ch & (kLeafBit | kSphereLeafBit)) | ((count - 1) << kLeafCountShift) | w.first[c];
-      }
-      n.child[c] = ch;
-    }
-    n.pad_[0] = n.pad_[1] = 0;
+      abs_max_of[std::min<unsigned>(t, hw)] = amax;
+    });
+    if (bad_leaf) return rh::set_error(RH_ERR_ARG, "rh_scene_create: more than 134 M triangle slots, or a cull-tree leaf out of range");
+    for (float a : abs_max_of) abs_max = std::max(abs_max, a);
   }
   stage("float boxes");
   S->ms_trees = ms_since(t_begin);
@@ -933,7 +1059,25 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
           if (slots.empty()) continue;
           if ((rc = upload(slot_bufs[m], slots.data(), slots.size()))) return rc;
           const uint32_t* d_slots = (const uint32_t*)slot_bufs[m].p;
-          const bool want_lit = slots.size() * (size_t)d->n_lights <= kLitMaxQueriesDevice && !(env_lit && env_lit[0] == '0');
+          // the cube maps first: a mesh none of whose maps is worth having is a triangle soup around its lights, where
+          // nearly every triangle is shadowed by another one — the lit-triangle queries (long hulls through the whole
+          // soup, ~0.25 us each on the GPU) are not made either
+          uint32_t point_lights = 0, useful_maps = 0;
+          for (uint32_t li = 0; li < d->n_lights; li++) {
+            if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+            point_lights++;
+            int useful = 0;
+            double empty = 0;
+            RH_CUDA((cudaError_t)device_light_map(d->lights[li].vec, (const rh_tri*)S->tris.p, d_slots, slots.size(), R,
+                                                  (float*)S->light_maps.p + (size_t)n_maps * cells, kLightMapMinEmpty,
+                                                  (unsigned long long*)words.p, &useful, &empty, D->stream));
+            if (useful) {
+              index[(size_t)li * kOccMeshes + m] = n_maps++;
+              useful_maps++;
+            }
+          }
+          const bool want_lit = slots.size() * (size_t)d->n_lights <= kLitMaxQueriesDevice && !(env_lit && env_lit[0] == '0') &&
+                                (point_lights == 0 || useful_maps > 0);
           if (want_lit) {
             if (!any_lit_query) {
               const size_t lit_bytes = ((dtris.size() + 1) / 2) * 4;  // (whole 32-bit words: the kernel sets bits with atomicOr)
@@ -944,15 +1088,6 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
             RH_CUDA((cudaError_t)device_lit_flags((const rh_tri*)S->tris.p, (const WideNode32*)S->wide32.p, center, occ_meshes[m], d_slots,
                                                   (uint32_t)slots.size(), (const rh_light*)S->lights.p, d->n_lights, (uint32_t)m,
                                                   (uint16_t*)S->lit_flags.p, (unsigned long long*)words.p + 2, D->stream));
-          }
-          for (uint32_t li = 0; li < d->n_lights; li++) {  // (the lit queries run on the GPU while the host waits for the maps' counts)
-            if (d->lights[li].kind != RH_LIGHT_POINT) continue;
-            int useful = 0;
-            double empty = 0;
-            RH_CUDA((cudaError_t)device_light_map(d->lights[li].vec, (const rh_tri*)S->tris.p, d_slots, slots.size(), R,
-                                                  (float*)S->light_maps.p + (size_t)n_maps * cells, kLightMapMinEmpty,
-                                                  (unsigned long long*)words.p, &useful, &empty, D->stream));
-            if (useful) index[(size_t)li * kOccMeshes + m] = n_maps++;
           }
         }
         if (on_device) {
@@ -1049,20 +1184,24 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
             lit_found = flagged.load();
           };
           std::thread lit_thread;
-          if (want_lit) lit_thread = std::thread(lit_job);
           bool maps_failed = false;
+          uint32_t point_lights = 0, useful_maps = 0;
           try {
             for (uint32_t li = 0; li < d->n_lights; li++) {
               if (d->lights[li].kind != RH_LIGHT_POINT) continue;
+              point_lights++;
               double empty = 0;
               if (!rh::build_light_map(d->lights[li].vec, dtris.data(), slots.data(), slots.size(), R, one.data(), kLightMapMinEmpty, &empty))
                 continue;
               index[(size_t)li * kOccMeshes + m] = n_maps++;
+              useful_maps++;
               maps.insert(maps.end(), one.begin(), one.end());
             }
           } catch (...) {
-            maps_failed = true;  // (the query threads must be joined before anything unwinds)
+            maps_failed = true;
           }
+          // (same rule as the GPU builder: no lit-triangle queries for a mesh that is a soup around its lights)
+          if (want_lit && !maps_failed && (point_lights == 0 || useful_maps > 0)) lit_thread = std::thread(lit_job);
           if (lit_thread.joinable()) lit_thread.join();
           if (lit_failed || maps_failed) throw std::bad_alloc();
           n_lit += lit_found;
@@ -1103,7 +1242,7 @@ int scene_create_on(Device* D, const rh_scene_desc* d, rh_scene** out) {
   v.textures = (const rh_texture*)S->textures.p;
   v.texels = (const double*)S->texels.p;
   v.n_wide = (uint32_t)cull.size();
-  v.n_tris = d->n_tris;
+  v.n_tris = (uint32_t)dtris.size();  // triangle slots on the device (the meshes' triangles, in cull-tree leaf order)
   v.n_objects = d->n_objects;
   v.n_materials = d->n_materials;
   v.n_lights = d->n_lights;
@@ -1871,8 +2010,10 @@ int rh_render(const rh_scene* scene, const rh_camera* camera, const rh_render_op
 
 int rh_default_band_height(int height, int shard_count) {
   if (shard_count <= 1) return height > 0 ? height : 1;
-  // interleave bands so that every shard sees every part of the frame
-  int bh = 16;
+  // interleave bands so that every shard sees every part of the frame.  Narrow bands balance the shards (the
+  // dragon covers the middle third of the bench frame; measured on 8 B200: 16 rows 6.64 ms, 4 rows 6.60, 1 row 6.52 per
+  // frame); 4 rows keep a shard's offset upload at a few hundred copies per frame.
+  int bh = 4;
   while (bh > 1 && height / (bh * shard_count) < 4) bh /= 2;
   return bh;
 }

@@ -73,9 +73,9 @@ def test_product_never_references_the_oracle():
 
 def test_shard_row_arithmetic():
     L = capi.lib()
-    assert L.rh_shard_rows(2160, 8, 16) == 272 and L.rh_shard_rows(2160, 1, 2160) == 2160
+    assert L.rh_shard_rows(2160, 8, 16) == 272 and L.rh_shard_rows(2160, 8, 4) == 272 and L.rh_shard_rows(2160, 1, 2160) == 2160
     assert L.rh_shard_rows(10, 2, 2) == 6
-    assert L.rh_default_band_height(2160, 1) == 2160 and L.rh_default_band_height(2160, 8) == 16
+    assert L.rh_default_band_height(2160, 1) == 2160 and L.rh_default_band_height(2160, 8) == 4
     import rayhs_b200 as rh
 
     for H, G, bh in ((10, 2, 2), (2160, 8, 16), (7, 4, 1), (150, 8, 4)):
