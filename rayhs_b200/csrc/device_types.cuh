@@ -166,9 +166,10 @@ struct CameraParams {
 // Per-chunk control block in device memory (zeroed before each chunk).
 struct ChunkCtl {
   uint32_t ray_slabs[kMaxPasses + 2];     // slabs reserved in the ray queue that pass k consumes
-  // The hit queue is filled front to back by ALL passes of a chunk (one running slab counter): pass k's shaded hits are
-  // the slabs [hit_start[k], hit_start[k + 1]), so that pass k + 1's trace kernel can append while pass k's hits are
-  // still being classified on the other stream.  hit_start[k + 1] is written when pass k's trace kernel has ended.
+  // The hit queue is a ring of slabs addressed by ONE running counter over all passes of a chunk: pass k's shaded hits
+  // are the slabs [hit_start[k], hit_start[k + 1]) (mod the ring), so that pass k + 1's trace kernel can append while
+  // pass k's hits are still being classified on the other stream; pass k + 2 reuses pass k's slabs.  hit_start[k + 1] is
+  // written when pass k's trace kernel has ended.
   uint32_t hit_start[kMaxPasses + 3];
   uint32_t shadow_slabs[kMaxPasses + 2];  // slabs of hits whose shadow rays have to walk a tree (walk queue)
   uint32_t trace_cursor[kMaxPasses + 2];  // persistent-warp work cursors, in claim units
@@ -246,6 +247,8 @@ struct ChunkParams {
   int32_t pass;           // wavefront pass (0 = primary)
   int32_t exact_boxes;    // RH_FLAG_EXACT_BOXES: double slab test for every ray (validation)
   int32_t no_light_maps;  // RH_FLAG_NO_LIGHT_MAPS: shadow rays ignore the lights' cube maps (validation, A/B)
+  int32_t hit_live_pass;  // the hit queue (a ring) still holds the hits of this pass and later ones (pass, or pass - 1 when pipelined)
+  int32_t pad6_;
   const void* offsets;    // device
   uint32_t offset_linear; // f64 pairs in work-item order: pair of item i at offsets[offset_base + i] (bulk-copy staging)
   uint32_t pad5_;
@@ -271,13 +274,15 @@ struct ChunkParams {
 void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams& P, bool count, int grid, void* stream);
 // classify_kernel, then the walks of the hits it queued — refill: the per-lane-refill kernel (incoherent rays) instead of
 // the pooled one (coherent rays).  Returns the number of launches.
-int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream);
+// `classified`: a cudaEvent_t recorded after the classify kernel (or null).
+int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream, void* classified);
 void launch_resolve(const ChunkParams& P, void* stream);
 void launch_deinterleave(const uint8_t* gathered, uint8_t* out, int width, int height, int shard_count, int band_height,
                          void* stream);
 int configure_kernels();  // opt in to > 48 KB dynamic shared memory; returns a cudaError_t
 int max_threads_per_launch(int n_sms);  // largest grid * block of the trace / shadow kernels (sizes the deep-stack scratch)
 // setup_kernels.cu: the light-space tables of rh_scene_create, built on the device (return a cudaError_t)
+int preload_setup_kernels();
 int device_light_map(const double L[3], const rh_tri* d_tris, const uint32_t* d_slots, size_t n, int R, float* d_out, double min_empty,
                      unsigned long long* d_words, int* useful, double* empty_fraction, void* stream);
 int device_lit_flags(const rh_tri* d_tris, const WideNode32* d_nodes, const double center[3], uint32_t root, const uint32_t* d_slots,

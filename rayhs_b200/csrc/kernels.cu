@@ -418,8 +418,8 @@ struct Closest {
     return mine.y > held.y || (mine.y == held.y && mine.x < held.x);
   }
   __device__ __forceinline__ bool offer(const Ray&, double tt, double uu, double vv, uint32_t s, double& bound) {
-    // (cur_obj < obj only happens when objects are not visited in scene order — intersect_kernel tests the planes and
-    // spheres before the meshes: the first object of the scene list wins a tie, RayHs.hs:67-71)
+    // (cur_obj < obj only happens when objects are not visited in scene order — the sphere tree is walked after the
+    // linear list: the first object of the scene list wins a tie, RayHs.hs:67-71)
     if (tt < t || (tt == t && (cur_obj < obj || (obj == cur_obj && wins_tie(s))))) {
       t = tt;
       u = uu;
@@ -916,8 +916,10 @@ struct SlabWriter {
 // one reserved with ONE atomic on the queue's slab counter — one global atomic per kSlab entries instead of one per
 // push.  The slab a push completes gets its fill count here; the last, partly filled one at slab_close.  Returns
 // kEmpty for an entry that does not fit the queue (overflow is flagged; the host re-renders with larger queues).
+// `live_from`: the queue is a ring of capacity / kSlab slabs addressed by a running counter; the slabs from `live_from` on
+// are still in use (0 and a counter that starts at 0 for a queue that is simply filled once).
 __device__ __forceinline__ uint32_t slab_reserve(SlabWriter& w, unsigned m, uint32_t lane, uint32_t* slab_counter, uint32_t* fill,
-                                                 uint32_t capacity, uint32_t* overflow) {
+                                                 uint32_t capacity, uint32_t* overflow, uint32_t live_from = 0) {
   // `w` lives in the warp's shared memory: every lane reads it, then lane 0 writes the new state
   const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane) - 1));
   __syncwarp();  // lane 0's update of the previous push is visible
@@ -937,7 +939,8 @@ __device__ __forceinline__ uint32_t slab_reserve(SlabWriter& w, unsigned m, uint
     ns = atomicAdd(slab_counter, 1u);
   }
   ns = __shfl_sync(kFull, ns, 0);
-  const bool full = ns >= capacity / kSlab;
+  const bool full = ns - live_from >= capacity / kSlab;
+  ns %= capacity / kSlab;
   if (lane == 0) {
     if (full) *overflow = 1;
     w.base = full ? kEmpty : ns * kSlab;
@@ -1024,10 +1027,10 @@ struct ShadowTask {
 };
 
 __device__ __forceinline__ void push_shadow(bool has, const ShadowTask& t, const ShadowQueue& q, SlabWriter& sw,
-                                            uint32_t* slab_counter, uint32_t* overflow, uint32_t lane) {
+                                            uint32_t* slab_counter, uint32_t* overflow, uint32_t lane, uint32_t live_from = 0) {
   const unsigned m = __ballot_sync(kFull, has);
   if (!m) return;
-  const uint32_t idx = slab_reserve(sw, m, lane, slab_counter, q.fill, q.capacity, overflow);
+  const uint32_t idx = slab_reserve(sw, m, lane, slab_counter, q.fill, q.capacity, overflow, live_from);
   if (has && idx != kEmpty) {
     const size_t cap = q.capacity;
     q.plane[idx] = make_double2(t.p.x, t.p.y);
@@ -1520,6 +1523,9 @@ __global__ void __launch_bounds__(kTraceBlock, kTracePerSm) trace_kernel(const _
   const bool primary = (P.pass == 0);
   ChunkCtl* ctl = P.ctl;
   const uint32_t n_slabs = primary ? (P.n_samples + kSlab - 1) / kSlab : min(ctl->ray_slabs[P.pass], P.q_in.capacity / kSlab);
+  // the hit queue is a ring: the slabs of pass `hit_live_pass` (this pass, or the one before it when that pass's hits may
+  // still be under classification on the other stream) and later are in use
+  const uint32_t hit_live_from = ctl->hit_start[P.hit_live_pass];
   uint32_t n_reflect = 0, n_probe = 0, n_exit = 0, n_shaded = 0;  // (per thread: far below 2^32)
   TraceWarpSmem& wsm = reinterpret_cast<TraceWarpSmem*>(rh_smem + sizeof(SmemTables) + (size_t)kShortStack * kTraceBlock * sizeof(uint2))[threadIdx.x >> 5];
   SlabWriter& out_rays = wsm.out_rays;  // warp-uniform state, kept out of the register file
@@ -1722,7 +1728,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTracePerSm) trace_kernel(const _
           task.walk = kHitDirect;
           task.settled = 0;
         }
-        push_shadow(lit_surface || direct, task, P.q_hits, out_shadow, &ctl->hit_slab_next, &ctl->overflow, lane);
+        push_shadow(lit_surface || direct, task, P.q_hits, out_shadow, &ctl->hit_slab_next, &ctl->overflow, lane, hit_live_from);
       }
     }
   }
@@ -1771,8 +1777,8 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
   Cnt<COUNT> cnt;
   cnt.zero();
   ChunkCtl* ctl = P.ctl;
-  const uint32_t slab0 = min(ctl->hit_start[P.pass], P.q_hits.capacity / kSlab);  // this pass's slabs of the hit queue
-  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1], P.q_hits.capacity / kSlab) - slab0;
+  const uint32_t ring_slabs = P.q_hits.capacity / kSlab, slab0 = ctl->hit_start[P.pass];  // this pass's slabs of the hit queue (a ring)
+  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1] - slab0, ring_slabs);
   const size_t cap = P.q_hits.capacity;
   const double2* qp = P.q_hits.plane;
   uint32_t n_culled = 0, n_walk_pairs = 0;
@@ -1785,7 +1791,7 @@ __global__ void __launch_bounds__(kClassifyBlock, RH_CLASSIFY_MINB) classify_ker
     for (uint32_t u = claim.x; u < claim_end;) {
       uint32_t slab, b, piece_n;
       next_piece(u, claim_end, slab, b, piece_n);
-      slab += slab0;
+      slab = (slab + slab0) % ring_slabs;
       const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
       if (b >= n_here) continue;
       const uint32_t item = slab * kSlab + b + lane;
@@ -2219,8 +2225,8 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
   cnt.zero();
   const uint32_t lane = threadIdx.x & 31;
   ChunkCtl* ctl = P.ctl;
-  const uint32_t slab0 = min(ctl->hit_start[P.pass], P.q_hits.capacity / kSlab);  // this pass's slabs of the hit queue
-  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1], P.q_hits.capacity / kSlab) - slab0;
+  const uint32_t ring_slabs = P.q_hits.capacity / kSlab, slab0 = ctl->hit_start[P.pass];  // this pass's slabs of the hit queue (a ring)
+  const uint32_t n_slabs = min(ctl->hit_start[P.pass + 1] - slab0, ring_slabs);
   const size_t cap = P.q_hits.capacity;
   unsigned long long n_culled = 0;
   for (;;) {
@@ -2228,7 +2234,7 @@ __global__ void __launch_bounds__(kShadowBlock, 1) shadow_simple_kernel(const __
     if (lane == 0) slab = atomicAdd(&ctl->hit_cursor[P.pass], 1u);
     slab = __shfl_sync(kFull, slab, 0);
     if (slab >= n_slabs) break;
-    slab += slab0;
+    slab = (slab + slab0) % ring_slabs;
     const uint32_t n_here = min(__ldg(P.q_hits.fill + slab), kSlab);
     for (uint32_t j = lane; j < n_here; j += 32) {
       const uint32_t item = slab * kSlab + j;
@@ -2475,11 +2481,12 @@ void launch_trace(const SceneView& S, const CameraParams& cam, const ChunkParams
   else trace_kernel<false><<<grid * kTracePerSm, kTraceBlock, kTraceSmem, st>>>(S, cam, P);
   close_hit_range_kernel<<<1, 1, 0, st>>>(P.ctl, P.pass);
 }
-int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream) {
+int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool refill, int grid, void* stream, void* classified) {
   cudaStream_t st = (cudaStream_t)stream;
   if (S.n_lights > (uint32_t)kMaskLights) {
     if (count) shadow_simple_kernel<true><<<grid, kShadowBlock, kSimpleSmem, st>>>(S, P);
     else shadow_simple_kernel<false><<<grid, kShadowBlock, kSimpleSmem, st>>>(S, P);
+    if (classified) cudaEventRecord((cudaEvent_t)classified, st);
     return 1;
   }
   // FAST: the occluder tables are the staged shared-memory ones (SceneView::shadow_fast)
@@ -2490,6 +2497,7 @@ int launch_shadow(const SceneView& S, const ChunkParams& P, bool count, bool ref
     if (count) classify_kernel<true, false><<<g_classify_grid[1], kClassifyBlock, kClassifySmem, st>>>(S, P);
     else classify_kernel<false, false><<<g_classify_grid[0], kClassifyBlock, kClassifySmem, st>>>(S, P);
   }
+  if (classified) cudaEventRecord((cudaEvent_t)classified, st);  // the pass's slabs of the hit queue are free again
   if (refill) {
     if (count) shadow_refill_kernel<true><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);
     else shadow_refill_kernel<false><<<grid, kWalkBlock, kWalkSmem, st>>>(S, P);

@@ -85,7 +85,7 @@ struct Device {
   // Per lane: the stream of the shadow kernels (classify + walks) when a chunk's passes are pipelined — the trace kernel of
   // pass k + 1 runs beside the shadow kernels of pass k — with an event per pass (trace done) and one per chunk (shadows done)
   cudaStream_t shadow_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_trace[2][kMaxPasses + 2] = {}, ev_shadows[2] = {nullptr, nullptr};
+  cudaEvent_t ev_trace[2][kMaxPasses + 2] = {}, ev_classified[2][kMaxPasses + 2] = {}, ev_shadows[2] = {nullptr, nullptr};
   cudaEvent_t ev_lane = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_up, ev_done;  // one pair per slot of the offset upload ring
@@ -115,11 +115,13 @@ struct Device {
       RH_CUDA(cudaStreamCreateWithFlags(&shadow_stream[l], cudaStreamNonBlocking));
       RH_CUDA(cudaEventCreateWithFlags(&ev_shadows[l], cudaEventDisableTiming));
       for (cudaEvent_t& e : ev_trace[l]) RH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (cudaEvent_t& e : ev_classified[l]) RH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     RH_CUDA(cudaEventCreateWithFlags(&ev_lane, cudaEventDisableTiming));
     RH_CUDA(cudaEventCreate(&ev_begin));
     RH_CUDA(cudaEventCreate(&ev_end));
     RH_CUDA((cudaError_t)configure_kernels());
+    RH_CUDA((cudaError_t)preload_setup_kernels());
     max_threads = max_threads_per_launch(n_sms);
     RH_CUDA(cudaGetLastError());
     return RH_OK;
@@ -136,6 +138,10 @@ struct Device {
       if (ev_shadows[l]) cudaEventDestroy(ev_shadows[l]);
       ev_shadows[l] = nullptr;
       for (cudaEvent_t& e : ev_trace[l]) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+      }
+      for (cudaEvent_t& e : ev_classified[l]) {
         if (e) cudaEventDestroy(e);
         e = nullptr;
       }
@@ -189,6 +195,7 @@ struct rh_scene {
   // hide behind the kernels of the expensive ones instead of the other way round.
   mutable std::vector<int> cost_key;      // {W, H, spp, shards, shard, band height} the row costs belong to
   mutable std::vector<float> row_cost;    // kernel ms per local row (its chunk's time / its chunk's rows)
+  mutable uint32_t queue_factor = 2;          // the queue capacity factor the scene's last frame needed
   mutable bool stream_compute_bound = false;  // ... and in that frame the kernels, not the upload, finished last
 };
 
@@ -1483,7 +1490,9 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
   // (a lone warp walks a tree at ~1 us per node: the tail of a small launch is most of it) start the other stream's
   // next kernel.  All adds to the accumulators are made by the shadow stream in pass order: same bits as one stream.
   static const bool pipeline_on = !(getenv("RAYHS_B200_PIPELINE") && getenv("RAYHS_B200_PIPELINE")[0] == '0');  // (A/B switch)
-  const bool pipelined = pipeline_on && !profile && !counting && n_passes >= 2;
+  // (single-chunk frames only: a frame of several chunks has two of them in flight, which fills the same gaps, and a ring
+  // that holds two passes' hits at a time needs the queue capacity a triangle soup does not leave)
+  const bool pipelined = pipeline_on && !profile && !counting && n_passes >= 2 && n_chunks == 1;
   for (int l = 0; l < n_lanes; l++)
     if ((rc = D->lane[l].accum.reserve(chunk_samples * 3 * sizeof(double)))) return rc;
   if ((rc = D->ctl.reserve((size_t)n_chunks * sizeof(ChunkCtl)))) return rc;
@@ -1533,7 +1542,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
     }
   }
 
-  uint32_t factor = 2;  // queue capacity = factor * chunk samples; doubled when a chunk overflows
+  uint32_t factor = std::max(2u, scene->queue_factor);  // queue capacity = factor * chunk samples; doubled when a chunk overflows (and remembered)
   for (;;) {
     // Queue capacity in entries, a whole number of slabs: factor x the chunk's samples, plus one partly filled slab
     // per warp that can be producing (each warp leaves its last slab of a queue open).
@@ -1709,6 +1718,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
         cudaEvent_t a = nullptr;
         if (profile) a = prof_event();
         P.deep_stack = (uint2*)sc.deep.p;
+        P.hit_live_pass = (pipelined && pass > 0) ? pass - 1 : pass;
+        if (pipelined && pass >= 2) RH_CUDA(cudaStreamWaitEvent(lane_stream, D->ev_classified[ln][pass - 2], 0));  // its slabs are free
         launch_trace(scene->view, cam, P, counting, D->n_sms, lane_stream);
         if (profile) { cudaEvent_t b2 = prof_event(); spans.push_back({a, b2, 0}); a = b2; }
         if (pipelined) {
@@ -1716,7 +1727,8 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
           RH_CUDA(cudaStreamWaitEvent(shadow_stream, D->ev_trace[ln][pass], 0));
           P.deep_stack = (uint2*)sc.deep_shadow.p;
         }
-        const int n_shadow = launch_shadow(scene->view, P, counting, use_refill, D->n_sms, shadow_stream);
+        const int n_shadow = launch_shadow(scene->view, P, counting, use_refill, D->n_sms, shadow_stream,
+                                           pipelined ? (void*)D->ev_classified[ln][pass] : nullptr);
         if (profile) spans.push_back({a, prof_event(), 1});
         launches += 2 + n_shadow;  // (trace, the one-thread kernel that closes its hit range, classify, walk)
       }
@@ -1758,6 +1770,7 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       if (cap >= 0x7fffff00u || factor >= (1u << 16))
         return rh::set_error(RH_ERR_OVERFLOW, "rh_render: ray queue overflow; lower chunk_samples");
       factor *= 2;
+      scene->queue_factor = factor;
       continue;
     }
     if (stats) {

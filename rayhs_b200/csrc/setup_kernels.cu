@@ -131,6 +131,18 @@ __global__ void lit_count_kernel(const uint32_t* __restrict__ slots, uint32_t n_
 
 }  // namespace
 
+// rh_init: loads this file's kernels (CUDA loads a kernel's code on first use) so that rh_scene_create does not pay for it.
+int preload_setup_kernels() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, light_map_raster_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, fill_u32_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, count_empty_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lit_init_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lit_query_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, lit_count_kernel);
+  return (int)e;
+}
+
 // Device version of rh::build_light_map (light_maps.cpp) — same sequence of triangle batches, same early-outs.
 // words: two 8-byte device words of scratch.  *useful = 0 when the map would be useless or unsafe.
 int device_light_map(const double L[3], const rh_tri* d_tris, const uint32_t* d_slots, size_t n, int R, float* d_out,
