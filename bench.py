@@ -73,6 +73,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("RAYHS_BENCH_NO_SMI"):   # (diagnosis only: how much the polling itself costs)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -400,6 +402,9 @@ def main():
         return step_device_fused(**kw) if use_fused[0] else step_device_nccl(**kw)
 
     def step_e2e():
+        if G == 1 and not c5:
+            # the call a host makes: rh_render with host buffers in and out (pinned offsets in, RGB8 frame out)
+            return rh.render(job, spp=spp, offsets=off_host, out=rgb_host.numpy()).stats
         if G == 1:
             st = rh.render_device(job, rgb_dev, spp=spp, **host_kw)
             rgb_host.copy_(rgb_dev)
