@@ -201,16 +201,22 @@ def config_dict(wl, n_gpus, name):
 def run_reference(args, rank, world, wl, name):
     if rank != 0:
         return
-    import rayhs_b200 as rh
-
-    sc = make_scene(rh, wl)
     W, H, spp = wl["width"], wl["height"], wl["spp"]
+    if name == "c4":
+        # nothing of the product on this arm: the pack is read and the offset stream generated by oracle/packio.py
+        from oracle import packio
+
+        sc = packio.PackScene(os.path.join(ROOT, "tests", "golden", wl["pack"] + ".pack"))
+    else:
+        import rayhs_b200 as rh   # (the synthetic scene generator is the front end's: rh_make_synthetic)
+
+        sc = make_scene(rh, wl)
     cores = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     vals, sample = [], ""
     t0 = time.time()
     if name == "c4":
-        offsets = rh.sample_offsets(W * H, spp, wl["seed"])
+        offsets = packio.sample_offsets(W * H, spp, wl["seed"])
         for i in range(args.warmup + args.steps):
             v, sample, _, _ = c4_oracle_sample(sc, W, H, spp, offsets, per_step)
             if i >= args.warmup:

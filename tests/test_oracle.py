@@ -260,3 +260,24 @@ def test_oracle_row_subsets_and_threads_agree(cornell):
     part = o.render(sc.camera, 48, 48, 3, rows=(1, 48, 2), threads=4)
     assert np.array_equal(full["rgb_u8"][1::2], part["rgb_u8"][1::2])
     assert not part["rgb_u8"][0::2].any()
+
+
+def test_pack_reader_of_the_reference_arm_equals_the_front_end():
+    """oracle/packio.py (what `bench.py --impl reference` uses, so that the arm never maps the product library) reads a
+    scene pack into the same raw scene as the front end's rh_load_pack, and generates the same offset stream."""
+    import rayhs_b200 as rh
+    from oracle import packio
+    from oracle.orc import OracleScene
+
+    assert np.array_equal(packio.sample_offsets(777, 3, 24), rh.sample_offsets(777, 3, 24))
+    for name in ("cornellBox", "texture", "dragon_low"):
+        path = os.path.join(GOLDEN, name + ".pack")
+        a, b = packio.PackScene(path), rh.Scene.from_pack(path)
+        assert (a.width, a.height, a.max_depth) == (b.width, b.height, b.max_depth)
+        oa, ob = OracleScene(a.raw), OracleScene(b.raw)
+        ra = oa.render(a.camera, 40, 30, a.max_depth, want_ids=True)
+        rb = ob.render(b.camera, 40, 30, b.max_depth, want_ids=True)
+        assert np.array_equal(ra["rgb_u8"], rb["rgb_u8"]) and np.array_equal(ra["hit_ids"], rb["hit_ids"])
+        assert ra["rays_total"] == rb["rays_total"]
+        oa.close()
+        ob.close()
