@@ -497,6 +497,10 @@ def main():
     del dst_u8
     clocks = sampler.stop() if rank == 0 else None
     rays = total_rays(stats[-1])
+    culled = torch.tensor([float(stats[-1]["rays_shadow_culled"])], dtype=torch.float64, device="cuda")
+    if G > 1:
+        dist.all_reduce(culled, op=dist.ReduceOp.SUM)
+    culled_all = culled.item()   # (hit, light) pairs the reference queries and this path settles by l.n <= 0 alone
     value = rays / (ms_dev * 1e-3) / 1e6
     e2e_value = rays / (ms_e2e * 1e-3) / 1e6
 
@@ -657,6 +661,7 @@ def main():
                 "shadow_rays_note": "rays_shadow counts every shadowIntersection call of the reference (hits x lights); of those, "
                                     "rays_shadow_culled have l.n <= 0 (Lambert term exactly 0, no query needed) and shadow_walk_pairs "
                                     "had to walk a tree; the rest are settled by plane / sphere / root-box / light-map tests",
+                "value_without_culled_shadow_pairs": (rays - culled_all) / (ms_dev * 1e-3) / 1e6,
                 "shadow_walk_schedule": "per-lane refill" if shadow_refill else "pooled",
                 "per_rank_kernel_ms": per_rank_ms, "setup": setup, "cold_start": cold,
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
