@@ -427,6 +427,12 @@ int rh_light_map_build(const double light_pos[3], const rh_tri* tris, uint32_t n
  * is not grazing.  The shadow kernels skip the walk of a hit's own mesh for such a triangle.  Brute force here
  * (O(n^2)); the library walks the mesh's tree. */
 int rh_lit_triangles(int light_kind, const double light_pos[3], const rh_tri* tris, uint32_t n_tris, uint8_t* out);
+/* Host-only validation hook: the cull tree rh_scene_create builds over one mesh's triangles (binned SAH, at most 4
+ * triangles per leaf, several host threads), refitted to exact padded boxes.  order_out[n_tris]: new slot -> given
+ * triangle; nodes_out (room for 2 * n_tris records; leaves: left = first new slot, right = count; inner nodes: child
+ * indices) ; *n_nodes_out, *depth_out.  Needs no GPU. */
+int rh_cull_tree_build(const rh_tri* tris, uint32_t n_tris, uint32_t* order_out, rh_node* nodes_out, uint32_t* n_nodes_out,
+                       uint32_t* depth_out);
 
 #ifdef __cplusplus
 }

@@ -168,6 +168,7 @@ SIGNATURES = {
     "rh_light_map_build": (C.c_int, [C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, C.c_int, vp, C.POINTER(C.c_int),
                                      C.POINTER(C.c_double)]),
     "rh_lit_triangles": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(rh_tri), C.c_uint32, vp]),
+    "rh_cull_tree_build": (C.c_int, [C.POINTER(rh_tri), C.c_uint32, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
 _lib = None

@@ -2005,6 +2005,28 @@ int rh_scene_light_tables(const rh_scene* scene, uint32_t* info4, float* maps_ou
   return RH_OK;
 }
 
+int rh_cull_tree_build(const rh_tri* tris, uint32_t n_tris, uint32_t* order_out, rh_node* nodes_out, uint32_t* n_nodes_out,
+                       uint32_t* depth_out) {
+  if ((!tris && n_tris) || !order_out || !nodes_out || !n_nodes_out) return rh::set_error(RH_ERR_ARG, "rh_cull_tree_build: null argument");
+  try {
+    SahTree sah(tris);
+    std::vector<uint32_t> slots(n_tris);
+    for (uint32_t i = 0; i < n_tris; i++) slots[i] = i;
+    sah.run(slots);
+    TriVec permuted(sah.order.size());
+    for (size_t k = 0; k < sah.order.size(); k++) permuted[k] = tris[sah.order[k]];
+    sah.refit(permuted);
+    if (sah.nodes.size() > 2 * (size_t)n_tris + 1) return rh::set_error(RH_ERR_STATE, "rh_cull_tree_build: more nodes than a binary tree has");
+    memcpy(order_out, sah.order.data(), sah.order.size() * sizeof(uint32_t));
+    memcpy(nodes_out, sah.nodes.data(), sah.nodes.size() * sizeof(rh_node));
+    *n_nodes_out = (uint32_t)sah.nodes.size();
+    if (depth_out) *depth_out = sah.max_depth;
+  } catch (const std::bad_alloc&) {
+    return rh::set_error(RH_ERR_OOM, "rh_cull_tree_build: out of host memory");
+  }
+  return RH_OK;
+}
+
 int rh_scene_record_bytes(const rh_scene* scene, uint64_t* bytes5) {
   if (!scene || !bytes5) return rh::set_error(RH_ERR_ARG, "rh_scene_record_bytes: null argument");
   bytes5[0] = scene->wide32.bytes;

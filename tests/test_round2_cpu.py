@@ -3,6 +3,7 @@ parallel reference-rule tree build."""
 import ctypes as C
 
 import numpy as np
+import pytest
 
 import rayhs_b200 as rh
 from rayhs_b200 import capi
@@ -60,3 +61,58 @@ def test_parallel_tree_build_equals_the_oracles_own_build():
     assert int(counts.max()) == st["max_leaf"]
     # the image of a few rows agrees with the oracle (its own tree): the splice kept every index consistent
     o.close()
+
+
+def _random_tris(n, seed=5):
+    rng = np.random.default_rng(seed)
+    tris = (capi.rh_tri * n)()
+    a = np.frombuffer(tris, dtype=np.uint8).reshape(n, C.sizeof(capi.rh_tri))
+    d = np.frombuffer(tris, dtype=np.float64).reshape(n, C.sizeof(capi.rh_tri) // 8)
+    d[:, 0:3] = rng.uniform(-10, 10, (n, 3))          # p0
+    d[:, 3:9] = rng.normal(0, 0.05, (n, 6))           # e1, e2
+    ids = np.frombuffer(tris, dtype=np.uint32).reshape(n, C.sizeof(capi.rh_tri) // 4)
+    ids[:, 18] = np.arange(n, dtype=np.uint32)        # tri_id
+    del a
+    return tris, d
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 1000, 1 << 20])
+def test_cull_tree_of_the_set_up_path(n):
+    """rh_cull_tree_build = the binned-SAH tree rh_scene_create builds for the float path (several host threads; the
+    ranges of 2^20 triangles and more are binned in pieces): every triangle in exactly one leaf of at most 4, every node's
+    box holds its triangles / children, and the build does not depend on how the threads interleave."""
+    L = capi.lib()
+    tris, d = _random_tris(n)
+    order = np.empty(n, dtype=np.uint32)
+    nodes = (capi.rh_node * (2 * n + 1))()
+    n_nodes, depth = C.c_uint32(), C.c_uint32()
+    capi.check(L.rh_cull_tree_build(tris, n, order.ctypes.data, C.cast(nodes, C.c_void_p), C.byref(n_nodes), C.byref(depth)))
+    assert sorted(order.tolist()) == list(range(n)) if n <= 1000 else np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    nn = n_nodes.value
+    nd = np.frombuffer(nodes, dtype=np.uint8)[: nn * C.sizeof(capi.rh_node)].reshape(nn, C.sizeof(capi.rh_node))
+    box = nd[:, :48].copy().view(np.float64).reshape(nn, 6)
+    words = nd[:, 48:64].copy().view(np.uint32).reshape(nn, 4)      # left, right, leaf_index, is_leaf
+    leaf = words[:, 3] != 0
+    assert words[leaf, 1].max() <= 4 and words[leaf, 1].min() >= 1
+    assert int(words[leaf, 1].sum()) == n                            # the leaves partition the slots ...
+    firsts = np.sort(words[leaf, 0])
+    assert firsts[0] == 0 and np.all(np.diff(firsts) >= 1)           # ... with distinct first slots
+    # triangle boxes in new slot order
+    p0, e1, e2 = d[order, 0:3], d[order, 3:6], d[order, 6:9]
+    lo = np.minimum(p0, np.minimum(p0 + e1, p0 + e2))
+    hi = np.maximum(p0, np.maximum(p0 + e1, p0 + e2))
+    for i in np.flatnonzero(leaf)[:: max(1, int(leaf.sum()) // 2000)]:   # a sample of the leaves
+        f, c = int(words[i, 0]), int(words[i, 1])
+        assert np.all(box[i, :3] <= lo[f:f + c].min(axis=0)) and np.all(box[i, 3:] >= hi[f:f + c].max(axis=0))
+    inner = np.flatnonzero(~leaf)
+    if len(inner):
+        l, r = words[inner, 0], words[inner, 1]
+        assert np.all(l > inner) and np.all(r > inner) and r.max() < nn   # children follow their parent
+        assert np.all(box[inner, :3] <= np.minimum(box[l, :3], box[r, :3])) and np.all(box[inner, 3:] >= np.maximum(box[l, 3:], box[r, 3:]))
+    assert depth.value <= 64
+    if n >= 1000:   # a second build gives the same tree
+        order2 = np.empty(n, dtype=np.uint32)
+        nodes2 = (capi.rh_node * (2 * n + 1))()
+        capi.check(L.rh_cull_tree_build(tris, n, order2.ctypes.data, C.cast(nodes2, C.c_void_p), C.byref(n_nodes), C.byref(depth)))
+        assert n_nodes.value == nn and np.array_equal(order, order2)
+        assert bytes(nodes2)[: nn * C.sizeof(capi.rh_node)] == nd.tobytes()
