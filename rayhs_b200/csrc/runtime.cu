@@ -1434,28 +1434,28 @@ int render_on(Device* D, const rh_scene* scene, const rh_camera* camera, const r
       }
       ramped = true;
     } else {
-    int row = 0;
-    while (row < rows_local) {
-      const size_t w = plan.empty() ? first : want;
-      const int n = (int)std::max<size_t>(1, std::min<size_t>(w / row_samples, (size_t)(rows_local - row)));
-      plan.push_back(n);
-      row += n;
-    }
-    // Streamed offsets: the frame ends with the kernels of the chunk whose upload finishes last, so the frame's last
-    // chunk is cut into halves of halves (down to ~1 Mi samples): what is left to do after the last byte has arrived is
-    // a small chunk's work.
-    if (tail_shaping && host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
-      int last = plan.back();
-      plan.pop_back();
-      const int min_rows = (int)std::max<size_t>(1, ((size_t)1 << 20) / row_samples);
-      while (last > 2 * min_rows && n_tail < 4) {
-        plan.push_back(last - last / 2);
-        last /= 2;
+      int row = 0;
+      while (row < rows_local) {
+        const size_t w = plan.empty() ? first : want;
+        const int n = (int)std::max<size_t>(1, std::min<size_t>(w / row_samples, (size_t)(rows_local - row)));
+        plan.push_back(n);
+        row += n;
+      }
+      // Streamed offsets: the frame ends with the kernels of the chunk whose upload finishes last, so the frame's last
+      // chunk is cut into halves of halves (down to ~1 Mi samples): what is left to do after the last byte has arrived is
+      // a small chunk's work.
+      if (tail_shaping && host_offsets && o->chunk_samples <= 0 && plan.size() >= 4) {
+        int last = plan.back();
+        plan.pop_back();
+        const int min_rows = (int)std::max<size_t>(1, ((size_t)1 << 20) / row_samples);
+        while (last > 2 * min_rows && n_tail < 4) {
+          plan.push_back(last - last / 2);
+          last /= 2;
+          n_tail++;
+        }
+        plan.push_back(last);
         n_tail++;
       }
-      plan.push_back(last);
-      n_tail++;
-    }
     }
   }
   const int n_chunks = (int)plan.size();
